@@ -1,0 +1,164 @@
+/*
+ * vpca.h -- C ABI of libvpca.so: the B200-native VariantsPca hot path
+ *           (genotype encode -> N x N similarity/Gram accumulation -> centering + top-k eigenvectors).
+ *
+ * Drop-in boundary.  The reference (googlegenomics/spark-examples) has no FFI; the boundary is the
+ * public method set of `class VariantsPcaDriver` as used by `main`
+ * (src/main/scala/com/google/cloud/genomics/spark/examples/VariantsPca.scala:38-50).  Each entry
+ * point below names the reference lines whose work it replaces; INTEGRATION.md shows the JNI class
+ * (`NativePca`) and the Scala changes a maintainer would add to bind them.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every pointer is either HOST memory owned by the caller or a raw
+ *     CUDA device pointer where the parameter name starts with `d_`.
+ *   - every function returns VPCA_OK (0) or a negative vpca_status; vpca_last_error() gives the text.
+ *     No C++ exception crosses the ABI.
+ *   - a vpca_ctx owns one GPU's worth of state (device buffers, streams, staging).  Calls on one ctx
+ *     are serialised internally, so Spark task threads may call accumulate/commit concurrently.
+ *   - all device work is ordered on the stream given in vpca_config.stream (or a private stream);
+ *     functions that return host data synchronise that stream before returning.
+ *   - there is no CPU fallback: vpca_create fails with VPCA_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef VPCA_H_
+#define VPCA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPCA_VERSION_MAJOR 0
+#define VPCA_VERSION_MINOR 1
+
+typedef enum vpca_status {
+    VPCA_OK = 0,
+    VPCA_ERR_BAD_ARG = -1,
+    VPCA_ERR_INDEX_OUT_OF_RANGE = -2, /* sample index outside [0, n_samples): the reference would throw
+                                         (VariantsPca.scala:59 NoSuchElementException / :188 Breeze bounds) */
+    VPCA_ERR_CUDA = -3,
+    VPCA_ERR_NCCL = -4,     /* reserved: collectives are driven by the host */
+    VPCA_ERR_OVERFLOW = -5, /* an int32 similarity count (VariantsPca.scala:185) could exceed 2^31-1,
+                               or a multiplicity does not fit the encoding */
+    VPCA_ERR_STATE = -6,
+    VPCA_ERR_NOMEM = -7,
+    VPCA_ERR_UNSUPPORTED = -8
+} vpca_status;
+
+typedef enum vpca_dtype {
+    VPCA_DTYPE_I8 = 0,  /* int8 genotype encoding, tcgen05 kind::i8, exact int32 accumulation   */
+    VPCA_DTYPE_BF16 = 1 /* bf16 genotype encoding, tcgen05 kind::f16, fp32 TMEM accumulation flushed
+                           into the int32 Gram before 2^24 could be reached (exact)              */
+} vpca_dtype;
+
+typedef struct vpca_ctx vpca_ctx;
+
+typedef struct vpca_config {
+    uint32_t struct_size;      /* sizeof(vpca_config), for forward compatibility                     */
+    int32_t n_samples;         /* N = common.indexes.size (VariantsPca.scala:183,199)                 */
+    int32_t device;            /* CUDA device ordinal                                                  */
+    int32_t dtype;             /* vpca_dtype                                                           */
+    int32_t num_pc;            /* PcaConf.numPc (GenomicsConf.scala:85); default 2 when 0             */
+    int32_t max_multiplicity;  /* largest value a genotype cell may take (1 = binary carriers, the
+                                  reference rule VariantsPca.scala:58; 2 = dosage / a sample listed
+                                  twice).  0 -> 2.  Used for the overflow guards.                     */
+    int32_t partitions_in_flight; /* staging Grams for uncommitted partitions; 0 -> 4                 */
+    int32_t reserved0;
+    int64_t chunk_variants;    /* variants per device staging chunk for CSR input; 0 -> automatic     */
+    int64_t chunk_nnz;         /* sample-index entries per device staging chunk; 0 -> automatic       */
+    void* stream;              /* cudaStream_t to order all work on; NULL -> private stream           */
+    void* d_gram;              /* optional caller-owned device buffer of n_samples^2 int32 (e.g. the
+                                  tensor the host all-reduces with NCCL); NULL -> library-owned       */
+} vpca_config;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int vpca_version(void);                                  /* major * 1000 + minor */
+int vpca_create(const vpca_config* cfg, vpca_ctx** out); /* replaces `new VariantsPcaDriver(conf)` state
+                                                            that lives on the executor side
+                                                            (VariantsPca.scala:81-85, :185)             */
+int vpca_destroy(vpca_ctx* ctx);
+/* Last error text of `ctx` (or of the calling thread when ctx == NULL).  Never NULL. */
+const char* vpca_last_error(const vpca_ctx* ctx);
+/* Zero the Gram and forget all partitions: start a new analysis on the same ctx. */
+int vpca_reset(vpca_ctx* ctx);
+
+/* ---- encode (VariantsPca.scala:56-60 extractCallInfo, :153-168 getCallsRdd) ---------------------
+ * Host-side records arrive already projected to `RDD[Seq[Int]]` rows (CSR: row v = the sample indices
+ * with hasVariation at variant v, duplicates allowed, any order; offsets has nv+1 entries).
+ * vpca_encode_calls runs ONLY the device encode (CSR -> dense sample-major tile) and copies the tile
+ * back: out[s * ld + v] = multiplicity of sample s in row v.  It exists so the encode kernel can be
+ * parity-checked on its own; accumulate_calls below fuses it with the Gram.
+ * Element type of `out` follows cfg.dtype (int8_t or bf16 bits as uint16_t); ld in elements, >= nv. */
+int vpca_encode_calls(vpca_ctx* ctx, const int64_t* offsets, const int32_t* sample_idx, int64_t nv, void* out,
+                      int64_t ld);
+
+/* ---- similarity / Gram accumulation (VariantsPca.scala:182-191 getSimilarityMatrix) --------------
+ * vpca_accumulate_calls = the body of `mapPartitions` (:184-189) for one batch of rows of Spark
+ * partition `partition_id`: encode on device + S_partition += X X^T on tcgen05 tensor cores.  May be
+ * called many times per partition.  Nothing is visible in the Gram until vpca_commit(partition_id)
+ * (task success); vpca_abort discards it (task failure / retry), so a retried task is counted exactly
+ * once -- the property the reference gets from returning a fresh matrix per task (:185).
+ * partition_id < 0 means "no staging": accumulate straight into the Gram (single-shot callers). */
+int vpca_accumulate_calls(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const int32_t* sample_idx,
+                          int64_t nv);
+int vpca_commit(vpca_ctx* ctx, int64_t partition_id);
+int vpca_abort(vpca_ctx* ctx, int64_t partition_id);
+
+/* Pre-encoded dense input, sample-major: x[s * ld + v], s in [0, n_samples), v in [0, nv); element
+ * type per cfg.dtype; ld (elements) must make rows 16-byte aligned.  on_device != 0: `x` is a device
+ * pointer and is consumed in place (no copy) -- the resident-in-HBM path of bench.py; otherwise it is
+ * host memory and is staged through the device in chunks.  Accumulates straight into the Gram. */
+int vpca_accumulate_dense(vpca_ctx* ctx, const void* x, int64_t nv, int64_t ld, int on_device);
+
+/* `reduceByKey(_ + _)` (:190) across GPUs is ONE all-reduce of the raw Gram buffer, driven by the host
+ * (torch.distributed / NCCL in this repo): all-reduce the n_samples^2 int32 at
+ * vpca_gram_device_ptr() between the last commit and vpca_finalize_gram().  Until finalize only the
+ * lower triangle (row >= col) of the buffer is meaningful. */
+int vpca_gram_device_ptr(vpca_ctx* ctx, void** d_gram);
+/* Mirror the lower triangle into the upper one: after this the buffer equals the reference's
+ * similarity matrix with all N^2 entries present (:189-190). */
+int vpca_finalize_gram(vpca_ctx* ctx);
+/* Copy the finalized Gram to host, row-major n_samples x n_samples int32 (the collected
+ * RDD[((Int, Int), Int)] in key order). */
+int vpca_get_gram(vpca_ctx* ctx, int32_t* out);
+/* Load a Gram (checkpoint restore / tests); marks it finalized. */
+int vpca_set_gram(vpca_ctx* ctx, const int32_t* gram);
+
+/* ---- computePca (VariantsPca.scala:198-231) --------------------------------------------------------
+ * Centering (:199-223) in FP64 with the reference's operation order, then the top-k eigenvectors of the
+ * centered matrix (= the first k columns of U that MLlib's RowMatrix.computePrincipalComponents returns
+ * at :226) by Householder tridiagonalisation + Sturm bisection + inverse iteration on the GPU.
+ *   vecs : n_samples x k, column-major -- the layout of `pca.toArray` (:227); vecs[i + c*n] is PC c of
+ *          sample i.  Each column is unit-norm and sign-normalised (largest-|.| entry positive).
+ *   evals: k eigenvalues of the centered matrix, descending (may be NULL).
+ *   non_zero_rows: `rowSums.filter(_ > 0).size` (:207), may be NULL. */
+int vpca_compute_pca(vpca_ctx* ctx, int32_t k, double* vecs, double* evals, int32_t* non_zero_rows);
+/* The centered matrix itself (row-major N x N doubles) for parity tests of :199-223. */
+int vpca_get_centered(vpca_ctx* ctx, double* out);
+/* Tridiagonal form of the centered matrix after the last vpca_compute_pca (diag: n, offdiag: n-1). */
+int vpca_get_tridiagonal(vpca_ctx* ctx, double* diag, double* offdiag);
+
+/* ---- synthetic cohort (stands in for the retired Genomics API ingestion, rdd/VariantsRDD.scala:187-236;
+ *      specification in DESIGN.md "Synthetic generator") --------------------------------------------------
+ * Fill a dense sample-major device tile d_x[s * ld + (v - v0)] for variants [v0, v0+nv).
+ * mode 0: binary carrier x = (dosage > 0) (reference encode rule); mode 1: dosage 0/1/2. */
+int vpca_synth_dense_device(vpca_ctx* ctx, uint64_t seed, int64_t v0, int64_t nv, int mode, void* d_x, int64_t ld);
+
+/* ---- introspection ---------------------------------------------------------------------------------- */
+typedef struct vpca_stats {
+    int64_t variants_accumulated; /* rows folded into the Gram or into staged partitions                  */
+    int64_t gram_launches;        /* tcgen05 Gram kernel launches                                         */
+    int64_t kernel_launches;      /* all kernels launched by this ctx                                     */
+    int64_t h2d_bytes;            /* bytes copied host -> device by accumulate_* / encode / set_gram      */
+    int64_t d2h_bytes;            /* bytes copied device -> host by get_* / compute_pca                   */
+    float last_gram_ms;           /* device time of the most recent Gram launch (CUDA events)             */
+    float last_eig_ms;            /* device time of the most recent centering + eigensolve                */
+    int32_t gram_cta_group;       /* 1 or 2: tcgen05 cta_group used                                       */
+    int32_t gram_resident;        /* 1 when the last launch kept accumulators in TMEM for the whole K loop */
+} vpca_stats;
+int vpca_get_stats(vpca_ctx* ctx, vpca_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPCA_H_ */

@@ -1,0 +1,533 @@
+// Centering + symmetric eigensolve (top-k) in FP64 on the device.
+//
+// Replaces VariantsPcaDriver.computePca (reference:
+//   src/main/scala/com/google/cloud/genomics/spark/examples/VariantsPca.scala:198-231):
+//   :199-223  row sums, matrixMean = sum / N / N, C(i,j) = S(i,j) - rowMean(i) - colMean(j) + matrixMean
+//   :224-227  RowMatrix(rows).computePrincipalComponents(numPc): spark-mllib 1.6.1 forms Cov = C^T C/(m-1) - ... and
+//             takes the first k left singular vectors of Cov (LAPACK dgesdd).  C = J S J is symmetric PSD, so those
+//             are the eigenvectors of C for its k largest eigenvalues; we compute them from C directly:
+//               1. Householder tridiagonalisation  C = Q T Q^T           (N steps, 2 kernels per step)
+//               2. k largest eigenvalues of T by Sturm-count multisection (parallel over shifts)
+//               3. eigenvectors of T by inverse iteration               (tridiagonal LU with partial pivoting)
+//               4. back-transformation  z = Q y  with the stored reflectors, normalise, fix the sign.
+// Everything is HBM/L2-latency bound FP64 vector work (the 50 MB matrix at N = 2504 lives in L2): rows are
+// contiguous so every pass is coalesced; one warp owns one row in the trailing update.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#include "vpca_internal.h"
+
+namespace vpca {
+namespace {
+
+constexpr int kSmallThreads = 1024;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the block; result valid in every thread.  `red` has >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();   // protect `red` from the previous use
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double t = (lane < nw) ? red[lane] : 0.0;
+    t = warp_sum(t);
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------ centering
+__global__ void rowsum_kernel(const int32_t* __restrict__ S, int n, double* __restrict__ rowsum) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const int32_t* r = S + (size_t)row * n;
+    long long acc = 0;
+    for (int j = lane; j < n; j += 32) acc += r[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    // integer-valued and < 2^53: identical to the reference's foldLeft(0D)(_ + _) at :206
+    if (lane == 0) rowsum[row] = (double)acc;
+}
+
+// scal[0] = matrixMean (:211), nz = rowSums.filter(_ > 0).size (:207)
+__global__ void matrix_mean_kernel(const double* __restrict__ rowsum, int n, double* __restrict__ scal,
+                                   int* __restrict__ nz) {
+    __shared__ double red[33];
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    double acc = 0.0;
+    int c = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double r = rowsum[i];
+        acc += r;   // exact: integer-valued partial sums below 2^53, so the order of `reduce(_ + _)` (:210) is immaterial
+        c += (r > 0.0);
+    }
+    const double tot = block_sum(acc, red);
+    atomicAdd(&cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double rc = (double)n;
+        scal[0] = __ddiv_rn(__ddiv_rn(tot, rc), rc);
+        *nz = cnt;
+    }
+}
+
+__global__ void center_kernel(const int32_t* __restrict__ S, const double* __restrict__ rowsum,
+                              const double* __restrict__ scal, int n, double* __restrict__ C) {
+    const int row = blockIdx.y;
+    const double rc = (double)n;
+    const double row_mean = __ddiv_rn(rowsum[row], rc);
+    const double mm = scal[0];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const double col_mean = __ddiv_rn(rowsum[j], rc);
+        const double data = (double)S[(size_t)row * n + j];
+        // data - rowMean - colMean + matrixMean, left to right (:221)
+        C[(size_t)row * n + j] = __dadd_rn(__dsub_rn(__dsub_rn(data, row_mean), col_mean), mm);
+    }
+}
+
+// ---------------------------------------------------------------------------- tridiagonalisation
+// Step j (0 <= j <= n-1), single block:
+//   (a) finish the previous step: w = p - (tau_prev/2)(p.v_prev) v_prev          on indices [j, n)
+//   (b) apply the pending rank-2 update to row j:  A[j][t] -= v_prev[j] w[t] + w[j] v_prev[t],  t in [j, n)
+//   (c) d[j] = A[j][j];  build the reflector that annihilates A[j][j+2..n):  v (v[j+1] = 1), tau, e[j] = beta;
+//       the reflector is kept in row j of A (for the back-transformation) and in `vcur`.
+// vprev/vcur/w/p are length-n vectors; scal[1] = tau_prev on entry, tau_j on exit.
+__global__ void __launch_bounds__(kSmallThreads) tridiag_small_kernel(double* __restrict__ A, int n, int j,
+                                                                       const double* __restrict__ vprev,
+                                                                       double* __restrict__ vcur,
+                                                                       const double* __restrict__ p,
+                                                                       double* __restrict__ w, double* __restrict__ diag,
+                                                                       double* __restrict__ off, double* __restrict__ tau,
+                                                                       double* __restrict__ scal) {
+    __shared__ double red[33];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* rowj = A + (size_t)j * n;
+    if (j > 0) {
+        const double tau_prev = tau[j - 1];
+        double acc = 0.0;
+        for (int t = j + tid; t < n; t += nt) acc += p[t] * vprev[t];
+        const double pv = block_sum(acc, red);
+        const double alpha = 0.5 * tau_prev * pv;
+        for (int t = j + tid; t < n; t += nt) w[t] = p[t] - alpha * vprev[t];
+        __syncthreads();
+        const double vj = vprev[j], wj = w[j];
+        for (int t = j + tid; t < n; t += nt) rowj[t] -= vj * w[t] + wj * vprev[t];
+        __syncthreads();
+    }
+    if (tid == 0) diag[j] = rowj[j];
+    if (j >= n - 1) return;
+    // reflector from x = rowj[j+1 .. n)
+    const double alpha = rowj[j + 1];
+    double acc = 0.0;
+    for (int t = j + 2 + tid; t < n; t += nt) {
+        const double x = rowj[t];
+        acc += x * x;
+    }
+    const double xnorm2 = block_sum(acc, red);
+    double beta, tj, scale;
+    if (xnorm2 == 0.0) {
+        beta = alpha;
+        tj = 0.0;
+        scale = 0.0;
+    } else {
+        beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+        tj = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+    }
+    for (int t = j + 1 + tid; t < n; t += nt) {
+        const double v = (t == j + 1) ? 1.0 : rowj[t] * scale;
+        vcur[t] = v;
+        rowj[t] = v;
+    }
+    if (tid == 0) {
+        off[j] = beta;
+        tau[j] = tj;
+        scal[1] = tj;
+    }
+}
+
+// Step j, grid-wide: for every trailing row i in [j+1, n) (one warp per row)
+//   A[i][t] -= vprev[i] w[t] + w[i] vprev[t]      (pending rank-2 update of step j-1),  t in [j+1, n)
+//   p[i]     = tau_j * sum_t A[i][t] vcur[t]      (symmetric matrix-vector product of step j, full rows)
+__global__ void __launch_bounds__(256) tridiag_big_kernel(double* __restrict__ A, int n, int j,
+                                                          const double* __restrict__ vprev,
+                                                          const double* __restrict__ w,
+                                                          const double* __restrict__ vcur, const double* __restrict__ tau,
+                                                          double* __restrict__ p) {
+    const int lane = threadIdx.x & 31;
+    const int i = j + 1 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const double tj = tau[j];
+    double* row = A + (size_t)i * n;
+    const double vi = vprev[i], wi = w[i];
+    double acc = 0.0;
+    if (j > 0) {
+        for (int t = j + 1 + lane; t < n; t += 32) {
+            const double a = row[t] - (vi * w[t] + wi * vprev[t]);
+            row[t] = a;
+            acc += a * vcur[t];
+        }
+    } else {
+        for (int t = j + 1 + lane; t < n; t += 32) acc += row[t] * vcur[t];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) p[i] = tj * acc;
+}
+
+// ------------------------------------------------------------------------- eigenvalues of T (bisection)
+// Number of eigenvalues of T strictly below x (Sturm count with the LAPACK dlaebz pivmin safeguard).
+__device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2, int n,
+                                           double x, double pivmin) {
+    double q = d[0] - x;
+    if (fabs(q) < pivmin) q = -pivmin;
+    int cnt = q < 0.0;
+    for (int i = 1; i < n; ++i) {
+        q = d[i] - x - e2[i - 1] / q;
+        if (fabs(q) < pivmin) q = -pivmin;
+        cnt += q < 0.0;
+    }
+    return cnt;
+}
+
+// block b computes the (b+1)-th largest eigenvalue by multisection: every round each thread counts at one shift.
+__global__ void __launch_bounds__(256) bisect_kernel(const double* __restrict__ d, const double* __restrict__ e, int n,
+                                                     double* __restrict__ e2, double* __restrict__ evals,
+                                                     double* __restrict__ scal) {
+    __shared__ int sel;
+    __shared__ double sh_lo, sh_hi, sh_piv;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // Gershgorin interval, pivmin, squared off-diagonals (every block writes the same e2 values)
+    double gl = DBL_MAX, gu = -DBL_MAX, emax = 0.0;
+    for (int i = tid; i < n; i += nt) {
+        const double el = (i > 0) ? fabs(e[i - 1]) : 0.0, er = (i < n - 1) ? fabs(e[i]) : 0.0;
+        gl = fmin(gl, d[i] - el - er);
+        gu = fmax(gu, d[i] + el + er);
+        if (i < n - 1) {
+            e2[i] = e[i] * e[i];
+            emax = fmax(emax, e[i] * e[i]);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
+        gu = fmax(gu, __shfl_xor_sync(0xffffffffu, gu, o));
+        emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    }
+    __shared__ double rl[8], ru[8], rm[8];
+    if ((tid & 31) == 0) {
+        rl[tid >> 5] = gl;
+        ru[tid >> 5] = gu;
+        rm[tid >> 5] = emax;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a = rl[0], b = ru[0], m = rm[0];
+        for (int i = 1; i < (nt >> 5); ++i) {
+            a = fmin(a, rl[i]);
+            b = fmax(b, ru[i]);
+            m = fmax(m, rm[i]);
+        }
+        const double tnorm = fmax(fabs(a), fabs(b));
+        sh_piv = DBL_MIN * fmax(1.0, m);
+        sh_lo = a - 2.0 * tnorm * DBL_EPSILON * n - 2.0 * sh_piv;
+        sh_hi = b + 2.0 * tnorm * DBL_EPSILON * n + 2.0 * sh_piv;
+        if (blockIdx.x == 0) scal[2] = tnorm;
+    }
+    __syncthreads();
+    const double pivmin = sh_piv;
+    const int target = n - 1 - (int)blockIdx.x;   // ascending index of the wanted eigenvalue
+    double lo = sh_lo, hi = sh_hi;                // invariant: count(lo) <= target < count(hi)
+    for (int round = 0; round < 16; ++round) {
+        const double width = hi - lo;
+        if (width <= 2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) break;
+        const double x = lo + width * ((double)(tid + 1) / (double)(nt + 1));
+        const int c = sturm_count(d, e2, n, x, pivmin);
+        if (tid == 0) sel = nt;
+        __syncthreads();
+        if (c > target) atomicMin(&sel, tid);   // first shift with more than `target` eigenvalues below it
+        __syncthreads();
+        const int s = sel;
+        const double nlo = (s == 0) ? lo : lo + width * ((double)s / (double)(nt + 1));
+        const double nhi = (s == nt) ? hi : lo + width * ((double)(s + 1) / (double)(nt + 1));
+        __syncthreads();
+        lo = nlo;
+        hi = nhi;
+    }
+    if (tid == 0) evals[blockIdx.x] = 0.5 * (lo + hi);
+}
+
+// ------------------------------------------------------------- eigenvectors of T (inverse iteration)
+__device__ __forceinline__ double block_max(double v, double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double t = (lane < nw) ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    return t;
+}
+
+// One block; the k eigenvalues are processed one after the other.  The tridiagonal LU (partial pivoting) and the
+// two substitutions are serial recurrences run by thread 0 out of shared memory (SMEM) or an 8n-double global
+// scratch; dot products / scaling run on the whole block.  Y: n x k column-major, unit 2-norm eigenvectors of T.
+template <bool SMEM>
+__global__ void __launch_bounds__(256) invit_kernel(const double* __restrict__ d, const double* __restrict__ e, int n,
+                                                    int k, const double* __restrict__ evals,
+                                                    const double* __restrict__ scal, double* __restrict__ scratch,
+                                                    double* __restrict__ Y) {
+    extern __shared__ double sm[];
+    __shared__ double red[33];
+    double* base = SMEM ? sm : scratch;
+    double* sd = base;
+    double* se = base + (size_t)n;
+    double* u0 = base + 2 * (size_t)n;
+    double* u1 = base + 3 * (size_t)n;
+    double* u2 = base + 4 * (size_t)n;
+    double* lm = base + 5 * (size_t)n;
+    double* pv = base + 6 * (size_t)n;
+    double* y = base + 7 * (size_t)n;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < n; i += nt) {
+        sd[i] = d[i];
+        se[i] = (i < n - 1) ? e[i] : 0.0;
+    }
+    __syncthreads();
+    const double tnorm = fmax(scal[2], DBL_MIN);
+    const double tiny = DBL_EPSILON * tnorm;
+    for (int c = 0; c < k; ++c) {
+        if (tid == 0) {
+            double lam = evals[c];
+            // separate numerically coincident eigenvalues a little (LAPACK dstein does the same)
+            if (c > 0 && fabs(lam - evals[c - 1]) < 10.0 * tiny) lam = evals[c - 1] - 10.0 * tiny;
+            // factor T - lam I = P L U, U with two super-diagonals
+            double cur_d = sd[0] - lam, cur_u = (n > 1) ? se[0] : 0.0;
+            for (int i = 0; i < n - 1; ++i) {
+                const double sub = se[i];
+                const double next_d = sd[i + 1] - lam;
+                const double next_u = (i + 1 < n - 1) ? se[i + 1] : 0.0;
+                if (fabs(cur_d) >= fabs(sub)) {
+                    if (fabs(cur_d) < tiny) cur_d = copysign(tiny, cur_d);
+                    const double m = sub / cur_d;
+                    lm[i] = m;
+                    pv[i] = 0.0;
+                    u0[i] = cur_d;
+                    u1[i] = cur_u;
+                    u2[i] = 0.0;
+                    cur_d = next_d - m * cur_u;
+                    cur_u = next_u;
+                } else {
+                    const double m = cur_d / sub;
+                    lm[i] = m;
+                    pv[i] = 1.0;
+                    u0[i] = sub;
+                    u1[i] = next_d;
+                    u2[i] = next_u;
+                    cur_d = cur_u - m * next_d;
+                    cur_u = -m * next_u;
+                }
+            }
+            if (fabs(cur_d) < tiny) cur_d = copysign(tiny, cur_d);
+            u0[n - 1] = cur_d;
+            u1[n - 1] = 0.0;
+            u2[n - 1] = 0.0;
+        }
+        for (int i = tid; i < n; i += nt) y[i] = 1.0;
+        for (int itn = 0; itn < 4; ++itn) {
+            __syncthreads();
+            if (tid == 0) {
+                if (itn > 0) {   // forward substitution with the row interchanges (skipped on the first pass)
+                    for (int i = 0; i < n - 1; ++i) {
+                        if (pv[i] != 0.0) {
+                            const double t = y[i];
+                            y[i] = y[i + 1];
+                            y[i + 1] = t;
+                        }
+                        y[i + 1] -= lm[i] * y[i];
+                    }
+                }
+                y[n - 1] = y[n - 1] / u0[n - 1];
+                if (n > 1) y[n - 2] = (y[n - 2] - u1[n - 2] * y[n - 1]) / u0[n - 2];
+                for (int i = n - 3; i >= 0; --i) y[i] = (y[i] - u1[i] * y[i + 1] - u2[i] * y[i + 2]) / u0[i];
+            }
+            __syncthreads();
+            // scale to unit max-norm first (the solve may have grown the vector by 1/eps), then orthogonalise
+            double mx = 0.0;
+            for (int i = tid; i < n; i += nt) mx = fmax(mx, fabs(y[i]));
+            mx = block_max(mx, red);
+            const double inv = 1.0 / fmax(mx, DBL_MIN);
+            for (int i = tid; i < n; i += nt) y[i] *= inv;
+            for (int q = 0; q < c; ++q) {
+                const double* z = Y + (size_t)q * n;
+                double acc = 0.0;
+                for (int i = tid; i < n; i += nt) acc += z[i] * y[i];
+                const double dot = block_sum(acc, red);
+                for (int i = tid; i < n; i += nt) y[i] -= dot * z[i];
+            }
+        }
+        __syncthreads();
+        double acc = 0.0;
+        for (int i = tid; i < n; i += nt) acc += y[i] * y[i];
+        const double inv = 1.0 / sqrt(block_sum(acc, red));
+        for (int i = tid; i < n; i += nt) Y[(size_t)c * n + i] = y[i] * inv;
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------- back-transformation
+// z = H_0 H_1 ... H_{n-2} y, H_j = I - tau_j v_j v_j^T with v_j in row j of A at [j+1, n).  One block per eigenvector.
+__global__ void __launch_bounds__(512) backtransform_kernel(const double* __restrict__ A, int n,
+                                                            const double* __restrict__ tau, double* __restrict__ Y) {
+    __shared__ double red[33];
+    __shared__ int arg;
+    double* y = Y + (size_t)blockIdx.x * n;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = n - 2; j >= 0; --j) {
+        const double tj = tau[j];
+        if (tj == 0.0) continue;
+        const double* v = A + (size_t)j * n;
+        double acc = 0.0;
+        for (int t = j + 1 + tid; t < n; t += nt) acc += v[t] * y[t];
+        const double s = tj * block_sum(acc, red);
+        for (int t = j + 1 + tid; t < n; t += nt) y[t] -= s * v[t];
+        __syncthreads();
+    }
+    // unit 2-norm, then the sign rule: the largest-|.| entry (lowest index on ties) is positive
+    double acc = 0.0;
+    for (int t = tid; t < n; t += nt) acc += y[t] * y[t];
+    const double inv = 1.0 / sqrt(block_sum(acc, red));
+    double best = -1.0;
+    int besti = n;
+    for (int t = tid; t < n; t += nt) {
+        const double a = fabs(y[t]);
+        if (a > best) {
+            best = a;
+            besti = t;
+        }
+    }
+    // block arg-max (value, then lowest index)
+    __shared__ double bv[16];
+    __shared__ int bi[16];
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ov > best || (ov == best && oi < besti)) {
+            best = ov;
+            besti = oi;
+        }
+    }
+    if ((tid & 31) == 0) {
+        bv[tid >> 5] = best;
+        bi[tid >> 5] = besti;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double b = bv[0];
+        int ix = bi[0];
+        for (int i = 1; i < (nt >> 5); ++i)
+            if (bv[i] > b || (bv[i] == b && bi[i] < ix)) {
+                b = bv[i];
+                ix = bi[i];
+            }
+        arg = ix;
+    }
+    __syncthreads();
+    const double sgn = (y[arg] < 0.0) ? -inv : inv;
+    __syncthreads();
+    for (int t = tid; t < n; t += nt) y[t] *= sgn;
+}
+
+}  // namespace
+
+cudaError_t eig_alloc(EigWork& w, int n, int kmax) {
+    w.n = n;
+    w.kmax = kmax;
+    cudaError_t e;
+#define VPCA_TRY(x) if ((e = (x)) != cudaSuccess) return e
+    VPCA_TRY(cudaMalloc(&w.d_C, (size_t)n * n * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_rowsum, (size_t)n * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_v, 2 * (size_t)n * sizeof(double)));   // vprev / vcur ping-pong
+    VPCA_TRY(cudaMalloc(&w.d_w, (size_t)n * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_p, (size_t)n * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_diag, (size_t)n * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_off, 2 * (size_t)n * sizeof(double)));   // e and e^2
+    VPCA_TRY(cudaMalloc(&w.d_tau, (size_t)n * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_scal, 16 * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_evals, (size_t)kmax * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_evecs, (size_t)n * kmax * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_lu, 8 * (size_t)n * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_nz, sizeof(int)));
+#undef VPCA_TRY
+    return cudaSuccess;
+}
+
+void eig_free(EigWork& w) {
+    cudaFree(w.d_C); cudaFree(w.d_rowsum); cudaFree(w.d_v); cudaFree(w.d_w); cudaFree(w.d_p);
+    cudaFree(w.d_diag); cudaFree(w.d_off); cudaFree(w.d_tau); cudaFree(w.d_scal); cudaFree(w.d_evals);
+    cudaFree(w.d_evecs); cudaFree(w.d_lu); cudaFree(w.d_nz);
+    w = EigWork{};
+}
+
+cudaError_t center_gram(EigWork& w, const int32_t* d_S, cudaStream_t stream) {
+    const int n = w.n;
+    rowsum_kernel<<<(n + 7) / 8, 256, 0, stream>>>(d_S, n, w.d_rowsum);
+    matrix_mean_kernel<<<1, 1024, 0, stream>>>(w.d_rowsum, n, w.d_scal, w.d_nz);
+    const int bx = (n + 1023) / 1024 < 1 ? 1 : (n + 1023) / 1024;
+    center_kernel<<<dim3(bx, n), 256, 0, stream>>>(d_S, w.d_rowsum, w.d_scal, n, w.d_C);
+    return cudaGetLastError();
+}
+
+cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) {
+    const int n = w.n;
+    if (k < 1 || k > w.kmax || k > n) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(w.d_v, 0, 2 * (size_t)n * sizeof(double), stream);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(w.d_w, 0, (size_t)n * sizeof(double), stream);
+    cudaMemsetAsync(w.d_p, 0, (size_t)n * sizeof(double), stream);
+    cudaMemsetAsync(w.d_tau, 0, (size_t)n * sizeof(double), stream);
+    cudaMemsetAsync(w.d_off, 0, 2 * (size_t)n * sizeof(double), stream);
+    int64_t nl = 0;
+    for (int j = 0; j < n; ++j) {
+        double* vprev = w.d_v + (size_t)((j + 1) & 1) * n;
+        double* vcur = w.d_v + (size_t)(j & 1) * n;
+        tridiag_small_kernel<<<1, kSmallThreads, 0, stream>>>(w.d_C, n, j, vprev, vcur, w.d_p, w.d_w, w.d_diag, w.d_off,
+                                                              w.d_tau, w.d_scal);
+        ++nl;
+        const int rows = n - 1 - j;
+        if (rows > 0) {
+            tridiag_big_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(w.d_C, n, j, vprev, w.d_w, vcur, w.d_tau, w.d_p);
+            ++nl;
+        }
+    }
+    bisect_kernel<<<k, 256, 0, stream>>>(w.d_diag, w.d_off, n, w.d_off + n, w.d_evals, w.d_scal);
+    const size_t invit_smem = 8 * (size_t)n * sizeof(double);
+    if (invit_smem <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            e = cudaFuncSetAttribute(invit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        invit_kernel<true><<<1, 256, invit_smem, stream>>>(w.d_diag, w.d_off, n, k, w.d_evals, w.d_scal, w.d_lu,
+                                                           w.d_evecs);
+    } else {
+        invit_kernel<false><<<1, 256, 0, stream>>>(w.d_diag, w.d_off, n, k, w.d_evals, w.d_scal, w.d_lu, w.d_evecs);
+    }
+    backtransform_kernel<<<k, 512, 0, stream>>>(w.d_C, n, w.d_tau, w.d_evecs);
+    nl += 3;
+    if (launches) *launches += nl;
+    return cudaGetLastError();
+}
+
+}  // namespace vpca

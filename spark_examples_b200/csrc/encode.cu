@@ -1,0 +1,96 @@
+// Genotype encode on the device: RDD[Seq[Int]] rows (CSR) -> dense sample-major tile.
+//
+// Device half of VariantsPcaDriver.getCallsRdd / extractCallInfo
+// (reference: src/main/scala/com/google/cloud/genomics/spark/examples/VariantsPca.scala:56-60, :153-168):
+// row v lists the callset indices that have `hasVariation` at variant v; the dense equivalent is column v of
+// X in {0,1,..}^N where X[s][v] = number of times s is listed (a sample listed twice counts twice, exactly as the
+// reference's `for (c1 <- callset; c2 <- callset)` at :187 would count it).  The tile is written sample-major
+// (row = sample, contiguous along variants) because that is the K-major operand layout the tcgen05 Gram kernel
+// streams through TMA.
+//
+// HBM-bound scatter: one warp per variant row reads its indices coalesced and adds 1 to X[s][v] with a packed
+// 32-bit atomic (4 int8 cells or 2 bf16 cells per word), so duplicates and any index order are handled.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "vpca_internal.h"
+
+namespace vpca {
+namespace {
+
+__global__ void encode_i8_kernel(const int64_t* __restrict__ off, int64_t base, const int32_t* __restrict__ idx,
+                                 int64_t nv, int n, int max_mult, uint32_t* __restrict__ xw, int64_t ld,
+                                 int* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int bad = 0;
+    for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nv; v += warps) {
+        const int64_t e0 = off[v] - base, e1 = off[v + 1] - base;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const int s = idx[e];
+            if (s < 0 || s >= n) {
+                bad |= 1;
+                continue;
+            }
+            const int64_t byte = (int64_t)s * ld + v;
+            const uint32_t shift = (uint32_t)(byte & 3) * 8u;
+            const uint32_t old = atomicAdd(xw + (byte >> 2), 1u << shift);
+            if ((int)((old >> shift) & 0xFFu) >= max_mult) bad |= 2;
+        }
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
+__global__ void encode_bf16_kernel(const int64_t* __restrict__ off, int64_t base, const int32_t* __restrict__ idx,
+                                   int64_t nv, int n, int max_mult, __nv_bfloat162* __restrict__ x2, int64_t ld,
+                                   int* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int bad = 0;
+    for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nv; v += warps) {
+        const int64_t e0 = off[v] - base, e1 = off[v + 1] - base;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const int s = idx[e];
+            if (s < 0 || s >= n) {
+                bad |= 1;
+                continue;
+            }
+            const int64_t el = (int64_t)s * ld + v;
+            const bool hi = (el & 1) != 0;
+            const __nv_bfloat162 one = __floats2bfloat162_rn(hi ? 0.f : 1.f, hi ? 1.f : 0.f);
+            const __nv_bfloat162 old = atomicAdd(x2 + (el >> 1), one);
+            const float prev = hi ? __high2float(old) : __low2float(old);
+            if (prev >= (float)max_mult) bad |= 2;
+        }
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
+}  // namespace
+
+cudaError_t encode_calls(const int64_t* d_off, int64_t base, const int32_t* d_idx, int64_t nv, int n, int elem_bytes,
+                         int max_mult, void* d_x, int64_t ld, int* d_flags, cudaStream_t stream) {
+    // zero the nv columns (rounded up to the 128-byte k-block the Gram kernel reads) of every sample row
+    size_t width = (((size_t)nv * elem_bytes + 127) / 128) * 128;
+    if (width > (size_t)ld * elem_bytes) width = (size_t)ld * elem_bytes;
+    cudaError_t e = cudaSuccess;
+    if (width > 0) e = cudaMemset2DAsync(d_x, (size_t)ld * elem_bytes, 0, width, (size_t)n, stream);
+    if (e != cudaSuccess || nv <= 0) return e;
+    const int threads = 256;
+    const int64_t want = (nv * 32 + threads - 1) / threads;
+    const int blocks = (int)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
+    if (elem_bytes == 1) {
+        const int cap = max_mult > 127 ? 127 : max_mult;
+        encode_i8_kernel<<<blocks, threads, 0, stream>>>(d_off, base, d_idx, nv, n, cap, reinterpret_cast<uint32_t*>(d_x), ld,
+                                                         d_flags);
+    } else {
+        const int cap = max_mult > 256 ? 256 : max_mult;   // bf16 holds integers exactly up to 256
+        encode_bf16_kernel<<<blocks, threads, 0, stream>>>(d_off, base, d_idx, nv, n, cap,
+                                                           reinterpret_cast<__nv_bfloat162*>(d_x), ld, d_flags);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace vpca

@@ -1,0 +1,505 @@
+// Gram / similarity accumulation  S += X X^T  on sm_100a tensor cores.
+//
+// Replaces the hot loop of VariantsPcaDriver.getSimilarityMatrix
+// (reference: src/main/scala/com/google/cloud/genomics/spark/examples/VariantsPca.scala:182-191,
+//  `for (c1 <- callset; c2 <- callset) matrix(c1, c2) += 1` over every variant) by a dense symmetric
+// rank-V update on the genotype matrix X (samples x variants, sample-major in HBM):
+//
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B)  ->  shared memory ring  ->  tcgen05.mma (kind::i8 / kind::f16)
+//   ->  int32 / fp32 accumulators in TMEM  ->  tcgen05.ld  ->  red.global.add.s32 into the lower triangle of S.
+//
+// Work decomposition ("window-synchronous stream-K"):
+//   * output tiles are BM x BN blocks of S that touch the lower triangle (BM x BN = 256 x 256 per CTA pair with
+//     cta_group::2, 128 x 256 per CTA with cta_group::1); the accumulator of tile (a, b) holds
+//     D[m][n] = sum_v X[a*BM + m][v] * X[b*BN + n][v] and is written TRANSPOSED, S[b*BN + n][a*BM + m], so that the
+//     32 lanes of a warp (= 32 consecutive m) hit 32 consecutive int32 of one row of S;
+//   * the variant axis is cut into k-blocks of 128 bytes (one swizzle atom) and into windows of `kb_window`
+//     k-blocks; in every window the (tile, k-block) units are split evenly over the workers (CTA pairs), and all
+//     workers walk the windows in the same order, so the slice of X a window needs (n x kb_window*128 B, sized to
+//     sit in L2) is fetched from HBM once and re-read from L2 by the other tiles;
+//   * when there are at most as many tiles as workers (N = 2504: 55 tiles, 74 pairs) a worker touches <= 2 tiles,
+//     always the same two, so both accumulators stay resident in TMEM (2 x 256 columns) for the whole launch and
+//     are flushed once at the end; otherwise (large N) it is plain stream-K with double-buffered accumulators.
+// Integer atomics make the result independent of the order of the flushes: S is bit-exact.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "ptx_sm100.cuh"
+#include "vpca_internal.h"
+
+namespace vpca {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kKBytes = 128;                    // bytes of K per k-block: one SWIZZLE_128B atom
+constexpr int kBoxRows = 128;                   // rows per TMA box
+constexpr int kBoxBytes = kBoxRows * kKBytes;   // 16 KiB
+constexpr int kUmmaN = 256;
+constexpr uint32_t kTmemCols = 512;             // two 256-column accumulators
+constexpr long long kWatchdogCycles = 20000000000LL;   // ~10 s: a stuck barrier traps instead of hanging the box
+
+template <int CG>
+struct Cfg {
+    static constexpr int BM = 128 * CG;
+    static constexpr int BN = kUmmaN;
+    static constexpr int A_BYTES = kBoxBytes;                  // per CTA per stage
+    static constexpr int B_BYTES = (BN / CG) * kKBytes;        // per CTA per stage (32 KiB / 16 KiB)
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = CG == 1 ? 4 : 6;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + slack for 1024 B alignment
+};
+
+struct GramArgs {
+    int32_t* S;
+    const int2* tiles;
+    int* err;          // mapped host memory: watchdog diagnostics
+    int n;
+    int num_tiles;
+    int kb_total;
+    int kb_window;
+    int num_workers;
+    int resident;
+    int elems_per_kb;  // 128 / sizeof(element)
+};
+
+struct Seg {
+    int tile, kb0, kb1, slot, first, flush, use;
+};
+
+// Every role of a worker (TMA producer, MMA issuer, epilogue) replays the same deterministic schedule.
+struct Sched {
+    long long u_begin, u_end, u;
+    int kbw, nwin, kb_total, resident, win, seg_in_win, nflush;
+
+    __device__ void init(const GramArgs& a, int worker) {
+        kbw = a.kb_window;
+        kb_total = a.kb_total;
+        resident = a.resident;
+        nwin = (kb_total + kbw - 1) / kbw;
+        const long long uw = (long long)a.num_tiles * kbw;
+        u_begin = uw * worker / a.num_workers;
+        u_end = uw * (worker + 1) / a.num_workers;
+        u = u_begin;
+        win = 0;
+        seg_in_win = 0;
+        nflush = 0;
+    }
+    __device__ bool next(Seg& s) {
+        if (u_begin >= u_end) return false;
+        if (u >= u_end) {
+            ++win;
+            u = u_begin;
+            seg_in_win = 0;
+        }
+        if (win >= nwin) return false;
+        const int tile = (int)(u / kbw);
+        const int lo = (int)(u - (long long)tile * kbw);
+        const long long rem = u_end - u;
+        const int hi = rem < (long long)(kbw - lo) ? lo + (int)rem : kbw;
+        u += hi - lo;
+        const int base = win * kbw;
+        const int cnt = min(kbw, kb_total - base);
+        s.tile = tile;
+        s.kb0 = base + min(lo, cnt);
+        s.kb1 = base + min(hi, cnt);
+        if (resident) {
+            s.slot = seg_in_win;
+            s.first = (win == 0);
+            s.flush = (win == nwin - 1);
+            s.use = 0;
+        } else {
+            s.slot = nflush & 1;
+            s.first = 1;
+            s.flush = 1;
+            s.use = nflush >> 1;
+            ++nflush;
+        }
+        ++seg_in_win;
+        return true;
+    }
+};
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    if (ptx::mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > kWatchdogCycles) {
+            if (err != nullptr) {
+                err[0] = code;
+                err[1] = (int)blockIdx.x;
+                err[2] = (int)bar;
+                err[3] = (int)parity;
+                __threadfence_system();
+            }
+            __trap();
+        }
+    }
+}
+
+// K-major SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), one atom along K (LBO unused).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int CG, int KIND>
+__device__ __forceinline__ uint32_t make_instr_desc() {
+    constexpr uint32_t M = 128 * CG, N = kUmmaN;
+    // c_format [4,6): 1 = F32, 2 = S32; a/b_format [7,10)/[10,13): i8 -> 1 (signed), f16 kind -> 1 (BF16);
+    // a/b major bits 15/16 = 0 (K-major); n_dim [17,23) = N >> 3; m_dim [24,29) = M >> 4.
+    constexpr uint32_t cfmt = (KIND == 0) ? 2u : 1u;
+    return (cfmt << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+template <int CG, int KIND>
+__global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
+    using C = Cfg<CG>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto sA = [&](uint32_t st) { return smem_base + st * C::A_BYTES; };
+    auto sB = [&](uint32_t st) { return smem_base + C::STAGES * C::A_BYTES + st * C::B_BYTES; };
+    auto full_bar = [&](uint32_t i) { return bar_base + 8u * i; };
+    auto empty_bar = [&](uint32_t i) { return bar_base + 8u * (C::STAGES + i); };
+    auto tfull_bar = [&](uint32_t i) { return bar_base + 8u * (2 * C::STAGES + i); };
+    auto tempty_bar = [&](uint32_t i) { return bar_base + 8u * (2 * C::STAGES + 2 + i); };
+    volatile uint32_t* tmem_ptr_smem =
+        reinterpret_cast<volatile uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const uint32_t lane = ptx::lane_id();
+    const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int worker = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const bool issuer = ptx::elect_one();   // one fixed lane per warp issues TMA / MMA / commits
+
+    if constexpr (CG == 2) ptx::cluster_sync();   // both CTAs of the pair are resident before the paired TMEM alloc
+
+    if (warp == 0 && issuer) {
+        ptx::prefetch_tensormap(&tmap);
+    } else if (warp == 1 && issuer) {
+        for (uint32_t i = 0; i < (uint32_t)C::STAGES; ++i) {
+            ptx::mbar_init(full_bar(i), CG);    // producer arrive(s): leader expect_tx (+ peer's remote arrive)
+            ptx::mbar_init(empty_bar(i), 1);    // one tcgen05.commit per use
+        }
+        for (uint32_t i = 0; i < 2; ++i) {
+            ptx::mbar_init(tfull_bar(i), 1);
+            ptx::mbar_init(tempty_bar(i), CG * 128);   // every epilogue thread of the pair arrives at the leader
+        }
+        ptx::fence_mbar_init();
+    } else if (warp == 2) {
+        ptx::tmem_alloc<CG>(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
+        ptx::tmem_relinquish<CG>();
+    }
+    ptx::tc_fence_before();
+    if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (issuer) {
+            Sched sc;
+            sc.init(a, worker);
+            Seg s;
+            uint32_t it = 0;
+            while (sc.next(s)) {
+                const int2 t = a.tiles[s.tile];
+                const int rowA = t.x * C::BM + (int)cta_rank * kBoxRows;
+                const int rowB = t.y * C::BN + ((CG == 2) ? (int)cta_rank * kBoxRows : 0);
+                for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
+                    const uint32_t st = it % C::STAGES, ph = (it / C::STAGES) & 1u;
+                    mbar_wait(empty_bar(st), ph ^ 1u, a.err, 1);
+                    const int kc = kb * a.elems_per_kb;
+                    if constexpr (CG == 1) {
+                        ptx::mbar_arrive_expect_tx(full_bar(st), C::STAGE_BYTES);
+                        ptx::tma_load_2d(sA(st), &tmap, full_bar(st), kc, rowA);
+                        ptx::tma_load_2d(sB(st), &tmap, full_bar(st), kc, rowB);
+                        ptx::tma_load_2d(sB(st) + kBoxBytes, &tmap, full_bar(st), kc, rowB + kBoxRows);
+                    } else {
+                        ptx::tma_load_2d_2sm(sA(st), &tmap, full_bar(st), kc, rowA);
+                        ptx::tma_load_2d_2sm(sB(st), &tmap, full_bar(st), kc, rowB);
+                        if (leader) ptx::mbar_arrive_expect_tx(full_bar(st), 2 * C::STAGE_BYTES);
+                        else ptx::mbar_arrive_cluster(full_bar(st), 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ===================================== MMA issuer =======================================
+        const uint32_t idesc = make_instr_desc<CG, KIND>();
+        Sched sc;
+        sc.init(a, worker);
+        Seg s;
+        uint32_t it = 0;
+        while (sc.next(s)) {
+            if (s.first) {
+                mbar_wait(tempty_bar(s.slot), (uint32_t)(s.use & 1) ^ 1u, a.err, 2);
+                ptx::tc_fence_after();
+            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)s.slot * kUmmaN;
+            for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
+                const uint32_t st = it % C::STAGES, ph = (it / C::STAGES) & 1u;
+                mbar_wait(full_bar(st), ph, a.err, 3);
+                ptx::tc_fence_after();
+                if (issuer) {
+                    const uint64_t adesc = make_smem_desc(sA(st));
+                    const uint64_t bdesc = make_smem_desc(sB(st));
+                    uint32_t acc = (s.first && kb == s.kb0) ? 0u : 1u;
+#pragma unroll
+                    for (int k = 0; k < kKBytes / 32; ++k) {           // UMMA_K = 32 bytes of K
+                        ptx::umma_ss<CG, KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                        acc = 1u;
+                    }
+                    ptx::umma_commit<CG>(empty_bar(st));               // frees the smem stage (both CTAs)
+                }
+                __syncwarp();
+            }
+            if (s.flush) {
+                if (issuer) ptx::umma_commit<CG>(tfull_bar(s.slot));   // accumulator complete -> epilogue
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================== epilogue =========================================
+        const int q = warp & 3;   // TMEM lane quarter this warp may read
+        Sched sc;
+        sc.init(a, worker);
+        Seg s;
+        while (sc.next(s)) {
+            if (!s.flush) continue;
+            mbar_wait(tfull_bar(s.slot), (uint32_t)(s.use & 1), a.err, 4);
+            ptx::tc_fence_after();
+            const int2 t = a.tiles[s.tile];
+            const int col = t.x * C::BM + (int)cta_rank * kBoxRows + q * 32 + (int)lane;   // sample of the A row
+            const int col_warp_min = col - (int)lane;
+            const int row0 = t.y * C::BN;                                                  // samples of the B rows
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s.slot * kUmmaN;
+            int32_t* out = a.S + col;
+#pragma unroll 1
+            for (int c = 0; c < C::BN / 32; ++c) {
+                const int rbase = row0 + c * 32;
+                if (rbase >= a.n || rbase + 31 < col_warp_min) continue;   // outside S or strictly above the diagonal
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int row = rbase + j;
+                    if (row < a.n && col < a.n && row >= col) {
+                        int v;
+                        if constexpr (KIND == 0) v = (int)r[j];
+                        else v = __float2int_rn(__uint_as_float(r[j]));
+                        if (v != 0)
+                            asm volatile("red.global.add.s32 [%0], %1;" ::"l"(out + (size_t)row * (size_t)a.n), "r"(v)
+                                         : "memory");
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(s.slot));
+            else ptx::mbar_arrive_cluster(tempty_bar(s.slot), 0);
+        }
+    }
+
+    ptx::tc_fence_before();
+    if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void symmetrize_kernel(int32_t* __restrict__ S, int n) {
+    // block (bx >= by): read lower tile (bx, by), write it transposed into the upper tile (by, bx)
+    __shared__ int32_t tile[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (bx < by) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int row = bx * 32 + r, col = by * 32 + tx;
+        tile[r][tx] = (row < n && col < n) ? S[(size_t)row * n + col] : 0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int row = by * 32 + r, col = bx * 32 + tx;   // target (upper)
+        if (row < n && col < n && row < col) S[(size_t)row * n + col] = tile[tx][r];
+    }
+}
+
+__global__ void add_i32_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, int64_t count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) dst[i] += src[i];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int CG, int KIND>
+cudaError_t launch(const CUtensorMap& tmap, const GramArgs& args, int grid, cudaStream_t stream) {
+    using C = Cfg<CG>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gram_kernel<CG, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gram_kernel<CG, KIND>, tmap, args);
+}
+
+}  // namespace
+
+void gram_plan_free(GramPlan& plan) {
+    if (plan.d_tiles) cudaFree(plan.d_tiles);
+    if (plan.d_err) cudaFreeHost(plan.d_err);
+    plan.d_tiles = nullptr;
+    plan.d_err = nullptr;
+    plan.tiles_for_n = -1;
+}
+
+static cudaError_t build_tiles(GramPlan& plan, int n, cudaStream_t stream) {
+    const int BM = 128 * plan.cta_group, BN = kUmmaN;
+    std::vector<int2> tiles;
+    const int nbn = (n + BN - 1) / BN, nbm = (n + BM - 1) / BM;
+    for (int b = 0; b < nbn; ++b)
+        for (int am = 0; am < nbm; ++am) {
+            // tile covers output rows [b*BN, b*BN+BN) x cols [am*BM, am*BM+BM); keep it if it touches row >= col
+            const int max_row = std::min(n, b * BN + BN) - 1;
+            if (am * BM <= max_row) tiles.push_back(make_int2(am, b));
+        }
+    if (plan.d_tiles) cudaFree(plan.d_tiles);
+    plan.d_tiles = nullptr;
+    cudaError_t e = cudaMalloc(&plan.d_tiles, tiles.size() * sizeof(int2));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(plan.d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(stream);   // `tiles` is a stack vector
+    plan.num_tiles = (int)tiles.size();
+    plan.tiles_for_n = n;
+    plan.tiles_for_cg = plan.cta_group;
+    return e;
+}
+
+cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bytes, int n, int64_t nv, int64_t ld,
+                            int32_t* d_S, cudaStream_t stream, std::string* err) {
+    if (nv <= 0) return cudaSuccess;
+    EncodeTiledFn encode = get_encode_fn();
+    if (encode == nullptr) {
+        if (err) *err = "cuTensorMapEncodeTiled entry point not available";
+        return cudaErrorNotSupported;
+    }
+    if (plan.num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&plan.num_sms, cudaDevAttrMultiProcessorCount, dev);
+        const char* cg = getenv("VPCA_CTA_GROUP");
+        if (cg != nullptr) plan.cta_group = (atoi(cg) == 1) ? 1 : 2;
+        const char* kw = getenv("VPCA_KB_WINDOW");
+        if (kw != nullptr) plan.kb_window = atoi(kw);
+    }
+    if (plan.d_err == nullptr) {
+        cudaError_t e = cudaHostAlloc(&plan.d_err, 4 * sizeof(int), cudaHostAllocMapped);
+        if (e != cudaSuccess) return e;
+        for (int i = 0; i < 4; ++i) plan.d_err[i] = 0;
+    }
+    if (plan.tiles_for_n != n || plan.tiles_for_cg != plan.cta_group) {
+        cudaError_t e = build_tiles(plan, n, stream);
+        if (e != cudaSuccess) return e;
+    }
+    if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0 || ((ld * elem_bytes) & 15) != 0) {
+        if (err) *err = "dense tile must be 16-byte aligned with a 16-byte multiple row pitch";
+        return cudaErrorInvalidValue;
+    }
+
+    const int cgp = plan.cta_group;
+    const int workers = (cgp == 2) ? plan.num_sms / 2 : plan.num_sms;
+    const int elems_per_kb = kKBytes / elem_bytes;
+    const int kind = (elem_bytes == 1) ? 0 : 1;
+
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)nv, (cuuint64_t)n};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)elems_per_kb, (cuuint32_t)kBoxRows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(d_x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return cudaErrorInvalidValue;
+    }
+
+    GramArgs args{};
+    args.S = d_S;
+    args.tiles = plan.d_tiles;
+    cudaHostGetDevicePointer(reinterpret_cast<void**>(&args.err), plan.d_err, 0);
+    args.n = n;
+    args.num_tiles = plan.num_tiles;
+    args.kb_total = (int)((nv + elems_per_kb - 1) / elems_per_kb);
+    args.num_workers = workers;
+    args.resident = plan.num_tiles <= workers ? 1 : 0;
+    args.elems_per_kb = elems_per_kb;
+    if (args.resident) {
+        int kbw = plan.kb_window;
+        if (kbw <= 0) {
+            // window of X sized to ~32 MiB so that every tile re-reads it from L2 (126 MB) rather than HBM
+            const long long target = 32ll << 20;
+            kbw = (int)std::max<long long>(8, std::min<long long>(4096, target / ((long long)n * kKBytes)));
+        }
+        args.kb_window = std::min(kbw, args.kb_total);
+    } else {
+        args.kb_window = args.kb_total;
+    }
+    plan.last_resident = args.resident;
+
+    const int grid = workers * cgp;
+    if (cgp == 2) return kind == 0 ? launch<2, 0>(tmap, args, grid, stream) : launch<2, 1>(tmap, args, grid, stream);
+    return kind == 0 ? launch<1, 0>(tmap, args, grid, stream) : launch<1, 1>(tmap, args, grid, stream);
+}
+
+cudaError_t gram_symmetrize(int32_t* d_S, int n, cudaStream_t stream) {
+    const int nb = (n + 31) / 32;
+    symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, stream>>>(d_S, n);
+    return cudaGetLastError();
+}
+
+cudaError_t gram_add(int32_t* d_dst, const int32_t* d_src, int64_t count, cudaStream_t stream) {
+    add_i32_kernel<<<592, 256, 0, stream>>>(d_dst, d_src, count);
+    return cudaGetLastError();
+}
+
+}  // namespace vpca

@@ -1,0 +1,68 @@
+// Internal declarations shared by the libvpca translation units (not part of the ABI).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <string>
+
+#include "../../include/vpca.h"
+
+namespace vpca {
+
+// ---- Gram (gram_sm100.cu) --------------------------------------------------------------------
+struct GramPlan {
+    int cta_group = 2;        // tcgen05 cta_group (1: 128x256 tiles per CTA, 2: 256x256 per CTA pair)
+    int kb_window = 0;        // k-blocks per L2 window (0 -> automatic)
+    int num_sms = 0;
+    int2* d_tiles = nullptr;  // device tile list (A row block, B row block)
+    int num_tiles = 0;
+    int tiles_for_n = -1;     // n_samples the tile list was built for
+    int tiles_for_cg = 0;
+    int last_resident = 0;
+    int* d_err = nullptr;     // device debug words written before a watchdog trap
+};
+
+// S(lower triangle, row >= col) += X X^T for the nv variants of a dense sample-major tile.
+//   d_x : device, element (s, v) at d_x[s * ld + v]; elem_bytes 1 (int8) or 2 (bf16)
+//   d_S : device int32 n x n row-major
+// Returns cudaSuccess or the first CUDA error; never synchronises.
+cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bytes, int n, int64_t nv, int64_t ld,
+                            int32_t* d_S, cudaStream_t stream, std::string* err);
+cudaError_t gram_symmetrize(int32_t* d_S, int n, cudaStream_t stream);
+cudaError_t gram_add(int32_t* d_dst, const int32_t* d_src, int64_t count, cudaStream_t stream);
+void gram_plan_free(GramPlan& plan);
+
+// ---- encode (encode.cu) ------------------------------------------------------------------------
+// CSR rows [0, nv) (d_off has nv+1 entries; entry e of row v is d_idx[d_off[v] - base + ...]) -> dense
+// sample-major tile, zero-filled first.  d_flags[0] is OR-ed with 1 on an out-of-range index and 2 on a
+// multiplicity overflow.
+cudaError_t encode_calls(const int64_t* d_off, int64_t base, const int32_t* d_idx, int64_t nv, int n,
+                         int elem_bytes, int max_mult, void* d_x, int64_t ld, int* d_flags, cudaStream_t stream);
+
+// ---- centering + eigensolve (eig.cu) ---------------------------------------------------------------
+struct EigWork {
+    int n = 0;
+    double* d_C = nullptr;     // n x n centered matrix, overwritten by the tridiagonalisation
+    double* d_rowsum = nullptr;
+    double* d_v = nullptr;     // Householder vector of the current step (n)
+    double* d_w = nullptr;     // w vector of the current step (n)
+    double* d_p = nullptr;     // p = tau A v (n)
+    double* d_diag = nullptr;  // n
+    double* d_off = nullptr;   // n
+    double* d_tau = nullptr;   // n
+    double* d_scal = nullptr;  // small scalar scratch
+    double* d_evals = nullptr; // k
+    double* d_evecs = nullptr; // n x k (column-major)
+    double* d_lu = nullptr;    // 8 n scratch for inverse iteration
+    int* d_nz = nullptr;
+    int kmax = 0;
+};
+cudaError_t eig_alloc(EigWork& w, int n, int kmax);
+void eig_free(EigWork& w);
+cudaError_t center_gram(EigWork& w, const int32_t* d_S, cudaStream_t stream);
+cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches);
+
+// ---- synthetic generator (synth.cu) ----------------------------------------------------------------
+cudaError_t synth_dense(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, int elem_bytes, void* d_x,
+                        int64_t ld, cudaStream_t stream);
+
+}  // namespace vpca

@@ -1,0 +1,294 @@
+"""ctypes binding of libvpca.so (include/vpca.h) -- the Python twin of the JNI class ``NativePca``
+shown in INTEGRATION.md.  One ``NativePca`` object = one ``vpca_ctx`` = one GPU.
+
+There is no CPU fallback: importing this module never fails (so host logic stays testable without a
+GPU), but constructing ``NativePca`` raises ``VpcaError`` when the CUDA library is missing or no
+sm_100 device is usable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+from typing import Optional, Tuple
+
+import numpy as np
+
+VPCA_OK = 0
+VPCA_ERR_BAD_ARG = -1
+VPCA_ERR_INDEX_OUT_OF_RANGE = -2
+VPCA_ERR_CUDA = -3
+VPCA_ERR_NCCL = -4
+VPCA_ERR_OVERFLOW = -5
+VPCA_ERR_STATE = -6
+VPCA_ERR_NOMEM = -7
+VPCA_ERR_UNSUPPORTED = -8
+
+DTYPE_I8 = 0
+DTYPE_BF16 = 1
+
+_STATUS_NAMES = {
+    -1: "BAD_ARG", -2: "INDEX_OUT_OF_RANGE", -3: "CUDA", -4: "NCCL", -5: "OVERFLOW", -6: "STATE",
+    -7: "NOMEM", -8: "UNSUPPORTED",
+}
+
+# every symbol include/vpca.h declares (checked by tests/test_abi.py against the header)
+EXPORTED_SYMBOLS = (
+    "vpca_version", "vpca_create", "vpca_destroy", "vpca_last_error", "vpca_reset", "vpca_encode_calls",
+    "vpca_accumulate_calls", "vpca_commit", "vpca_abort", "vpca_accumulate_dense", "vpca_gram_device_ptr",
+    "vpca_finalize_gram", "vpca_get_gram", "vpca_set_gram", "vpca_compute_pca", "vpca_get_centered",
+    "vpca_get_tridiagonal", "vpca_synth_dense_device", "vpca_get_stats",
+)
+
+
+class VpcaError(RuntimeError):
+    """Raised for every negative vpca_status (the JNI shim rethrows the same way as RuntimeException)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"vpca {_STATUS_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+class IndexOutOfRange(VpcaError, IndexError):
+    """Sample index outside [0, N): the reference throws at VariantsPca.scala:59 / :188."""
+
+
+class VpcaConfig(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("n_samples", ctypes.c_int32),
+        ("device", ctypes.c_int32),
+        ("dtype", ctypes.c_int32),
+        ("num_pc", ctypes.c_int32),
+        ("max_multiplicity", ctypes.c_int32),
+        ("partitions_in_flight", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
+        ("chunk_variants", ctypes.c_int64),
+        ("chunk_nnz", ctypes.c_int64),
+        ("stream", ctypes.c_void_p),
+        ("d_gram", ctypes.c_void_p),
+    ]
+
+
+class VpcaStats(ctypes.Structure):
+    _fields_ = [
+        ("variants_accumulated", ctypes.c_int64),
+        ("gram_launches", ctypes.c_int64),
+        ("kernel_launches", ctypes.c_int64),
+        ("h2d_bytes", ctypes.c_int64),
+        ("d2h_bytes", ctypes.c_int64),
+        ("last_gram_ms", ctypes.c_float),
+        ("last_eig_ms", ctypes.c_float),
+        ("gram_cta_group", ctypes.c_int32),
+        ("gram_resident", ctypes.c_int32),
+    ]
+
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libvpca.so"
+_lib: Optional[ctypes.CDLL] = None
+
+
+def library_path() -> Path:
+    return Path(os.environ.get("VPCA_LIBRARY", str(LIB_PATH)))
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libvpca.so and declare the prototypes.  Raises VpcaError if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise VpcaError(VPCA_ERR_CUDA, f"{path} not found: build it with `python -c 'import __graft_entry__ as g; "
+                        "g.build()'` (there is no CPU fallback)")
+    L = ctypes.CDLL(str(path))
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.vpca_version.restype = ctypes.c_int
+    L.vpca_version.argtypes = []
+    L.vpca_create.restype = ctypes.c_int
+    L.vpca_create.argtypes = [ctypes.POINTER(VpcaConfig), ctypes.POINTER(vp)]
+    L.vpca_destroy.restype = ctypes.c_int
+    L.vpca_destroy.argtypes = [vp]
+    L.vpca_last_error.restype = ctypes.c_char_p
+    L.vpca_last_error.argtypes = [vp]
+    L.vpca_reset.restype = ctypes.c_int
+    L.vpca_reset.argtypes = [vp]
+    L.vpca_encode_calls.restype = ctypes.c_int
+    L.vpca_encode_calls.argtypes = [vp, vp, vp, i64, vp, i64]
+    L.vpca_accumulate_calls.restype = ctypes.c_int
+    L.vpca_accumulate_calls.argtypes = [vp, i64, vp, vp, i64]
+    L.vpca_commit.restype = ctypes.c_int
+    L.vpca_commit.argtypes = [vp, i64]
+    L.vpca_abort.restype = ctypes.c_int
+    L.vpca_abort.argtypes = [vp, i64]
+    L.vpca_accumulate_dense.restype = ctypes.c_int
+    L.vpca_accumulate_dense.argtypes = [vp, vp, i64, i64, ctypes.c_int]
+    L.vpca_gram_device_ptr.restype = ctypes.c_int
+    L.vpca_gram_device_ptr.argtypes = [vp, ctypes.POINTER(vp)]
+    L.vpca_finalize_gram.restype = ctypes.c_int
+    L.vpca_finalize_gram.argtypes = [vp]
+    L.vpca_get_gram.restype = ctypes.c_int
+    L.vpca_get_gram.argtypes = [vp, vp]
+    L.vpca_set_gram.restype = ctypes.c_int
+    L.vpca_set_gram.argtypes = [vp, vp]
+    L.vpca_compute_pca.restype = ctypes.c_int
+    L.vpca_compute_pca.argtypes = [vp, i32, vp, vp, ctypes.POINTER(i32)]
+    L.vpca_get_centered.restype = ctypes.c_int
+    L.vpca_get_centered.argtypes = [vp, vp]
+    L.vpca_get_tridiagonal.restype = ctypes.c_int
+    L.vpca_get_tridiagonal.argtypes = [vp, vp, vp]
+    L.vpca_synth_dense_device.restype = ctypes.c_int
+    L.vpca_synth_dense_device.argtypes = [vp, ctypes.c_uint64, i64, i64, ctypes.c_int, vp, i64]
+    L.vpca_get_stats.restype = ctypes.c_int
+    L.vpca_get_stats.argtypes = [vp, ctypes.POINTER(VpcaStats)]
+    _lib = L
+    return L
+
+
+def _host_ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+class NativePca:
+    """One GPU's VariantsPca state.  Method names follow the JNI class of INTEGRATION.md 1:1."""
+
+    def __init__(self, n_samples: int, device: int = 0, dtype: int = DTYPE_I8, num_pc: int = 2,
+                 max_multiplicity: int = 2, partitions_in_flight: int = 4, chunk_variants: int = 0,
+                 chunk_nnz: int = 0, stream: int = 0, d_gram: int = 0):
+        self._lib = load_library()
+        self.n = int(n_samples)
+        self.dtype = int(dtype)
+        self.elem_bytes = 1 if dtype == DTYPE_I8 else 2
+        cfg = VpcaConfig(ctypes.sizeof(VpcaConfig), n_samples, device, dtype, num_pc, max_multiplicity,
+                         partitions_in_flight, 0, chunk_variants, chunk_nnz, stream or None, d_gram or None)
+        handle = ctypes.c_void_p()
+        rc = self._lib.vpca_create(ctypes.byref(cfg), ctypes.byref(handle))
+        self._h = handle if rc == VPCA_OK else None
+        if rc != VPCA_OK:
+            self._raise(rc, None)
+
+    # -- error plumbing ------------------------------------------------------------------------
+    def _raise(self, rc: int, handle):
+        msg = self._lib.vpca_last_error(handle).decode("utf-8", "replace")
+        if rc == VPCA_ERR_INDEX_OUT_OF_RANGE:
+            raise IndexOutOfRange(rc, msg)
+        raise VpcaError(rc, msg)
+
+    def _check(self, rc: int):
+        if rc != VPCA_OK:
+            self._raise(rc, self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.vpca_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- API -------------------------------------------------------------------------------------
+    def reset(self):
+        self._check(self._lib.vpca_reset(self._h))
+
+    @staticmethod
+    def _csr(offsets, sample_idx) -> Tuple[np.ndarray, np.ndarray]:
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        if off.ndim != 1 or len(off) < 1:
+            raise VpcaError(VPCA_ERR_BAD_ARG, "offsets must be a 1-D array with nv+1 entries")
+        return off, idx
+
+    def encodeCalls(self, offsets, sample_idx) -> np.ndarray:
+        """Device encode only (CSR rows -> dense sample-major tile), copied back: shape (n, nv)."""
+        off, idx = self._csr(offsets, sample_idx)
+        nv = len(off) - 1
+        out = np.zeros((self.n, max(nv, 1)), dtype=np.int8 if self.elem_bytes == 1 else np.uint16)
+        self._check(self._lib.vpca_encode_calls(self._h, _host_ptr(off), _host_ptr(idx) if len(idx) else None, nv,
+                                                _host_ptr(out), out.shape[1]))
+        return out[:, :nv]
+
+    def accumulateCalls(self, partition_id: int, offsets, sample_idx):
+        off, idx = self._csr(offsets, sample_idx)
+        self._check(self._lib.vpca_accumulate_calls(self._h, int(partition_id), _host_ptr(off),
+                                                    _host_ptr(idx) if len(idx) else None, len(off) - 1))
+
+    def accumulateCallsRaw(self, partition_id: int, off_ptr: int, idx_ptr: int, nv: int):
+        """Same, from raw host addresses (e.g. pinned torch tensors) -- no copies on the Python side."""
+        self._check(self._lib.vpca_accumulate_calls(self._h, int(partition_id), off_ptr, idx_ptr, int(nv)))
+
+    def commit(self, partition_id: int):
+        self._check(self._lib.vpca_commit(self._h, int(partition_id)))
+
+    def abort(self, partition_id: int):
+        self._check(self._lib.vpca_abort(self._h, int(partition_id)))
+
+    def accumulateDense(self, x: np.ndarray):
+        """Host dense tile, shape (n, nv), int8 (or uint16 bf16 bits)."""
+        want = np.int8 if self.elem_bytes == 1 else np.uint16
+        x = np.asarray(x)
+        if x.dtype != want or x.ndim != 2 or x.shape[0] != self.n:
+            raise VpcaError(VPCA_ERR_BAD_ARG, f"dense tile must be ({self.n}, nv) {np.dtype(want).name}")
+        if not x.flags.c_contiguous:
+            x = np.ascontiguousarray(x)
+        self._check(self._lib.vpca_accumulate_dense(self._h, _host_ptr(x), x.shape[1], x.shape[1], 0))
+
+    def accumulateDenseDevice(self, d_ptr: int, nv: int, ld: int):
+        self._check(self._lib.vpca_accumulate_dense(self._h, d_ptr, int(nv), int(ld), 1))
+
+    def gramDevicePtr(self) -> int:
+        p = ctypes.c_void_p()
+        self._check(self._lib.vpca_gram_device_ptr(self._h, ctypes.byref(p)))
+        return int(p.value)
+
+    def finalizeGram(self):
+        self._check(self._lib.vpca_finalize_gram(self._h))
+
+    def getGram(self) -> np.ndarray:
+        out = np.empty((self.n, self.n), dtype=np.int32)
+        self._check(self._lib.vpca_get_gram(self._h, _host_ptr(out)))
+        return out
+
+    def setGram(self, gram: np.ndarray):
+        g = np.ascontiguousarray(gram, dtype=np.int32)
+        if g.shape != (self.n, self.n):
+            raise VpcaError(VPCA_ERR_BAD_ARG, "gram must be (n, n)")
+        self._check(self._lib.vpca_set_gram(self._h, _host_ptr(g)))
+
+    def computePca(self, k: int = 2):
+        """-> (vecs (n, k) with column c = PC c, evals (k,), nonZeroRows).  `vecs.T.ravel()` is the
+        column-major array ``pca.toArray`` of VariantsPca.scala:227."""
+        flat = np.empty(self.n * k, dtype=np.float64)
+        evals = np.empty(k, dtype=np.float64)
+        nz = ctypes.c_int32(0)
+        self._check(self._lib.vpca_compute_pca(self._h, int(k), _host_ptr(flat), _host_ptr(evals), ctypes.byref(nz)))
+        return flat.reshape(k, self.n).T.copy(), evals, int(nz.value)
+
+    def getCentered(self) -> np.ndarray:
+        out = np.empty((self.n, self.n), dtype=np.float64)
+        self._check(self._lib.vpca_get_centered(self._h, _host_ptr(out)))
+        return out
+
+    def getTridiagonal(self):
+        d = np.empty(self.n, dtype=np.float64)
+        e = np.empty(self.n - 1, dtype=np.float64)
+        self._check(self._lib.vpca_get_tridiagonal(self._h, _host_ptr(d), _host_ptr(e)))
+        return d, e
+
+    def synthDenseDevice(self, seed: int, v0: int, nv: int, mode: int, d_ptr: int, ld: int):
+        self._check(self._lib.vpca_synth_dense_device(self._h, ctypes.c_uint64(seed), int(v0), int(nv), int(mode),
+                                                      d_ptr, int(ld)))
+
+    def stats(self) -> dict:
+        st = VpcaStats()
+        self._check(self._lib.vpca_get_stats(self._h, ctypes.byref(st)))
+        return {name: getattr(st, name) for name, _ in VpcaStats._fields_}

@@ -1,0 +1,268 @@
+"""GPU parity tests of the encode + Gram kernels against the CPU oracle (bit-exact), through the C ABI.
+
+Reference behaviour under test: VariantsPca.scala:56-60, :153-168 (encode) and :182-191 (similarity matrix)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20240901
+
+
+def _native(n, **kw):
+    from spark_examples_b200 import native
+    return native.NativePca(n, **kw)
+
+
+def _set_env(monkeypatch, cta_group=None, kb_window=None):
+    if cta_group is None:
+        monkeypatch.delenv("VPCA_CTA_GROUP", raising=False)
+    else:
+        monkeypatch.setenv("VPCA_CTA_GROUP", str(cta_group))
+    if kb_window is None:
+        monkeypatch.delenv("VPCA_KB_WINDOW", raising=False)
+    else:
+        monkeypatch.setenv("VPCA_KB_WINDOW", str(kb_window))
+
+
+def _random_rows(rng, n, nv, density=0.3, dup_every=0):
+    rows = []
+    for v in range(nv):
+        k = rng.binomial(n, density)
+        r = rng.choice(n, size=k, replace=False).astype(np.int32)
+        if dup_every and v % dup_every == 0 and k > 0:
+            r = np.concatenate([r, r[:1]])          # one sample listed twice (multi-dataset join case)
+        rows.append(r)
+    off = np.zeros(nv + 1, np.int64)
+    off[1:] = np.cumsum([len(r) for r in rows])
+    idx = np.concatenate(rows) if rows else np.zeros(0, np.int32)
+    return off, idx.astype(np.int32), rows
+
+
+def test_encode_tile_bit_exact(oracle):
+    rng = np.random.default_rng(1)
+    n, nv = 203, 517
+    off, idx, rows = _random_rows(rng, n, nv, 0.2, dup_every=7)
+    want = np.zeros((n, nv), np.int8)
+    for v, r in enumerate(rows):
+        np.add.at(want[:, v], r, 1)
+    with _native(n) as nat:
+        got = nat.encodeCalls(off, idx)
+    assert got.dtype == np.int8 and got.shape == (n, nv)
+    assert np.array_equal(got, want)
+
+
+def test_encode_tile_bf16(oracle):
+    rng = np.random.default_rng(2)
+    n, nv = 130, 260
+    off, idx, rows = _random_rows(rng, n, nv, 0.3, dup_every=5)
+    want = np.zeros((n, nv), np.int64)
+    for v, r in enumerate(rows):
+        np.add.at(want[:, v], r, 1)
+    from spark_examples_b200 import native
+    with _native(n, dtype=native.DTYPE_BF16) as nat:
+        got = nat.encodeCalls(off, idx)
+    bf16_bits = {0: 0x0000, 1: 0x3F80, 2: 0x4000}
+    want_bits = np.vectorize(bf16_bits.get)(want).astype(np.uint16)
+    assert np.array_equal(got, want_bits)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gram_small_dense_host(oracle, monkeypatch, cta_group):
+    _set_env(monkeypatch, cta_group)
+    rng = np.random.default_rng(3)
+    n, nv = 300, 1000
+    X = (rng.random((n, nv)) < 0.35).astype(np.int8)
+    with _native(n) as nat:
+        nat.accumulateDense(X)
+        nat.finalizeGram()
+        S = nat.getGram()
+        st = nat.stats()
+    assert st["gram_cta_group"] == cta_group
+    assert np.array_equal(S, oracle.np_similarity_dense(X))
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gram_c1_calls_vs_reference_loop(oracle, monkeypatch, cta_group):
+    """BASELINE configs[0]: 1092 samples x 8000 variants, through the RDD[Seq[Int]] entry point."""
+    _set_env(monkeypatch, cta_group)
+    n, nv = 1092, 8000
+    off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
+    want = oracle.c_similarity(n, off, idx, 4)
+    with _native(n) as nat:
+        nat.accumulateCalls(-1, off, idx)
+        nat.finalizeGram()
+        S = nat.getGram()
+    assert np.array_equal(S, want)
+    assert np.array_equal(S, S.T)
+    assert np.array_equal(np.diag(S), np.bincount(idx, minlength=n))
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gram_multi_window_and_ragged_k(oracle, monkeypatch, cta_group):
+    """Several L2 windows, K not a multiple of the 128-byte k-block, N not a multiple of the tile."""
+    _set_env(monkeypatch, cta_group, kb_window=8)
+    rng = np.random.default_rng(4)
+    n, nv = 777, 5003
+    X = (rng.random((n, nv)) < 0.25).astype(np.int8)
+    X[:, 100] = 0                       # an empty variant
+    X[5, :] = 0                         # a sample that never varies -> zero row/column must be present
+    with _native(n) as nat:
+        nat.accumulateDense(X[:, :3000])
+        nat.accumulateDense(X[:, 3000:])    # accumulation across calls
+        nat.finalizeGram()
+        S = nat.getGram()
+        st = nat.stats()
+    assert st["gram_resident"] == 1
+    assert np.array_equal(S, oracle.np_similarity_dense(X))
+    assert not S[5].any() and not S[:, 5].any()
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gram_stream_k_many_tiles(oracle, monkeypatch, cta_group):
+    """More tiles than workers (N = 5000): the non-resident, double-buffered stream-K path."""
+    _set_env(monkeypatch, cta_group)
+    rng = np.random.default_rng(5)
+    n, nv = 5000, 1500
+    X = (rng.random((n, nv)) < 0.2).astype(np.int8)
+    with _native(n) as nat:
+        nat.accumulateDense(X)
+        nat.finalizeGram()
+        S = nat.getGram()
+        st = nat.stats()
+    assert st["gram_resident"] == 0
+    Xf = X.astype(np.float32)
+    want = (Xf @ Xf.T).astype(np.int32)          # exact: counts < 2^24
+    assert np.array_equal(S, want)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gram_dosage_int8(oracle, monkeypatch, cta_group):
+    _set_env(monkeypatch, cta_group)
+    n, nv = 500, 2000
+    X = oracle.c_synth_dense(SEED, n, 0, nv, mode=1)
+    assert X.max() == 2
+    with _native(n) as nat:
+        nat.accumulateDense(X)
+        nat.finalizeGram()
+        S = nat.getGram()
+    assert np.array_equal(S, oracle.np_similarity_dense(X))
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gram_bf16(oracle, monkeypatch, cta_group):
+    _set_env(monkeypatch, cta_group)
+    from spark_examples_b200 import native
+    n, nv = 640, 3001
+    off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
+    want = oracle.c_similarity(n, off, idx, 2)
+    with _native(n, dtype=native.DTYPE_BF16) as nat:
+        nat.accumulateCalls(-1, off, idx)
+        nat.finalizeGram()
+        S = nat.getGram()
+    assert np.array_equal(S, want)
+
+
+def test_partition_commit_abort_exactly_once(oracle):
+    """Task retry semantics: an aborted partition leaves no trace, a committed one counts once."""
+    n, nv = 400, 1200
+    off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
+    nvk = len(off) - 1
+    half = nvk // 2
+    off_a, idx_a = off[: half + 1], idx[: off[half]]
+    off_b, idx_b = off[half:] - off[half], idx[off[half]:]
+    with _native(n) as nat:
+        nat.accumulateCalls(0, off_a, idx_a)
+        nat.accumulateCalls(1, off_b, idx_b)
+        nat.abort(1)                                  # task 1 failed ...
+        nat.accumulateCalls(1, off_b, idx_b)          # ... and was retried
+        nat.commit(0)
+        nat.commit(1)
+        nat.commit(7)                                 # empty partition: no-op
+        nat.finalizeGram()
+        S = nat.getGram()
+    assert np.array_equal(S, oracle.c_similarity(n, off, idx, 1))
+
+
+def test_uncommitted_partition_blocks_finalize(oracle):
+    from spark_examples_b200 import native
+    n = 64
+    off, idx = oracle.c_synth_calls(SEED, n, 0, 50)
+    with _native(n) as nat:
+        nat.accumulateCalls(3, off, idx)
+        with pytest.raises(native.VpcaError) as ei:
+            nat.finalizeGram()
+        assert ei.value.code == native.VPCA_ERR_STATE
+
+
+def test_index_out_of_range_is_an_error(oracle):
+    from spark_examples_b200 import native
+    n = 50
+    off = np.array([0, 2, 3], np.int64)
+    idx = np.array([1, 50, 2], np.int32)               # 50 == n: the reference throws (VariantsPca.scala:188)
+    with _native(n) as nat:
+        with pytest.raises(IndexError):
+            nat.accumulateCalls(-1, off, idx)
+        with pytest.raises(native.IndexOutOfRange):
+            nat.accumulateCalls(5, off, np.array([1, -1, 2], np.int32))
+
+
+def test_empty_and_degenerate_inputs(oracle):
+    n = 40
+    with _native(n) as nat:
+        nat.accumulateCalls(-1, np.zeros(1, np.int64), np.zeros(0, np.int32))      # no rows
+        nat.accumulateCalls(-1, np.array([0, 0, 0], np.int64), np.zeros(0, np.int32))  # two empty rows
+        nat.accumulateCalls(-1, np.array([0, 1], np.int64), np.array([7], np.int32))   # a singleton
+        nat.finalizeGram()
+        S = nat.getGram()
+    want = np.zeros((n, n), np.int32)
+    want[7, 7] = 1
+    assert np.array_equal(S, want)
+
+
+def test_synth_device_matches_oracle_generator(oracle):
+    import torch
+    n, v0, nv = 333, 12345, 1003
+    for mode in (0, 1):
+        want = oracle.c_synth_dense(SEED, n, v0, nv, mode)
+        ld = 1008
+        buf = torch.zeros((n, ld), dtype=torch.int8, device="cuda")
+        with _native(n) as nat:
+            nat.synthDenseDevice(SEED, v0, nv, mode, buf.data_ptr(), ld)
+            torch.cuda.synchronize()
+        got = buf.cpu().numpy()
+        assert np.array_equal(got[:, :nv], want)
+        assert not got[:, nv:].any()
+
+
+def test_resident_device_tile_full_properties(oracle):
+    """Device-resident input at a size the O(N^2 V) oracle loop would not finish quickly: check the
+    size-independent properties of SURVEY 8d (symmetry, diag = carrier counts, S.1 = X (X^T 1)) and
+    bit-exactness on a random 4096-variant slice."""
+    import torch
+    n, nv = 2504, 200_000
+    ld = nv
+    X = torch.empty((n, ld), dtype=torch.int8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    with _native(n, stream=stream, max_multiplicity=1) as nat:
+        nat.synthDenseDevice(SEED, 0, nv, 0, X.data_ptr(), ld)
+        nat.accumulateDenseDevice(X.data_ptr(), nv, ld)
+        nat.finalizeGram()
+        S = nat.getGram()
+    Xi = X.to(torch.int32)
+    carriers = Xi.sum(dim=1).cpu().numpy()
+    col = Xi.sum(dim=0).to(torch.float64)
+    s1 = (X.to(torch.float64) @ col).cpu().numpy()
+    assert np.array_equal(S, S.T)
+    assert np.array_equal(np.diag(S), carriers)
+    assert np.array_equal(S.sum(axis=1).astype(np.float64), s1)
+    # slice parity through a fresh context on a 16-byte aligned column offset
+    v0 = 77_776
+    sl = oracle.c_synth_dense(SEED, n, v0, 4096, 0)
+    with _native(n, stream=stream) as nat3:
+        nat3.accumulateDenseDevice(X.data_ptr() + v0, 4096, ld)
+        nat3.finalizeGram()
+        S3 = nat3.getGram()
+    assert np.array_equal(S3, oracle.np_similarity_dense(sl))
