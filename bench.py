@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- genotype-cells/s (N x V) into the Gram on B200, the metric BASELINE.json names.
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU algorithm (oracle port)
+
+Workload (config.workload): BASELINE.json configs[1] -- 2504 samples x 1 M variants, int8 binary carrier encoding,
+per GPU (weak scaling: every rank owns `--variants-per-gpu` variants; 8 ranks x 5 M is configs[2]).  Synthetic
+Balding-Nichols-like cohort generated on the device (DESIGN.md "Synthetic generator").
+
+A step = one pass of the hot path over the rank's resident genotype matrix:
+    zero S -> tcgen05 Gram kernel over all V variants -> [N > 1: one NCCL all-reduce of S] -> symmetrize.
+`value`  = N_samples * V_total * steps / time, inputs resident in HBM (X is 2.5 GB per rank, far larger than the
+           126 MB L2, so no flush is needed between iterations), CUDA-event timed, max over ranks.
+`e2e`    = the same metric through the public API with HOST inputs: pinned RDD[Seq[Int]] rows (CSR) -> H2D ->
+           device encode -> Gram -> centering -> eigensolve -> top-2 PCs back on the host, every step.
+`roofline` = the Gram kernel alone against the tensor-core peak (int8 peak taken as 2 x the measured bf16 figure of
+           MEASURED_PEAKS.json); numerator = SYRK-minimal ops N (N+1) V.
+`cpu_baseline` = the oracle's restatement of VariantsPca.scala:182-191 timed on this box's host cores on a bounded
+           sample (rank 0, N = 1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+N_SAMPLES = 2504
+SEED = 20240901
+METRIC = "genotype-cells/sec (N x V) into Gram"
+UNIT = "cells/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--samples", type=int, default=N_SAMPLES)
+    ap.add_argument("--variants-per-gpu", type=int, default=1_000_000)
+    ap.add_argument("--dtype", choices=["i8", "bf16"], default="i8")
+    ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 5); 0 disables the e2e leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eig-check", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per bounded sample")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_tflops": float(d.get("bf16_tflops", 1590.0)),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", 1400.0)),
+                "hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock, power and throttle reasons through NVML (what nvidia-smi reads) while a region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self._halt = threading.Event()
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._halt.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((mhz, pw))
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        mhz = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(mhz), "power_w_max": max(s[1] for s in self.samples)}
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def cpu_similarity_sample(n, seconds, threads=None):
+    """Time the oracle's getSimilarityMatrix restatement on a bounded sample; returns (cells/s, info)."""
+    from oracle import oracle
+    oracle.build()
+    threads = threads or oracle.c_num_threads()
+    probe = 64
+    off, idx = oracle.c_synth_calls(SEED, n, 0, probe)
+    t0 = time.perf_counter()
+    oracle.c_similarity(n, off, idx, threads)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    per_variant = dt / probe
+    nv = int(max(threads * 8, min(200_000, seconds / per_variant)))
+    off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
+    t0 = time.perf_counter()
+    S = oracle.c_similarity(n, off, idx, threads)
+    dt = time.perf_counter() - t0
+    return n * nv / dt, {"variants": nv, "seconds": dt, "threads": threads, "checksum": int(S.trace())}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    oracle.build()
+    n = args.samples
+    threads = oracle.c_num_threads()
+    per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    vals, nvs = [], []
+    for i in range(args.warmup + args.steps):
+        v, info = cpu_similarity_sample(n, per_step, threads)
+        if i >= args.warmup:
+            vals.append(v)
+            nvs.append(info["variants"])
+    total_cells = sum(n * nv for nv in nvs)
+    total_time = sum(n * nv / v for nv, v in zip(nvs, vals))
+    value = total_cells / total_time
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_time / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"{n} samples x {args.variants_per_gpu} variants per GPU (BASELINE configs[1]); each "
+                               f"step is a bounded sample of {nvs[-1]} variants of that cohort",
+                   "samples": n, "variants_per_gpu": args.variants_per_gpu},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{nvs[-1]} variants x {n} samples per step, oracle/vpca_oracle.c vo_similarity "
+                                   f"(VariantsPca.scala:182-191 restated; Spark/JVM not runnable here), OpenMP "
+                                   f"{threads} threads; Gram only"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ b200 arm
+def build_host_calls(torch, X, nv, chunk=50_000):
+    """Pinned-host RDD[Seq[Int]] rows (CSR) of the device-resident binary matrix X[:, :nv] (setup, untimed)."""
+    n = X.shape[0]
+    counts = torch.empty(nv, dtype=torch.int64, device=X.device)
+    for c0 in range(0, nv, chunk):
+        c1 = min(nv, c0 + chunk)
+        counts[c0:c1] = X[:, c0:c1].to(torch.int32).sum(dim=0)
+    off = torch.zeros(nv + 1, dtype=torch.int64, device=X.device)
+    off[1:] = torch.cumsum(counts, 0)
+    nnz = int(off[-1].item())
+    off_h = torch.empty(nv + 1, dtype=torch.int64, pin_memory=True)
+    off_h.copy_(off)
+    idx_h = torch.empty(max(nnz, 1), dtype=torch.int32, pin_memory=True)
+    pos = 0
+    for c0 in range(0, nv, chunk):
+        c1 = min(nv, c0 + chunk)
+        nz = torch.nonzero(X[:, c0:c1].t().contiguous())          # sorted by variant, then sample
+        m = nz.shape[0]
+        idx_h[pos:pos + m].copy_(nz[:, 1].to(torch.int32))
+        pos += m
+        del nz
+    assert pos == nnz
+    torch.cuda.synchronize()
+    return off_h, idx_h, nnz
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from spark_examples_b200 import native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, vpg = args.samples, args.variants_per_gpu
+    dtype = native.DTYPE_I8 if args.dtype == "i8" else native.DTYPE_BF16
+    eb = 1 if args.dtype == "i8" else 2
+    tdtype = torch.int8 if eb == 1 else torch.bfloat16
+    ld = ((vpg + 127) // 128) * 128
+    peaks = load_peaks()
+
+    # a non-default torch stream: libvpca orders all its work on it (a NULL handle would mean "private stream"),
+    # so torch.cuda.Event timing, NCCL collectives and the library's kernels share one queue
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    S = torch.zeros((n, n), dtype=torch.int32, device=dev)
+    nat = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=S.data_ptr(), max_multiplicity=1)
+    X = torch.empty((n, ld), dtype=tdtype, device=dev)
+    nat.synthDenseDevice(SEED, rank * vpg, vpg, 0, X.data_ptr(), ld)
+    torch.cuda.synchronize()
+
+    def step():
+        nat.reset()
+        nat.accumulateDenseDevice(X.data_ptr(), vpg, ld)
+        if world > 1:
+            dist.all_reduce(S)                 # reduceByKey(_ + _) (VariantsPca.scala:190) = one NCCL all-reduce
+        nat.finalizeGram()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    st0 = nat.stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    st1 = nat.stats()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n * vpg * world * args.steps / (ms * 1e-3)
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+
+    # ---- Gram kernel alone (roofline numerator / denominator) ----
+    kt = []
+    for _ in range(max(5, min(args.steps, 20))):
+        nat.reset()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        nat.accumulateDenseDevice(X.data_ptr(), vpg, ld)
+        b.record()
+        b.synchronize()
+        kt.append(a.elapsed_time(b))
+    kernel_ms = sum(kt) / len(kt)
+    ops = float(n) * (n + 1) * vpg                       # SYRK-minimal ops per launch
+    achieved_tops = ops / (kernel_ms * 1e-3) / 1e12
+    peak = 2.0 * peaks["bf16_tflops"] if eb == 1 else peaks["bf16_tflops"]
+    traffic = None
+    tp = ROOT / "profiles" / "gram_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved_tops / peak, "traffic": traffic,
+                "kernel": "gram_kernel<cta_group=%d>" % st1["gram_cta_group"], "kernel_ms": kernel_ms,
+                "ops_per_launch": ops, "ops_definition": "SYRK-minimal N(N+1)V (int8 MAC = 2 ops)",
+                "peak_source": ("2 x %s bf16 burst TFLOP/s of MEASURED_PEAKS.json (int8 dense = 2 x bf16 nominal)"
+                                if eb == 1 else "%s bf16 burst TFLOP/s of MEASURED_PEAKS.json") % peaks["source"],
+                "hbm_gbs_algorithmic": (n * vpg * eb + 4.0 * n * n) / (kernel_ms * 1e-3) / 1e9,
+                "hbm_peak_gbs": peaks["hbm_gbs"]}
+
+    # ---- size-independent parity properties + full-size eigenvector check (untimed) ----
+    checks = {}
+    step()
+    torch.cuda.synchronize()
+    checks["gram_symmetric"] = bool(torch.equal(S, S.t()))
+    if world == 1:
+        carriers = torch.zeros(n, dtype=torch.int64, device=dev)
+        colsum = torch.zeros(vpg, dtype=torch.float64, device=dev)
+        for c0 in range(0, vpg, 100_000):
+            c1 = min(vpg, c0 + 100_000)
+            blk = X[:, c0:c1].to(torch.int32)
+            carriers += blk.sum(dim=1)
+            colsum[c0:c1] = blk.sum(dim=0).to(torch.float64)
+        checks["diag_equals_carrier_counts"] = bool(torch.equal(torch.diagonal(S).to(torch.int64), carriers))
+        s1 = torch.zeros(n, dtype=torch.float64, device=dev)
+        for c0 in range(0, vpg, 100_000):
+            c1 = min(vpg, c0 + 100_000)
+            s1 += X[:, c0:c1].to(torch.float64) @ colsum[c0:c1]
+        checks["S_times_ones_equals_X_Xt1"] = bool(torch.equal(S.sum(dim=1).to(torch.float64), s1))
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    vecs, evals, nz = nat.computePca(2)
+    ee1.record()
+    ee1.synchronize()
+    eig_ms = ee0.elapsed_time(ee1)
+    if not args.no_eig_check and rank == 0:
+        Sd = S.to(torch.float64)
+        rs = Sd.sum(dim=1)
+        C = Sd - (rs / n)[:, None] - (rs / n)[None, :] + rs.sum() / n / n
+        w, V = torch.linalg.eigh(C)                       # library checker, not the product path
+        Vt = V[:, [-1, -2]].cpu().numpy()
+        for c in range(2):
+            i = int(np.argmax(np.abs(Vt[:, c])))
+            if Vt[i, c] < 0:
+                Vt[:, c] = -Vt[:, c]
+        err = np.max(np.abs(vecs - Vt), axis=0) / np.max(np.abs(Vt), axis=0)
+        checks["eigvec_max_rel_err_vs_torch_eigh"] = float(err.max())
+        checks["eigval_rel_err_vs_torch_eigh"] = float(np.max(np.abs(evals - w[[-1, -2]].cpu().numpy()) / abs(float(w[-1]))))
+
+    # ---- end to end through the public API with host inputs ----
+    e2e = None
+    e2e_steps = args.e2e_steps if args.e2e_steps >= 0 else min(args.steps, 5)
+    if e2e_steps > 0:
+        if eb != 1:
+            Xb = (X.to(torch.float32) > 0).to(torch.int8)
+        else:
+            Xb = X
+        off_h, idx_h, nnz = build_host_calls(torch, Xb, vpg)
+        S2 = torch.zeros((n, n), dtype=torch.int32, device=dev)
+        nat2 = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=S2.data_ptr(),
+                                max_multiplicity=1)
+
+        def e2e_step():
+            nat2.reset()
+            nat2.accumulateCallsRaw(-1, off_h.data_ptr(), idx_h.data_ptr(), vpg)     # H2D + encode + Gram
+            if world > 1:
+                dist.all_reduce(S2)
+            nat2.finalizeGram()
+            return nat2.computePca(2)                                                # center + eig + D2H of the PCs
+
+        e2e_step()
+        barrier()
+        s20 = nat2.stats()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(e2e_steps):
+            pcs = e2e_step()
+        b.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        s21 = nat2.stats()
+        ems = max(a.elapsed_time(b), 0.0)
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": n * vpg * world * e2e_steps / (ems * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": (s21["h2d_bytes"] - s20["h2d_bytes"]) // e2e_steps,
+               "d2h_bytes_per_step": (s21["d2h_bytes"] - s20["d2h_bytes"]) // e2e_steps,
+               "steps": e2e_steps, "ms_per_step": ems / e2e_steps, "wall_ms_per_step": 1e3 * wall / e2e_steps,
+               "includes": "pinned host CSR rows -> H2D -> encode -> Gram -> centering -> eigensolve -> PCs on host",
+               "nnz": nnz, "pcs_match_resident_path": bool(np.allclose(pcs[0], vecs, atol=1e-9))}
+        nat2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, info = cpu_similarity_sample(n, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": info["threads"], "kind": "port",
+               "sample": f"{info['variants']} variants x {n} samples ({info['seconds']:.1f} s), oracle/vpca_oracle.c "
+                         f"vo_similarity = VariantsPca.scala:182-191 restated, OpenMP; Gram only"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8" if eb == 1 else "bf16", "data": "synthetic",
+            "config": {"workload": f"{n} samples x {vpg} variants per GPU ({vpg * world} total), "
+                                   f"{'int8' if eb == 1 else 'bf16'} binary carrier genotypes, Gram"
+                                   f"{' + NCCL all-reduce' if world > 1 else ''} + symmetrize "
+                                   "(BASELINE configs[1] per GPU; 8 x 5M is configs[2])",
+                       "samples": n, "variants_per_gpu": vpg, "parallelism": f"variant-sharded x{world}",
+                       "l2_policy": "input (2.5 GB per rank) larger than L2; no flush between iterations"},
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+            "eig_ms": eig_ms, "checks": checks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    nat.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
