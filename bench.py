@@ -123,18 +123,30 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------- reference arm
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm must not obey that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_similarity_sample(n, seconds, threads=None):
-    """Time the oracle's getSimilarityMatrix restatement on a bounded sample; returns (cells/s, info)."""
+    """Time the oracle's getSimilarityMatrix restatement on a bounded sample; returns (cells/s, info).
+    One dense int32 N x N per thread = per Spark partition (VariantsPca.scala:185), summed at the end (:190)."""
     from oracle import oracle
     oracle.build()
-    threads = threads or oracle.c_num_threads()
-    probe = 64
-    off, idx = oracle.c_synth_calls(SEED, n, 0, probe)
-    t0 = time.perf_counter()
-    oracle.c_similarity(n, off, idx, threads)
-    dt = max(time.perf_counter() - t0, 1e-4)
-    per_variant = dt / probe
-    nv = int(max(threads * 8, min(200_000, seconds / per_variant)))
+    threads = threads or host_threads()
+    # two probes separate the fixed cost (allocating and summing `threads` matrices) from the per-variant cost
+    times = []
+    for probe in (threads * 2, threads * 10):
+        off, idx = oracle.c_synth_calls(SEED, n, 0, probe)
+        t0 = time.perf_counter()
+        oracle.c_similarity(n, off, idx, threads)
+        times.append((probe, time.perf_counter() - t0))
+    per_variant = max((times[1][1] - times[0][1]) / (times[1][0] - times[0][0]), 1e-7)
+    fixed = max(times[0][1] - per_variant * times[0][0], 0.0)
+    nv = int(max(threads * 8, min(400_000, (seconds - fixed) / per_variant)))
     off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
     t0 = time.perf_counter()
     S = oracle.c_similarity(n, off, idx, threads)
@@ -149,7 +161,7 @@ def run_reference(args):
     from oracle import oracle
     oracle.build()
     n = args.samples
-    threads = oracle.c_num_threads()
+    threads = host_threads()
     per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
     vals, nvs = [], []
     for i in range(args.warmup + args.steps):

@@ -96,7 +96,7 @@ int vo_similarity(int32_t n, int64_t nv, const int64_t *off, const int32_t *idx,
         }
     }
     /* reduceByKey(_ + _) :190 */
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(n_partitions)
     for (int64_t i = 0; i < (int64_t)nn; ++i) {
         int32_t acc = 0;
         for (int p = 0; p < n_partitions; ++p) acc += part[p][i];

@@ -362,6 +362,9 @@ def main(args: Optional[Sequence[str]] = None):
     driver.emitResult(result)
     driver.reportIoStats()
     driver.stop()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
