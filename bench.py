@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--samples", type=int, default=N_SAMPLES)
     ap.add_argument("--variants-per-gpu", type=int, default=1_000_000)
-    ap.add_argument("--dtype", choices=["i8", "bf16"], default="i8")
+    ap.add_argument("--dtype", choices=["i8", "bf16", "e2m1"], default="i8")
+    ap.add_argument("--no-alt", action="store_true", help="skip the packed-e2m1 comparison leg")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 5); 0 disables the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eig-check", action="store_true")
@@ -137,20 +138,17 @@ def cpu_similarity_sample(n, seconds, threads=None):
     from oracle import oracle
     oracle.build()
     threads = threads or host_threads()
-    # two probes separate the fixed cost (allocating and summing `threads` matrices) from the per-variant cost
-    times = []
-    for probe in (threads * 2, threads * 10):
-        off, idx = oracle.c_synth_calls(SEED, n, 0, probe)
+    # grow the sample geometrically until one pass costs about `seconds` (the fixed cost of allocating and summing
+    # `threads` dense matrices makes small probes useless for extrapolation on many-core hosts)
+    nv, dt = threads * 4, 0.0
+    while True:
+        off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
         t0 = time.perf_counter()
-        oracle.c_similarity(n, off, idx, threads)
-        times.append((probe, time.perf_counter() - t0))
-    per_variant = max((times[1][1] - times[0][1]) / (times[1][0] - times[0][0]), 1e-7)
-    fixed = max(times[0][1] - per_variant * times[0][0], 0.0)
-    nv = int(max(threads * 8, min(400_000, (seconds - fixed) / per_variant)))
-    off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
-    t0 = time.perf_counter()
-    S = oracle.c_similarity(n, off, idx, threads)
-    dt = time.perf_counter() - t0
+        S = oracle.c_similarity(n, off, idx, threads)
+        dt = time.perf_counter() - t0
+        if dt >= 0.5 * seconds or nv >= 200_000:
+            break
+        nv = int(min(200_000, max(nv * 2, nv * min(8.0, 0.8 * seconds / max(dt, 1e-3)))))
     return n * nv / dt, {"variants": nv, "seconds": dt, "threads": threads, "checksum": int(S.trace())}
 
 
@@ -190,14 +188,14 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ b200 arm
-def build_host_calls(torch, X, nv, chunk=50_000):
-    """Pinned-host RDD[Seq[Int]] rows (CSR) of the device-resident binary matrix X[:, :nv] (setup, untimed)."""
-    n = X.shape[0]
-    counts = torch.empty(nv, dtype=torch.int64, device=X.device)
+def build_host_calls(torch, cells, n, nv, dev, chunk=50_000):
+    """Pinned-host RDD[Seq[Int]] rows (CSR) of the device-resident binary matrix (setup, untimed).
+    `cells(c0, c1)` returns the int32 carrier block of variants [c0, c1)."""
+    counts = torch.empty(nv, dtype=torch.int64, device=dev)
     for c0 in range(0, nv, chunk):
         c1 = min(nv, c0 + chunk)
-        counts[c0:c1] = X[:, c0:c1].to(torch.int32).sum(dim=0)
-    off = torch.zeros(nv + 1, dtype=torch.int64, device=X.device)
+        counts[c0:c1] = cells(c0, c1).sum(dim=0)
+    off = torch.zeros(nv + 1, dtype=torch.int64, device=dev)
     off[1:] = torch.cumsum(counts, 0)
     nnz = int(off[-1].item())
     off_h = torch.empty(nv + 1, dtype=torch.int64, pin_memory=True)
@@ -206,7 +204,7 @@ def build_host_calls(torch, X, nv, chunk=50_000):
     pos = 0
     for c0 in range(0, nv, chunk):
         c1 = min(nv, c0 + chunk)
-        nz = torch.nonzero(X[:, c0:c1].t().contiguous())          # sorted by variant, then sample
+        nz = torch.nonzero(cells(c0, c1).t().contiguous())        # sorted by variant, then sample
         m = nz.shape[0]
         idx_h[pos:pos + m].copy_(nz[:, 1].to(torch.int32))
         pos += m
@@ -232,9 +230,10 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, vpg = args.samples, args.variants_per_gpu
-    dtype = native.DTYPE_I8 if args.dtype == "i8" else native.DTYPE_BF16
-    eb = 1 if args.dtype == "i8" else 2
-    tdtype = torch.int8 if eb == 1 else torch.bfloat16
+    dtype = {"i8": native.DTYPE_I8, "bf16": native.DTYPE_BF16, "e2m1": native.DTYPE_E2M1}[args.dtype]
+    eb = {"i8": 1, "bf16": 2, "e2m1": 0.5}[args.dtype]
+    tdtype = {"i8": torch.int8, "bf16": torch.bfloat16, "e2m1": torch.uint8}[args.dtype]
+    dname = {"i8": "int8", "bf16": "bf16", "e2m1": "e2m1 (4-bit packed cells, fp32 tensor accumulation, exact)"}[args.dtype]
     ld = ((vpg + 127) // 128) * 128
     peaks = load_peaks()
 
@@ -246,7 +245,7 @@ def run_b200(args):
     assert stream != 0
     S = torch.zeros((n, n), dtype=torch.int32, device=dev)
     nat = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=S.data_ptr(), max_multiplicity=1)
-    X = torch.empty((n, ld), dtype=tdtype, device=dev)
+    X = torch.empty((n, ld // 2 if args.dtype == "e2m1" else ld), dtype=tdtype, device=dev)
     nat.synthDenseDevice(SEED, rank * vpg, vpg, 0, X.data_ptr(), ld)
     torch.cuda.synchronize()
 
@@ -297,20 +296,21 @@ def run_b200(args):
     kernel_ms = sum(kt) / len(kt)
     ops = float(n) * (n + 1) * vpg                       # SYRK-minimal ops per launch
     achieved_tops = ops / (kernel_ms * 1e-3) / 1e12
-    peak = 2.0 * peaks["bf16_tflops"] if eb == 1 else peaks["bf16_tflops"]
+    peak = peaks["bf16_tflops"] if args.dtype == "bf16" else 2.0 * peaks["bf16_tflops"]
     traffic = None
     tp = ROOT / "profiles" / "gram_traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(tp.read_text())
+            traffic = (tj.get("e2m1", {}) if args.dtype == "e2m1" else tj).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved_tops / peak, "traffic": traffic,
                 "kernel": "gram_kernel<cta_group=%d>" % st1["gram_cta_group"], "kernel_ms": kernel_ms,
                 "ops_per_launch": ops, "ops_definition": "SYRK-minimal N(N+1)V (int8 MAC = 2 ops)",
-                "peak_source": ("2 x %s bf16 burst TFLOP/s of MEASURED_PEAKS.json (int8 dense = 2 x bf16 nominal)"
-                                if eb == 1 else "%s bf16 burst TFLOP/s of MEASURED_PEAKS.json") % peaks["source"],
+                "peak_source": ("2 x %s bf16 burst TFLOP/s of MEASURED_PEAKS.json (int8 / fp8-path dense = 2 x bf16 nominal)"
+                                if args.dtype != "bf16" else "%s bf16 burst TFLOP/s of MEASURED_PEAKS.json") % peaks["source"],
                 "hbm_gbs_algorithmic": (n * vpg * eb + 4.0 * n * n) / (kernel_ms * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
 
@@ -319,19 +319,29 @@ def run_b200(args):
     step()
     torch.cuda.synchronize()
     checks["gram_symmetric"] = bool(torch.equal(S, S.t()))
+    def cells(c0, c1):
+        """binary carrier block X[:, c0:c1] as int32, whatever the storage dtype"""
+        if args.dtype == "e2m1":
+            b = X[:, c0 // 2:c1 // 2]
+            out = torch.empty((n, c1 - c0), dtype=torch.int32, device=dev)
+            out[:, 0::2] = ((b & 0x0F) != 0).to(torch.int32)
+            out[:, 1::2] = ((b >> 4) != 0).to(torch.int32)
+            return out
+        return (X[:, c0:c1].to(torch.float32) > 0).to(torch.int32)
+
     if world == 1:
         carriers = torch.zeros(n, dtype=torch.int64, device=dev)
         colsum = torch.zeros(vpg, dtype=torch.float64, device=dev)
         for c0 in range(0, vpg, 100_000):
             c1 = min(vpg, c0 + 100_000)
-            blk = X[:, c0:c1].to(torch.int32)
+            blk = cells(c0, c1)
             carriers += blk.sum(dim=1)
             colsum[c0:c1] = blk.sum(dim=0).to(torch.float64)
         checks["diag_equals_carrier_counts"] = bool(torch.equal(torch.diagonal(S).to(torch.int64), carriers))
         s1 = torch.zeros(n, dtype=torch.float64, device=dev)
         for c0 in range(0, vpg, 100_000):
             c1 = min(vpg, c0 + 100_000)
-            s1 += X[:, c0:c1].to(torch.float64) @ colsum[c0:c1]
+            s1 += cells(c0, c1).to(torch.float64) @ colsum[c0:c1]
         checks["S_times_ones_equals_X_Xt1"] = bool(torch.equal(S.sum(dim=1).to(torch.float64), s1))
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record()
@@ -357,11 +367,7 @@ def run_b200(args):
     e2e = None
     e2e_steps = args.e2e_steps if args.e2e_steps >= 0 else min(args.steps, 5)
     if e2e_steps > 0:
-        if eb != 1:
-            Xb = (X.to(torch.float32) > 0).to(torch.int8)
-        else:
-            Xb = X
-        off_h, idx_h, nnz = build_host_calls(torch, Xb, vpg)
+        off_h, idx_h, nnz = build_host_calls(torch, cells, n, vpg, dev)
         S2 = torch.zeros((n, n), dtype=torch.int32, device=dev)
         nat2 = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=S2.data_ptr(),
                                 max_multiplicity=1)
@@ -399,6 +405,33 @@ def run_b200(args):
                "nnz": nnz, "pcs_match_resident_path": bool(np.allclose(pcs[0], vecs, atol=1e-9))}
         nat2.close()
 
+    # ---- comparison leg: the same cohort stored as packed 4-bit e2m1 cells (exact; half the bytes per cell) ----
+    alt = None
+    if args.dtype == "i8" and not args.no_alt:
+        S4 = torch.zeros((n, n), dtype=torch.int32, device=dev)
+        X4 = torch.empty((n, ld // 2), dtype=torch.uint8, device=dev)
+        with native.NativePca(n, device=local_rank, dtype=native.DTYPE_E2M1, stream=stream, d_gram=S4.data_ptr(),
+                              max_multiplicity=1) as nat4:
+            nat4.synthDenseDevice(SEED, rank * vpg, vpg, 0, X4.data_ptr(), ld)
+            t4 = []
+            for _ in range(max(5, min(args.steps, 20)) + 2):
+                nat4.reset()
+                a4, b4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a4.record()
+                nat4.accumulateDenseDevice(X4.data_ptr(), vpg, ld)
+                b4.record()
+                b4.synchronize()
+                t4.append(a4.elapsed_time(b4))
+            t4 = t4[2:]
+            ms4 = sum(t4) / len(t4)
+            nat4.finalizeGram()
+            torch.cuda.synchronize()
+            alt = {"dtype": "e2m1 (4-bit packed cells in HBM, tcgen05 kind::f8f6f4, fp32 accumulation flushed to int32)",
+                   "kernel_ms": ms4, "cells_per_s_kernel": n * vpg / (ms4 * 1e-3),
+                   "achieved_tflops_syrk": ops / (ms4 * 1e-3) / 1e12, "frac_of_2x_bf16_peak": ops / (ms4 * 1e-3) / 1e12 / (2.0 * peaks["bf16_tflops"]),
+                   "gram_bit_identical_to_int8_path": bool(torch.equal(S4, S)) if world == 1 else None}
+        del X4, S4
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, info = cpu_similarity_sample(n, args.cpu_seconds)
@@ -410,16 +443,18 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int8" if eb == 1 else "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": dname, "data": "synthetic",
             "config": {"workload": f"{n} samples x {vpg} variants per GPU ({vpg * world} total), "
-                                   f"{'int8' if eb == 1 else 'bf16'} binary carrier genotypes, Gram"
+                                   f"{dname} binary carrier genotypes, Gram"
                                    f"{' + NCCL all-reduce' if world > 1 else ''} + symmetrize "
                                    "(BASELINE configs[1] per GPU; 8 x 5M is configs[2])",
                        "samples": n, "variants_per_gpu": vpg, "parallelism": f"variant-sharded x{world}",
-                       "l2_policy": "input (2.5 GB per rank) larger than L2; no flush between iterations"},
+                       "l2_policy": f"input ({n * vpg * eb / 1e9:.2f} GB per rank) larger than L2; no flush between iterations"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
             "eig_ms": eig_ms, "checks": checks,
         }
+        if alt is not None:
+            line["packed_e2m1"] = alt
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:

@@ -47,8 +47,13 @@ typedef enum vpca_status {
 
 typedef enum vpca_dtype {
     VPCA_DTYPE_I8 = 0,  /* int8 genotype encoding, tcgen05 kind::i8, exact int32 accumulation   */
-    VPCA_DTYPE_BF16 = 1 /* bf16 genotype encoding, tcgen05 kind::f16, fp32 TMEM accumulation flushed
-                           into the int32 Gram before 2^24 could be reached (exact)              */
+    VPCA_DTYPE_BF16 = 1, /* bf16 genotype encoding, tcgen05 kind::f16, fp32 TMEM accumulation flushed
+                            into the int32 Gram before 2^24 could be reached (exact)              */
+    VPCA_DTYPE_E2M1 = 2  /* 4-bit e2m1 cells (0, 1, 2 exact), two per byte in HBM, expanded by TMA
+                            (16U4_ALIGN16B) on the way to shared memory; tcgen05 kind::f8f6f4 with
+                            fp32 accumulation, flushed like bf16 (exact).  Halves the HBM/L2 bytes
+                            per cell; dense tiles need ld % 128 == 0, 32-byte alignment and zero
+                            cells up to the next multiple of 128 variants; max_multiplicity <= 2.   */
 } vpca_dtype;
 
 typedef struct vpca_ctx vpca_ctx;
@@ -157,6 +162,10 @@ typedef struct vpca_stats {
     int32_t gram_resident;        /* 1 when the last launch kept accumulators in TMEM for the whole K loop */
 } vpca_stats;
 int vpca_get_stats(vpca_ctx* ctx, vpca_stats* out);
+/* Diagnostic (set VPCA_GRAM_PROF=1 before the first Gram launch): per-CTA timestamps of the last Gram launch,
+ * 4 x int64 nanoseconds per CTA {start, -, last MMA issued, end}; returns the number of CTAs written (<= max_ctas)
+ * or a negative vpca_status.  Synchronises the stream. */
+int vpca_debug_gram_profile(vpca_ctx* ctx, int64_t* out, int32_t max_ctas);
 
 #ifdef __cplusplus
 }

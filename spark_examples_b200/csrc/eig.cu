@@ -102,15 +102,20 @@ __global__ void center_kernel(const int32_t* __restrict__ S, const double* __res
 //   (c) d[j] = A[j][j];  build the reflector that annihilates A[j][j+2..n):  v (v[j+1] = 1), tau, e[j] = beta;
 //       the reflector is kept in row j of A (for the back-transformation) and in `vcur`.
 // vprev/vcur/w/p are length-n vectors; scal[1] = tau_prev on entry, tau_j on exit.
-__global__ void __launch_bounds__(kSmallThreads) tridiag_small_kernel(double* __restrict__ A, int n, int j,
-                                                                       const double* __restrict__ vprev,
-                                                                       double* __restrict__ vcur,
+// The step index j lives in device memory (step[0] = next step, step[1] = step of the pending big kernel) so that
+// every launch of the step loop is identical and the loop can be replayed from one CUDA graph.
+__global__ void __launch_bounds__(kSmallThreads) tridiag_small_kernel(double* __restrict__ A, int n,
+                                                                       int* __restrict__ step, double* __restrict__ v2,
                                                                        const double* __restrict__ p,
                                                                        double* __restrict__ w, double* __restrict__ diag,
                                                                        double* __restrict__ off, double* __restrict__ tau,
                                                                        double* __restrict__ scal) {
     __shared__ double red[33];
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int j = step[0];
+    if (j >= n) return;
+    const double* vprev = v2 + (size_t)((j + 1) & 1) * n;
+    double* vcur = v2 + (size_t)(j & 1) * n;
     double* rowj = A + (size_t)j * n;
     if (j > 0) {
         const double tau_prev = tau[j - 1];
@@ -125,7 +130,13 @@ __global__ void __launch_bounds__(kSmallThreads) tridiag_small_kernel(double* __
         __syncthreads();
     }
     if (tid == 0) diag[j] = rowj[j];
-    if (j >= n - 1) return;
+    if (j >= n - 1) {
+        if (tid == 0) {
+            step[1] = j;
+            step[0] = j + 1;
+        }
+        return;
+    }
     // reflector from x = rowj[j+1 .. n)
     const double alpha = rowj[j + 1];
     double acc = 0.0;
@@ -153,20 +164,24 @@ __global__ void __launch_bounds__(kSmallThreads) tridiag_small_kernel(double* __
         off[j] = beta;
         tau[j] = tj;
         scal[1] = tj;
+        step[1] = j;
+        step[0] = j + 1;
     }
 }
 
 // Step j, grid-wide: for every trailing row i in [j+1, n) (one warp per row)
 //   A[i][t] -= vprev[i] w[t] + w[i] vprev[t]      (pending rank-2 update of step j-1),  t in [j+1, n)
 //   p[i]     = tau_j * sum_t A[i][t] vcur[t]      (symmetric matrix-vector product of step j, full rows)
-__global__ void __launch_bounds__(256) tridiag_big_kernel(double* __restrict__ A, int n, int j,
-                                                          const double* __restrict__ vprev,
-                                                          const double* __restrict__ w,
-                                                          const double* __restrict__ vcur, const double* __restrict__ tau,
+__global__ void __launch_bounds__(256) tridiag_big_kernel(double* __restrict__ A, int n, const int* __restrict__ step,
+                                                          const double* __restrict__ v2,
+                                                          const double* __restrict__ w, const double* __restrict__ tau,
                                                           double* __restrict__ p) {
     const int lane = threadIdx.x & 31;
+    const int j = step[1];
     const int i = j + 1 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
+    const double* vprev = v2 + (size_t)((j + 1) & 1) * n;
+    const double* vcur = v2 + (size_t)(j & 1) * n;
     const double tj = tau[j];
     double* row = A + (size_t)i * n;
     const double vi = vprev[i], wi = w[i];
@@ -468,6 +483,7 @@ cudaError_t eig_alloc(EigWork& w, int n, int kmax) {
     VPCA_TRY(cudaMalloc(&w.d_evecs, (size_t)n * kmax * sizeof(double)));
     VPCA_TRY(cudaMalloc(&w.d_lu, 8 * (size_t)n * sizeof(double)));
     VPCA_TRY(cudaMalloc(&w.d_nz, sizeof(int)));
+    VPCA_TRY(cudaMalloc(&w.d_step, 2 * sizeof(int)));
 #undef VPCA_TRY
     return cudaSuccess;
 }
@@ -475,7 +491,8 @@ cudaError_t eig_alloc(EigWork& w, int n, int kmax) {
 void eig_free(EigWork& w) {
     cudaFree(w.d_C); cudaFree(w.d_rowsum); cudaFree(w.d_v); cudaFree(w.d_w); cudaFree(w.d_p);
     cudaFree(w.d_diag); cudaFree(w.d_off); cudaFree(w.d_tau); cudaFree(w.d_scal); cudaFree(w.d_evals);
-    cudaFree(w.d_evecs); cudaFree(w.d_lu); cudaFree(w.d_nz);
+    cudaFree(w.d_evecs); cudaFree(w.d_lu); cudaFree(w.d_nz); cudaFree(w.d_step);
+    if (w.graph_exec != nullptr) cudaGraphExecDestroy(w.graph_exec);
     w = EigWork{};
 }
 
@@ -498,17 +515,33 @@ cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) 
     cudaMemsetAsync(w.d_tau, 0, (size_t)n * sizeof(double), stream);
     cudaMemsetAsync(w.d_off, 0, 2 * (size_t)n * sizeof(double), stream);
     int64_t nl = 0;
-    for (int j = 0; j < n; ++j) {
-        double* vprev = w.d_v + (size_t)((j + 1) & 1) * n;
-        double* vcur = w.d_v + (size_t)(j & 1) * n;
-        tridiag_small_kernel<<<1, kSmallThreads, 0, stream>>>(w.d_C, n, j, vprev, vcur, w.d_p, w.d_w, w.d_diag, w.d_off,
-                                                              w.d_tau, w.d_scal);
-        ++nl;
-        const int rows = n - 1 - j;
-        if (rows > 0) {
-            tridiag_big_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(w.d_C, n, j, vprev, w.d_w, vcur, w.d_tau, w.d_p);
-            ++nl;
+    cudaMemsetAsync(w.d_step, 0, 2 * sizeof(int), stream);
+    // One CUDA graph holds kGraphSteps identical (small, big) launch pairs; it is replayed until all n steps ran.
+    // Blocks of the big kernel beyond the shrinking trailing matrix exit at once, launches past step n are no-ops.
+    constexpr int kGraphSteps = 64;
+    const int big_blocks = (n - 1 + 7) / 8 > 0 ? (n - 1 + 7) / 8 : 1;
+    if (w.graph_exec == nullptr || w.graph_n != n) {
+        if (w.graph_exec != nullptr) cudaGraphExecDestroy(w.graph_exec);
+        w.graph_exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) return e;
+        for (int g = 0; g < kGraphSteps; ++g) {
+            tridiag_small_kernel<<<1, kSmallThreads, 0, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_p, w.d_w, w.d_diag, w.d_off,
+                                                                  w.d_tau, w.d_scal);
+            tridiag_big_kernel<<<big_blocks, 256, 0, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_w, w.d_tau, w.d_p);
         }
+        e = cudaStreamEndCapture(stream, &graph);
+        if (e != cudaSuccess) return e;
+        e = cudaGraphInstantiate(&w.graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return e;
+        w.graph_n = n;
+    }
+    for (int j = 0; j < n; j += kGraphSteps) {
+        e = cudaGraphLaunch(w.graph_exec, stream);
+        if (e != cudaSuccess) return e;
+        nl += 2 * kGraphSteps;
     }
     bisect_kernel<<<k, 256, 0, stream>>>(w.d_diag, w.d_off, n, w.d_off + n, w.d_evals, w.d_scal);
     const size_t invit_smem = 8 * (size_t)n * sizeof(double);

@@ -68,20 +68,50 @@ __global__ void encode_bf16_kernel(const int64_t* __restrict__ off, int64_t base
     if (bad) atomicOr(flags, bad);
 }
 
+// packed e2m1 cells: multiplicity m in {0, 1, 2} is the code 2 m (0b0000, 0b0010 = 1.0, 0b0100 = 2.0), so one
+// occurrence adds 2 to the nibble of cell (s, v); eight cells per 32-bit word.
+__global__ void encode_e2m1_kernel(const int64_t* __restrict__ off, int64_t base, const int32_t* __restrict__ idx,
+                                   int64_t nv, int n, int max_mult, uint32_t* __restrict__ xw, int64_t ld,
+                                   int* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int bad = 0;
+    for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nv; v += warps) {
+        const int64_t e0 = off[v] - base, e1 = off[v + 1] - base;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const int s = idx[e];
+            if (s < 0 || s >= n) {
+                bad |= 1;
+                continue;
+            }
+            const int64_t cell = (int64_t)s * ld + v;
+            const uint32_t shift = (uint32_t)(cell & 7) * 4u;
+            const uint32_t old = atomicAdd(xw + (cell >> 3), 2u << shift);
+            if ((int)((old >> shift) & 0xFu) >= 2 * max_mult) bad |= 2;
+        }
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
 }  // namespace
 
-cudaError_t encode_calls(const int64_t* d_off, int64_t base, const int32_t* d_idx, int64_t nv, int n, int elem_bytes,
+cudaError_t encode_calls(const int64_t* d_off, int64_t base, const int32_t* d_idx, int64_t nv, int n, int elem_bits,
                          int max_mult, void* d_x, int64_t ld, int* d_flags, cudaStream_t stream) {
-    // zero the nv columns (rounded up to the 128-byte k-block the Gram kernel reads) of every sample row
-    size_t width = (((size_t)nv * elem_bytes + 127) / 128) * 128;
-    if (width > (size_t)ld * elem_bytes) width = (size_t)ld * elem_bytes;
+    // zero the nv columns (rounded up to the k-block of 128 cells / 128 bytes the Gram kernel reads) of every row
+    const size_t pitch = (size_t)ld * elem_bits / 8;
+    size_t width = elem_bits == 4 ? (((size_t)nv + 127) / 128) * 64 : ((((size_t)nv * elem_bits / 8) + 127) / 128) * 128;
+    if (width > pitch) width = pitch;
     cudaError_t e = cudaSuccess;
-    if (width > 0) e = cudaMemset2DAsync(d_x, (size_t)ld * elem_bytes, 0, width, (size_t)n, stream);
+    if (width > 0) e = cudaMemset2DAsync(d_x, pitch, 0, width, (size_t)n, stream);
     if (e != cudaSuccess || nv <= 0) return e;
     const int threads = 256;
     const int64_t want = (nv * 32 + threads - 1) / threads;
     const int blocks = (int)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
-    if (elem_bytes == 1) {
+    if (elem_bits == 4) {
+        const int cap = max_mult > 2 ? 2 : max_mult;
+        encode_e2m1_kernel<<<blocks, threads, 0, stream>>>(d_off, base, d_idx, nv, n, cap, reinterpret_cast<uint32_t*>(d_x),
+                                                           ld, d_flags);
+    } else if (elem_bits == 8) {
         const int cap = max_mult > 127 ? 127 : max_mult;
         encode_i8_kernel<<<blocks, threads, 0, stream>>>(d_off, base, d_idx, nv, n, cap, reinterpret_cast<uint32_t*>(d_x), ld,
                                                          d_flags);

@@ -68,10 +68,16 @@ struct GramArgs {
     int num_workers;
     int resident;
     int elems_per_kb;  // 128 / sizeof(element)
+    int sync_lead;     // > 0: a worker may run at most this many windows ahead of the slowest one (soft barrier)
+    int active_workers;
+    int* win_done;     // win_done[w] = number of workers whose producer has issued every load of window w
+    long long* prof;   // optional per-CTA timestamps (globaltimer ns): start, first MMA, MMA done, end
+    int tx_shift;      // TMA transaction bytes per stage = STAGE_BYTES >> tx_shift (1 for packed 4-bit sources: the
+                       // mbarrier counts the 8 data bytes of every 16-byte shared-memory chunk, not the gap)
 };
 
 struct Seg {
-    int tile, kb0, kb1, slot, first, flush, use;
+    int tile, kb0, kb1, slot, first, flush, use, win, last_in_win;
 };
 
 // Every role of a worker (TMA producer, MMA issuer, epilogue) replays the same deterministic schedule.
@@ -110,6 +116,8 @@ struct Sched {
         s.tile = tile;
         s.kb0 = base + min(lo, cnt);
         s.kb1 = base + min(hi, cnt);
+        s.win = win;
+        s.last_in_win = (u >= u_end);
         if (resident) {
             s.slot = seg_in_win;
             s.first = (win == 0);
@@ -144,6 +152,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
 }
 
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Soft inter-worker barrier: wait (bounded) until `need` workers have finished issuing window `w`.  Purely a pacing
+// hint that keeps all workers inside the same few L2-resident windows of X; correctness never depends on it.
+__device__ __forceinline__ void wait_window(const int* win_done, int w, int need) {
+    const long long t0 = globaltimer_ns();
+    while (true) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(win_done + w) : "memory");
+        if (v >= need) return;
+        if (globaltimer_ns() - t0 > 200000) return;   // 200 us: give up (e.g. not all workers co-resident)
+        __nanosleep(256);
+    }
+}
+
 // K-major SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), one atom along K (LBO unused).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -152,10 +179,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 template <int CG, int KIND>
 __device__ __forceinline__ uint32_t make_instr_desc() {
     constexpr uint32_t M = 128 * CG, N = kUmmaN;
-    // c_format [4,6): 1 = F32, 2 = S32; a/b_format [7,10)/[10,13): i8 -> 1 (signed), f16 kind -> 1 (BF16);
-    // a/b major bits 15/16 = 0 (K-major); n_dim [17,23) = N >> 3; m_dim [24,29) = M >> 4.
+    // c_format [4,6): 1 = F32, 2 = S32; a/b_format [7,10)/[10,13): kind::i8 -> 1 (signed int8), kind::f16 -> 1 (BF16),
+    // kind::f8f6f4 -> 5 (E2M1); a/b major bits 15/16 = 0 (K-major); n_dim [17,23) = N >> 3; m_dim [24,29) = M >> 4.
     constexpr uint32_t cfmt = (KIND == 0) ? 2u : 1u;
-    return (cfmt << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+    constexpr uint32_t abfmt = (KIND == 2) ? 5u : 1u;
+    return (cfmt << 4) | (abfmt << 7) | (abfmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 template <int CG, int KIND>
@@ -203,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
     if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (a.prof != nullptr && threadIdx.x == 0) a.prof[(size_t)blockIdx.x * 4 + 0] = globaltimer_ns();
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -211,26 +240,33 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
             sc.init(a, worker);
             Seg s;
             uint32_t it = 0;
+            int synced_win = -1;
             while (sc.next(s)) {
                 const int2 t = a.tiles[s.tile];
                 const int rowA = t.x * C::BM + (int)cta_rank * kBoxRows;
                 const int rowB = t.y * C::BN + ((CG == 2) ? (int)cta_rank * kBoxRows : 0);
+                if (a.sync_lead > 0 && leader && s.win != synced_win) {
+                    synced_win = s.win;
+                    if (s.win >= a.sync_lead) wait_window(a.win_done, s.win - a.sync_lead, a.active_workers);
+                }
                 for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
                     const uint32_t st = it % C::STAGES, ph = (it / C::STAGES) & 1u;
                     mbar_wait(empty_bar(st), ph ^ 1u, a.err, 1);
                     const int kc = kb * a.elems_per_kb;
                     if constexpr (CG == 1) {
-                        ptx::mbar_arrive_expect_tx(full_bar(st), C::STAGE_BYTES);
+                        ptx::mbar_arrive_expect_tx(full_bar(st), (uint32_t)C::STAGE_BYTES >> a.tx_shift);
                         ptx::tma_load_2d(sA(st), &tmap, full_bar(st), kc, rowA);
                         ptx::tma_load_2d(sB(st), &tmap, full_bar(st), kc, rowB);
                         ptx::tma_load_2d(sB(st) + kBoxBytes, &tmap, full_bar(st), kc, rowB + kBoxRows);
                     } else {
                         ptx::tma_load_2d_2sm(sA(st), &tmap, full_bar(st), kc, rowA);
                         ptx::tma_load_2d_2sm(sB(st), &tmap, full_bar(st), kc, rowB);
-                        if (leader) ptx::mbar_arrive_expect_tx(full_bar(st), 2 * C::STAGE_BYTES);
+                        if (leader) ptx::mbar_arrive_expect_tx(full_bar(st), (uint32_t)(2 * C::STAGE_BYTES) >> a.tx_shift);
                         else ptx::mbar_arrive_cluster(full_bar(st), 0);
                     }
                 }
+                if (a.sync_lead > 0 && leader && s.last_in_win)
+                    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(a.win_done + s.win) : "memory");
             }
         }
     } else if (warp == 1 && leader) {
@@ -268,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                 __syncwarp();
             }
         }
+        if (a.prof != nullptr && issuer) a.prof[(size_t)blockIdx.x * 4 + 2] = globaltimer_ns();
     } else if (warp >= 4) {
         // ===================================== epilogue =========================================
         const int q = warp & 3;   // TMEM lane quarter this warp may read
@@ -313,6 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
     ptx::tc_fence_before();
     if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
     if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
+    if (a.prof != nullptr && threadIdx.x == 0) a.prof[(size_t)blockIdx.x * 4 + 3] = globaltimer_ns();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -385,9 +423,20 @@ cudaError_t launch(const CUtensorMap& tmap, const GramArgs& args, int grid, cuda
 void gram_plan_free(GramPlan& plan) {
     if (plan.d_tiles) cudaFree(plan.d_tiles);
     if (plan.d_err) cudaFreeHost(plan.d_err);
+    if (plan.d_win_done) cudaFree(plan.d_win_done);
+    if (plan.d_prof) cudaFree(plan.d_prof);
+    plan.d_win_done = nullptr;
+    plan.d_prof = nullptr;
     plan.d_tiles = nullptr;
     plan.d_err = nullptr;
     plan.tiles_for_n = -1;
+}
+
+int gram_read_profile(GramPlan& plan, long long* out, int max_ctas) {
+    if (plan.d_prof == nullptr) return 0;
+    const int ctas = std::min(max_ctas, std::min(1024, plan.num_sms));
+    if (cudaMemcpy(out, plan.d_prof, (size_t)ctas * 4 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return ctas;
 }
 
 static cudaError_t build_tiles(GramPlan& plan, int n, cudaStream_t stream) {
@@ -413,7 +462,7 @@ static cudaError_t build_tiles(GramPlan& plan, int n, cudaStream_t stream) {
     return e;
 }
 
-cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bytes, int n, int64_t nv, int64_t ld,
+cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int n, int64_t nv, int64_t ld,
                             int32_t* d_S, cudaStream_t stream, std::string* err) {
     if (nv <= 0) return cudaSuccess;
     EncodeTiledFn encode = get_encode_fn();
@@ -429,6 +478,18 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bytes, int
         if (cg != nullptr) plan.cta_group = (atoi(cg) == 1) ? 1 : 2;
         const char* kw = getenv("VPCA_KB_WINDOW");
         if (kw != nullptr) plan.kb_window = atoi(kw);
+        const char* sl = getenv("VPCA_SYNC_LEAD");
+        if (sl != nullptr) plan.sync_lead = atoi(sl);
+        const char* pf = getenv("VPCA_GRAM_PROF");
+        plan.profile = (pf != nullptr && atoi(pf) != 0);
+    }
+    if (plan.d_win_done == nullptr) {
+        cudaError_t e = cudaMalloc(&plan.d_win_done, GramPlan::kMaxWindows * sizeof(int));
+        if (e != cudaSuccess) return e;
+    }
+    if (plan.profile && plan.d_prof == nullptr) {
+        cudaError_t e = cudaMalloc(&plan.d_prof, 1024 * 4 * sizeof(long long));
+        if (e != cudaSuccess) return e;
     }
     if (plan.d_err == nullptr) {
         cudaError_t e = cudaHostAlloc(&plan.d_err, 4 * sizeof(int), cudaHostAllocMapped);
@@ -439,22 +500,30 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bytes, int
         cudaError_t e = build_tiles(plan, n, stream);
         if (e != cudaSuccess) return e;
     }
-    if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0 || ((ld * elem_bytes) & 15) != 0) {
-        if (err) *err = "dense tile must be 16-byte aligned with a 16-byte multiple row pitch";
+    const uintptr_t align = (elem_bits == 4) ? 31 : 15;
+    if ((reinterpret_cast<uintptr_t>(d_x) & align) != 0 || (((ld * elem_bits) / 8) & align) != 0 ||
+        (elem_bits == 4 && (ld % 128) != 0)) {
+        if (err) *err = "dense tile must be 16-byte aligned with a 16-byte multiple row pitch (32 / ld % 128 == 0 for e2m1)";
         return cudaErrorInvalidValue;
     }
 
     const int cgp = plan.cta_group;
     const int workers = (cgp == 2) ? plan.num_sms / 2 : plan.num_sms;
-    const int elems_per_kb = kKBytes / elem_bytes;
-    const int kind = (elem_bytes == 1) ? 0 : 1;
+    // one k-block = one 128-byte swizzle atom of shared memory: 128 int8, 64 bf16 or 128 e2m1 cells (TMA expands
+    // 4-bit cells to one byte each, CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B)
+    const int elems_per_kb = (elem_bits == 16) ? 64 : 128;
+    const int kind = (elem_bits == 8) ? 0 : (elem_bits == 16 ? 1 : 2);
 
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)nv, (cuuint64_t)n};
-    const cuuint64_t gstride[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
+    // e2m1: globalDim[0] must be a multiple of 128 (the caller guarantees zero cells up to there)
+    const cuuint64_t gdim[2] = {(cuuint64_t)(elem_bits == 4 ? ((nv + 127) / 128) * 128 : nv), (cuuint64_t)n};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bits / 8};
     const cuuint32_t box[2] = {(cuuint32_t)elems_per_kb, (cuuint32_t)kBoxRows};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmap, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+    const CUtensorMapDataType tmtype = elem_bits == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                       : (elem_bits == 16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                          : CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B);
+    CUresult r = encode(&tmap, tmtype, 2,
                         const_cast<void*>(d_x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -485,10 +554,24 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bytes, int
         args.kb_window = args.kb_total;
     }
     plan.last_resident = args.resident;
+    const int nwin = (args.kb_total + args.kb_window - 1) / args.kb_window;
+    const long long uw = (long long)args.num_tiles * args.kb_window;
+    args.active_workers = (int)std::min<long long>(workers, uw);
+    args.sync_lead = (args.resident && nwin <= GramPlan::kMaxWindows) ? plan.sync_lead : 0;
+    args.win_done = plan.d_win_done;
+    args.prof = plan.profile ? plan.d_prof : nullptr;
+    args.tx_shift = (elem_bits == 4 && getenv("VPCA_E2M1_TX_FULL") == nullptr) ? 1 : 0;
+    if (args.sync_lead > 0) {
+        cudaError_t e = cudaMemsetAsync(plan.d_win_done, 0, (size_t)nwin * sizeof(int), stream);
+        if (e != cudaSuccess) return e;
+    }
 
     const int grid = workers * cgp;
-    if (cgp == 2) return kind == 0 ? launch<2, 0>(tmap, args, grid, stream) : launch<2, 1>(tmap, args, grid, stream);
-    return kind == 0 ? launch<1, 0>(tmap, args, grid, stream) : launch<1, 1>(tmap, args, grid, stream);
+    if (cgp == 2)
+        return kind == 0 ? launch<2, 0>(tmap, args, grid, stream)
+                         : (kind == 1 ? launch<2, 1>(tmap, args, grid, stream) : launch<2, 2>(tmap, args, grid, stream));
+    return kind == 0 ? launch<1, 0>(tmap, args, grid, stream)
+                     : (kind == 1 ? launch<1, 1>(tmap, args, grid, stream) : launch<1, 2>(tmap, args, grid, stream));
 }
 
 cudaError_t gram_symmetrize(int32_t* d_S, int n, cudaStream_t stream) {

@@ -144,11 +144,23 @@ __device__ __forceinline__ void tc_fence_after() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T ; KIND 0 = kind::i8 (s32 accumulate), 1 = kind::f16 (f32 accumulate)
+// D[tmem] (+)= A[smem] * B[smem]^T ; KIND 0 = kind::i8 (s32 accumulate), 1 = kind::f16, 2 = kind::f8f6f4 (f32 accumulate)
 template <int CG, int KIND>
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
-    if constexpr (CG == 1 && KIND == 0)
+    if constexpr (CG == 1 && KIND == 2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else if constexpr (CG == 2 && KIND == 2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else if constexpr (CG == 1 && KIND == 0)
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),

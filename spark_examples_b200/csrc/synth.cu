@@ -128,12 +128,54 @@ __global__ void synth_dense_kernel(uint64_t seed, int n, int64_t v0, int64_t nv,
     }
 }
 
+// packed e2m1 variant: one thread = one sample pair x 16 consecutive variants = 8 bytes per row (cell j of a row in
+// nibble j & 1 of byte j / 2; dosage m is the code 2 m).  Cells in [nv, round_up(nv, 128)) are written as zero.
+__global__ void synth_e2m1_kernel(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, const PopBounds pb,
+                                  const uint32_t* __restrict__ thr, uint8_t* __restrict__ x, int64_t pitch_bytes) {
+    const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair = blockIdx.y * blockDim.y + threadIdx.y;
+    const int64_t j0 = chunk * 16;
+    const int s0 = pair * 2;
+    const int64_t nv_pad = ((nv + 127) / 128) * 128;
+    if (j0 >= nv_pad || s0 >= n) return;
+    const bool has1 = (s0 + 1) < n;
+    const int pop0 = pop_of(s0, pb), pop1 = pop_of(has1 ? s0 + 1 : s0, pb);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t w0[2] = {0u, 0u}, w1[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int64_t j = j0 + i;
+        if (j < nv) {
+            const uint64_t v = (uint64_t)(v0 + j);
+            const Philox4 r = philox4x32_10((uint32_t)v, (uint32_t)(v >> 32), (uint32_t)pair, kTagCell, k0, k1);
+            const uint32_t t0 = thr[j * kNPop + pop0], t1 = thr[j * kNPop + pop1];
+            uint32_t g0 = (uint32_t)(r.x < t0) + (uint32_t)(r.y < t0);
+            uint32_t g1 = (uint32_t)(r.z < t1) + (uint32_t)(r.w < t1);
+            if (mode == 0) {
+                g0 = g0 > 0;
+                g1 = g1 > 0;
+            }
+            w0[i >> 3] |= (2u * g0) << (4 * (i & 7));
+            w1[i >> 3] |= (2u * g1) << (4 * (i & 7));
+        }
+    }
+    uint2* r0 = reinterpret_cast<uint2*>(x + (int64_t)s0 * pitch_bytes + j0 / 2);
+    *r0 = make_uint2(w0[0], w0[1]);
+    if (has1) *reinterpret_cast<uint2*>(x + (int64_t)(s0 + 1) * pitch_bytes + j0 / 2) = make_uint2(w1[0], w1[1]);
+}
+
 }  // namespace
 
-cudaError_t synth_dense(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, int elem_bytes, void* d_x, int64_t ld,
+cudaError_t synth_dense(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, int elem_bits, void* d_x, int64_t ld,
                         cudaStream_t stream) {
     if (nv <= 0 || n <= 0) return cudaSuccess;
-    if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0 || ((ld * elem_bytes) & 15) != 0) return cudaErrorInvalidValue;
+    const int elem_bytes = elem_bits / 8;
+    if (elem_bits == 4) {
+        if ((reinterpret_cast<uintptr_t>(d_x) & 31) != 0 || (ld % 128) != 0 || ld < ((nv + 127) / 128) * 128)
+            return cudaErrorInvalidValue;
+    } else if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0 || ((ld * elem_bytes) & 15) != 0) {
+        return cudaErrorInvalidValue;
+    }
     static const int cum[kNPop] = {26, 40, 60, 80, 100};
     PopBounds pb;
     for (int k = 0; k < kNPop; ++k) pb.b[k] = (int)(((int64_t)cum[k] * n) / 100);
@@ -148,7 +190,12 @@ cudaError_t synth_dense(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, 
         const int64_t chunks = (cnt + 15) / 16;
         const dim3 block(32, 8);
         const dim3 grid((unsigned)((chunks + 31) / 32), (unsigned)(((n + 1) / 2 + 7) / 8));
-        if (elem_bytes == 1)
+        if (elem_bits == 4) {
+            const int64_t chunks4 = (((cnt + 127) / 128) * 128) / 16;
+            const dim3 grid4((unsigned)((chunks4 + 31) / 32), grid.y);
+            synth_e2m1_kernel<<<grid4, block, 0, stream>>>(seed, n, v0 + b, cnt, mode, pb, d_thr,
+                                                           reinterpret_cast<uint8_t*>(d_x) + b / 2, ld / 2);
+        } else if (elem_bytes == 1)
             synth_dense_kernel<int8_t><<<grid, block, 0, stream>>>(seed, n, v0 + b, cnt, mode, pb, d_thr,
                                                                    reinterpret_cast<int8_t*>(d_x) + b, ld);
         else

@@ -23,7 +23,7 @@ thread_local std::string tls_error;
 struct vpca_ctx {
     vpca_config cfg{};
     int n = 0;
-    int elem_bytes = 1;
+    int elem_bits = 8;   // 8 = int8, 16 = bf16, 4 = packed e2m1
     int max_mult = 2;
     int num_pc = 2;
     cudaStream_t stream = nullptr;
@@ -95,10 +95,10 @@ int check_overflow(vpca_ctx* ctx, int64_t extra_variants) {
 
 int ensure_staging(vpca_ctx* ctx) {
     if (ctx->d_x[0] != nullptr) return VPCA_OK;
-    const int n = ctx->n, eb = ctx->elem_bytes;
+    const int n = ctx->n, bits = ctx->elem_bits;
     int64_t cv = ctx->cfg.chunk_variants;
     if (cv <= 0) {
-        cv = (256ll << 20) / ((int64_t)n * eb);
+        cv = (256ll << 20) * 8 / ((int64_t)n * bits);
         cv = std::max<int64_t>(1024, std::min<int64_t>(cv, 1 << 20));
     }
     cv = ((cv + 127) / 128) * 128;
@@ -111,7 +111,7 @@ int ensure_staging(vpca_ctx* ctx) {
     for (int b = 0; b < 2; ++b) {
         CUDA_OK(ctx, cudaMalloc(&ctx->d_off[b], (size_t)(cv + 1) * sizeof(int64_t)));
         CUDA_OK(ctx, cudaMalloc(&ctx->d_idx[b], (size_t)cz * sizeof(int32_t)));
-        CUDA_OK(ctx, cudaMalloc(&ctx->d_x[b], (size_t)n * (size_t)cv * eb));
+        CUDA_OK(ctx, cudaMalloc(&ctx->d_x[b], (size_t)n * (size_t)cv * bits / 8));
         CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[b], cudaEventDisableTiming));
         CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_done[b], cudaEventDisableTiming));
     }
@@ -122,16 +122,16 @@ int ensure_staging(vpca_ctx* ctx) {
 int launch_gram(vpca_ctx* ctx, const void* d_x, int64_t nv, int64_t ld, int32_t* d_target) {
     // fp32 TMEM accumulation (bf16) is exact only below 2^24: bound the variants one launch may fold
     int64_t limit = nv;
-    if (ctx->elem_bytes == 2) {
+    if (ctx->elem_bits != 8) {   // bf16 / e2m1 accumulate in fp32
         limit = (int64_t)(16777216ll / ((int64_t)ctx->max_mult * ctx->max_mult));
-        limit = std::max<int64_t>(64, (limit / 64) * 64);
+        limit = std::max<int64_t>(128, (limit / 128) * 128);
     }
     for (int64_t v0 = 0; v0 < nv; v0 += limit) {
         const int64_t cnt = std::min<int64_t>(limit, nv - v0);
         std::string msg;
         cudaEventRecord(ctx->ev_t0, ctx->stream);
-        cudaError_t e = gram_accumulate(ctx->plan, static_cast<const char*>(d_x) + (size_t)v0 * ctx->elem_bytes,
-                                        ctx->elem_bytes, ctx->n, cnt, ld, d_target, ctx->stream, &msg);
+        cudaError_t e = gram_accumulate(ctx->plan, static_cast<const char*>(d_x) + (size_t)v0 * ctx->elem_bits / 8,
+                                        ctx->elem_bits, ctx->n, cnt, ld, d_target, ctx->stream, &msg);
         cudaEventRecord(ctx->ev_t1, ctx->stream);
         if (e != cudaSuccess)
             return fail(ctx, VPCA_ERR_CUDA, "Gram launch failed: %s %s", cudaGetErrorString(e), msg.c_str());
@@ -178,7 +178,7 @@ int process_calls(vpca_ctx* ctx, const int64_t* offsets, const int32_t* sample_i
                   void* out_tile, int64_t out_ld) {
     int rc = ensure_staging(ctx);
     if (rc != VPCA_OK) return rc;
-    const int eb = ctx->elem_bytes;
+    const int bits = ctx->elem_bits;
     if (offsets[0] < 0) return fail(ctx, VPCA_ERR_BAD_ARG, "offsets[0] must be >= 0");
     *ctx->h_flags = 0;
     CUDA_OK(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
@@ -190,6 +190,7 @@ int process_calls(vpca_ctx* ctx, const int64_t* offsets, const int32_t* sample_i
         if (offsets[vend] - offsets[v] > ctx->chunk_nnz) {
             const int64_t* hi = std::upper_bound(offsets + v, offsets + vend + 1, offsets[v] + ctx->chunk_nnz);
             vend = (hi - offsets) - 1;
+            if (bits == 4 && vend - v >= 128) vend = v + ((vend - v) / 128) * 128;   // keep packed rows byte aligned
             if (vend <= v)
                 return fail(ctx, VPCA_ERR_BAD_ARG, "row %lld has %lld entries, more than chunk_nnz=%lld", (long long)v,
                             (long long)(offsets[v + 1] - offsets[v]), (long long)ctx->chunk_nnz);
@@ -208,14 +209,15 @@ int process_calls(vpca_ctx* ctx, const int64_t* offsets, const int32_t* sample_i
         CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
         ctx->st.h2d_bytes += (nvc + 1) * 8 + nnz * 4;
         CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
-        CUDA_OK(ctx, encode_calls(ctx->d_off[b], offsets[v], ctx->d_idx[b], nvc, ctx->n, eb, ctx->max_mult, ctx->d_x[b],
+        CUDA_OK(ctx, encode_calls(ctx->d_off[b], offsets[v], ctx->d_idx[b], nvc, ctx->n, bits, ctx->max_mult, ctx->d_x[b],
                                   ctx->ld_chunk, ctx->d_flags, ctx->stream));
         ctx->st.kernel_launches += 2;
         if (out_tile != nullptr) {
-            CUDA_OK(ctx, cudaMemcpy2DAsync(static_cast<char*>(out_tile) + (size_t)v * eb, (size_t)out_ld * eb, ctx->d_x[b],
-                                           (size_t)ctx->ld_chunk * eb, (size_t)nvc * eb, (size_t)ctx->n,
-                                           cudaMemcpyDeviceToHost, ctx->stream));
-            ctx->st.d2h_bytes += nvc * eb * (int64_t)ctx->n;
+            // (chunk boundaries are multiples of 128 variants, so 4-bit rows split on byte boundaries)
+            CUDA_OK(ctx, cudaMemcpy2DAsync(static_cast<char*>(out_tile) + (size_t)v * bits / 8, (size_t)out_ld * bits / 8,
+                                           ctx->d_x[b], (size_t)ctx->ld_chunk * bits / 8, (size_t)(nvc * bits + 7) / 8,
+                                           (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->st.d2h_bytes += (nvc * bits + 7) / 8 * (int64_t)ctx->n;
         } else {
             rc = launch_gram(ctx, ctx->d_x[b], nvc, ctx->ld_chunk, d_target);
             if (rc != VPCA_OK) return rc;
@@ -254,7 +256,7 @@ int vpca_create(const vpca_config* cfg, vpca_ctx** out) {
         return fail(nullptr, VPCA_ERR_BAD_ARG, "cfg is NULL or struct_size != sizeof(vpca_config) (%zu)",
                     sizeof(vpca_config));
     if (cfg->n_samples < 2) return fail(nullptr, VPCA_ERR_BAD_ARG, "n_samples must be >= 2");
-    if (cfg->dtype != VPCA_DTYPE_I8 && cfg->dtype != VPCA_DTYPE_BF16)
+    if (cfg->dtype != VPCA_DTYPE_I8 && cfg->dtype != VPCA_DTYPE_BF16 && cfg->dtype != VPCA_DTYPE_E2M1)
         return fail(nullptr, VPCA_ERR_BAD_ARG, "unknown dtype %d", cfg->dtype);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -271,9 +273,13 @@ int vpca_create(const vpca_config* cfg, vpca_ctx** out) {
     if (ctx == nullptr) return fail(nullptr, VPCA_ERR_NOMEM, "out of host memory");
     ctx->cfg = *cfg;
     ctx->n = cfg->n_samples;
-    ctx->elem_bytes = cfg->dtype == VPCA_DTYPE_I8 ? 1 : 2;
+    ctx->elem_bits = cfg->dtype == VPCA_DTYPE_I8 ? 8 : (cfg->dtype == VPCA_DTYPE_BF16 ? 16 : 4);
     ctx->max_mult = cfg->max_multiplicity > 0 ? cfg->max_multiplicity : 2;
     ctx->num_pc = cfg->num_pc > 0 ? cfg->num_pc : 2;
+    if (ctx->elem_bits == 4 && ctx->max_mult > 2) {
+        delete ctx;
+        return fail(nullptr, VPCA_ERR_BAD_ARG, "VPCA_DTYPE_E2M1 represents multiplicities 0, 1, 2 only (max_multiplicity <= 2)");
+    }
     if (cfg->stream != nullptr) {
         ctx->stream = static_cast<cudaStream_t>(cfg->stream);
     } else {
@@ -429,10 +435,14 @@ int vpca_accumulate_dense(vpca_ctx* ctx, const void* x, int64_t nv, int64_t ld, 
     if (nv == 0) return VPCA_OK;
     int rc = check_overflow(ctx, nv);
     if (rc != VPCA_OK) return rc;
-    const int eb = ctx->elem_bytes;
+    const int bits = ctx->elem_bits;
+    if (bits == 4 && (ld % 128) != 0)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "packed e2m1 tiles need ld %% 128 == 0 (and zero padding up to a multiple of 128 variants)");
     if (on_device) {
-        if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || ((ld * eb) & 15) != 0)
-            return fail(ctx, VPCA_ERR_BAD_ARG, "device tile must be 16-byte aligned with a 16-byte multiple row pitch");
+        const int align = bits == 4 ? 31 : 15;
+        if ((reinterpret_cast<uintptr_t>(x) & align) != 0 || ((ld * bits / 8) & align) != 0)
+            return fail(ctx, VPCA_ERR_BAD_ARG, "device tile must be %d-byte aligned with a %d-byte multiple row pitch",
+                        align + 1, align + 1);
         rc = launch_gram(ctx, x, nv, ld, ctx->d_S);
         if (rc != VPCA_OK) return rc;
     } else {
@@ -443,11 +453,15 @@ int vpca_accumulate_dense(vpca_ctx* ctx, const void* x, int64_t nv, int64_t ld, 
             const int64_t nvc = std::min(ctx->chunk_variants, nv - v);
             const int b = chunk & 1;
             CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
-            CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->d_x[b], (size_t)ctx->ld_chunk * eb, static_cast<const char*>(x) + (size_t)v * eb,
-                                           (size_t)ld * eb, (size_t)nvc * eb, (size_t)ctx->n, cudaMemcpyHostToDevice,
+            if (bits == 4 && (nvc % 128) != 0)   // the tail k-block of a packed tile must be zero beyond nv
+                CUDA_OK(ctx, cudaMemset2DAsync(ctx->d_x[b], (size_t)ctx->ld_chunk / 2, 0, (size_t)((nvc + 127) / 128) * 64,
+                                               (size_t)ctx->n, ctx->copy_stream));
+            CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->d_x[b], (size_t)ctx->ld_chunk * bits / 8,
+                                           static_cast<const char*>(x) + (size_t)v * bits / 8, (size_t)ld * bits / 8,
+                                           (size_t)(nvc * bits + 7) / 8, (size_t)ctx->n, cudaMemcpyHostToDevice,
                                            ctx->copy_stream));
             CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
-            ctx->st.h2d_bytes += nvc * eb * (int64_t)ctx->n;
+            ctx->st.h2d_bytes += (nvc * bits + 7) / 8 * (int64_t)ctx->n;
             CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
             rc = launch_gram(ctx, ctx->d_x[b], nvc, ctx->ld_chunk, ctx->d_S);
             if (rc != VPCA_OK) return rc;
@@ -580,7 +594,7 @@ int vpca_synth_dense_device(vpca_ctx* ctx, uint64_t seed, int64_t v0, int64_t nv
     if (mode == 1 && ctx->max_mult < 2)
         return fail(ctx, VPCA_ERR_BAD_ARG, "dosage mode needs max_multiplicity >= 2");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    cudaError_t e = synth_dense(seed, ctx->n, v0, nv, mode, ctx->elem_bytes, d_x, ld, ctx->stream);
+    cudaError_t e = synth_dense(seed, ctx->n, v0, nv, mode, ctx->elem_bits, d_x, ld, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, VPCA_ERR_CUDA, "synthetic generator: %s", cudaGetErrorString(e));
     ctx->st.kernel_launches += 2 * ((nv + (1 << 22) - 1) >> 22);
     return VPCA_OK;
@@ -600,6 +614,14 @@ int vpca_get_stats(vpca_ctx* ctx, vpca_stats* out) {
     }
     *out = ctx->st;
     return VPCA_OK;
+}
+
+int vpca_debug_gram_profile(vpca_ctx* ctx, int64_t* out, int32_t max_ctas) {
+    if (ctx == nullptr || out == nullptr || max_ctas <= 0) return fail(ctx, VPCA_ERR_BAD_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return gram_read_profile(ctx->plan, reinterpret_cast<long long*>(out), max_ctas);
 }
 
 }  // extern "C"

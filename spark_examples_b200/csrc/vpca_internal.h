@@ -19,13 +19,22 @@ struct GramPlan {
     int tiles_for_cg = 0;
     int last_resident = 0;
     int* d_err = nullptr;     // device debug words written before a watchdog trap
+    static constexpr int kMaxWindows = 1 << 16;
+    int sync_lead = 0;        // VPCA_SYNC_LEAD: windows a worker may lead the slowest one by (0 = no pacing; measured
+                              // on B200: pacing only slows every worker to the slowest one)
+    int* d_win_done = nullptr;
+    bool profile = false;     // VPCA_GRAM_PROF=1: per-CTA timestamps in d_prof
+    long long* d_prof = nullptr;
 };
+// Copies the per-CTA timestamps of the last profiled launch (4 per CTA) to host; returns the CTA count.
+int gram_read_profile(GramPlan& plan, long long* out, int max_ctas);
 
 // S(lower triangle, row >= col) += X X^T for the nv variants of a dense sample-major tile.
-//   d_x : device, element (s, v) at d_x[s * ld + v]; elem_bytes 1 (int8) or 2 (bf16)
+//   d_x : device, element (s, v) at index s * ld + v; elem_bits 8 (int8), 16 (bf16) or 4 (packed e2m1: two cells per
+//         byte, ld % 128 == 0 and zero cells up to the next multiple of 128 variants)
 //   d_S : device int32 n x n row-major
 // Returns cudaSuccess or the first CUDA error; never synchronises.
-cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bytes, int n, int64_t nv, int64_t ld,
+cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int n, int64_t nv, int64_t ld,
                             int32_t* d_S, cudaStream_t stream, std::string* err);
 cudaError_t gram_symmetrize(int32_t* d_S, int n, cudaStream_t stream);
 cudaError_t gram_add(int32_t* d_dst, const int32_t* d_src, int64_t count, cudaStream_t stream);
@@ -36,7 +45,7 @@ void gram_plan_free(GramPlan& plan);
 // sample-major tile, zero-filled first.  d_flags[0] is OR-ed with 1 on an out-of-range index and 2 on a
 // multiplicity overflow.
 cudaError_t encode_calls(const int64_t* d_off, int64_t base, const int32_t* d_idx, int64_t nv, int n,
-                         int elem_bytes, int max_mult, void* d_x, int64_t ld, int* d_flags, cudaStream_t stream);
+                         int elem_bits, int max_mult, void* d_x, int64_t ld, int* d_flags, cudaStream_t stream);
 
 // ---- centering + eigensolve (eig.cu) ---------------------------------------------------------------
 struct EigWork {
@@ -54,6 +63,9 @@ struct EigWork {
     double* d_evecs = nullptr; // n x k (column-major)
     double* d_lu = nullptr;    // 8 n scratch for inverse iteration
     int* d_nz = nullptr;
+    int* d_step = nullptr;               // {next step, step of the pending trailing update}
+    cudaGraphExec_t graph_exec = nullptr; // kGraphSteps tridiagonalisation steps, replayed n / kGraphSteps times
+    int graph_n = 0;
     int kmax = 0;
 };
 cudaError_t eig_alloc(EigWork& w, int n, int kmax);
@@ -62,7 +74,7 @@ cudaError_t center_gram(EigWork& w, const int32_t* d_S, cudaStream_t stream);
 cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches);
 
 // ---- synthetic generator (synth.cu) ----------------------------------------------------------------
-cudaError_t synth_dense(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, int elem_bytes, void* d_x,
+cudaError_t synth_dense(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, int elem_bits, void* d_x,
                         int64_t ld, cudaStream_t stream);
 
 }  // namespace vpca

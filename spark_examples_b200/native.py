@@ -26,6 +26,7 @@ VPCA_ERR_UNSUPPORTED = -8
 
 DTYPE_I8 = 0
 DTYPE_BF16 = 1
+DTYPE_E2M1 = 2   # 4-bit cells, two per byte (cell j of a row in nibble j & 1 of byte j // 2; value m is the code 2 m)
 
 _STATUS_NAMES = {
     -1: "BAD_ARG", -2: "INDEX_OUT_OF_RANGE", -3: "CUDA", -4: "NCCL", -5: "OVERFLOW", -6: "STATE",
@@ -37,7 +38,7 @@ EXPORTED_SYMBOLS = (
     "vpca_version", "vpca_create", "vpca_destroy", "vpca_last_error", "vpca_reset", "vpca_encode_calls",
     "vpca_accumulate_calls", "vpca_commit", "vpca_abort", "vpca_accumulate_dense", "vpca_gram_device_ptr",
     "vpca_finalize_gram", "vpca_get_gram", "vpca_set_gram", "vpca_compute_pca", "vpca_get_centered",
-    "vpca_get_tridiagonal", "vpca_synth_dense_device", "vpca_get_stats",
+    "vpca_get_tridiagonal", "vpca_synth_dense_device", "vpca_get_stats", "vpca_debug_gram_profile",
 )
 
 
@@ -142,6 +143,8 @@ def load_library() -> ctypes.CDLL:
     L.vpca_synth_dense_device.argtypes = [vp, ctypes.c_uint64, i64, i64, ctypes.c_int, vp, i64]
     L.vpca_get_stats.restype = ctypes.c_int
     L.vpca_get_stats.argtypes = [vp, ctypes.POINTER(VpcaStats)]
+    L.vpca_debug_gram_profile.restype = ctypes.c_int
+    L.vpca_debug_gram_profile.argtypes = [vp, vp, i32]
     _lib = L
     return L
 
@@ -159,7 +162,8 @@ class NativePca:
         self._lib = load_library()
         self.n = int(n_samples)
         self.dtype = int(dtype)
-        self.elem_bytes = 1 if dtype == DTYPE_I8 else 2
+        self.elem_bits = {DTYPE_I8: 8, DTYPE_BF16: 16, DTYPE_E2M1: 4}[self.dtype]
+        self.elem_bytes = self.elem_bits / 8
         cfg = VpcaConfig(ctypes.sizeof(VpcaConfig), n_samples, device, dtype, num_pc, max_multiplicity,
                          partitions_in_flight, 0, chunk_variants, chunk_nnz, stream or None, d_gram or None)
         handle = ctypes.c_void_p()
@@ -212,7 +216,13 @@ class NativePca:
         """Device encode only (CSR rows -> dense sample-major tile), copied back: shape (n, nv)."""
         off, idx = self._csr(offsets, sample_idx)
         nv = len(off) - 1
-        out = np.zeros((self.n, max(nv, 1)), dtype=np.int8 if self.elem_bytes == 1 else np.uint16)
+        if self.elem_bits == 4:                      # packed: (n, ld / 2) bytes, ld a multiple of 128 cells
+            ld = max(128, ((nv + 127) // 128) * 128)
+            out = np.zeros((self.n, ld // 2), dtype=np.uint8)
+            self._check(self._lib.vpca_encode_calls(self._h, _host_ptr(off), _host_ptr(idx) if len(idx) else None, nv,
+                                                    _host_ptr(out), ld))
+            return out
+        out = np.zeros((self.n, max(nv, 1)), dtype=np.int8 if self.elem_bits == 8 else np.uint16)
         self._check(self._lib.vpca_encode_calls(self._h, _host_ptr(off), _host_ptr(idx) if len(idx) else None, nv,
                                                 _host_ptr(out), out.shape[1]))
         return out[:, :nv]
@@ -232,10 +242,18 @@ class NativePca:
     def abort(self, partition_id: int):
         self._check(self._lib.vpca_abort(self._h, int(partition_id)))
 
-    def accumulateDense(self, x: np.ndarray):
-        """Host dense tile, shape (n, nv), int8 (or uint16 bf16 bits)."""
-        want = np.int8 if self.elem_bytes == 1 else np.uint16
+    def accumulateDense(self, x: np.ndarray, nv: Optional[int] = None):
+        """Host dense tile, shape (n, nv), int8 (or uint16 bf16 bits); for DTYPE_E2M1 packed uint8 of shape
+        (n, ld / 2) with ld % 128 == 0, `nv` valid cells per row and zero cells after them."""
         x = np.asarray(x)
+        if self.elem_bits == 4:
+            if x.dtype != np.uint8 or x.ndim != 2 or x.shape[0] != self.n or (x.shape[1] * 2) % 128:
+                raise VpcaError(VPCA_ERR_BAD_ARG, f"packed tile must be ({self.n}, ld/2) uint8 with ld % 128 == 0")
+            x = np.ascontiguousarray(x)
+            ld = x.shape[1] * 2
+            self._check(self._lib.vpca_accumulate_dense(self._h, _host_ptr(x), ld if nv is None else int(nv), ld, 0))
+            return
+        want = np.int8 if self.elem_bits == 8 else np.uint16
         if x.dtype != want or x.ndim != 2 or x.shape[0] != self.n:
             raise VpcaError(VPCA_ERR_BAD_ARG, f"dense tile must be ({self.n}, nv) {np.dtype(want).name}")
         if not x.flags.c_contiguous:
@@ -287,6 +305,14 @@ class NativePca:
     def synthDenseDevice(self, seed: int, v0: int, nv: int, mode: int, d_ptr: int, ld: int):
         self._check(self._lib.vpca_synth_dense_device(self._h, ctypes.c_uint64(seed), int(v0), int(nv), int(mode),
                                                       d_ptr, int(ld)))
+
+    def gramProfile(self, max_ctas: int = 1024) -> np.ndarray:
+        """(ctas, 4) int64 ns timestamps of the last Gram launch (needs VPCA_GRAM_PROF=1 at first launch)."""
+        out = np.zeros((max_ctas, 4), dtype=np.int64)
+        rc = self._lib.vpca_debug_gram_profile(self._h, _host_ptr(out), max_ctas)
+        if rc < 0:
+            self._raise(rc, self._h)
+        return out[:rc]
 
     def stats(self) -> dict:
         st = VpcaStats()

@@ -266,3 +266,79 @@ def test_resident_device_tile_full_properties(oracle):
         nat3.finalizeGram()
         S3 = nat3.getGram()
     assert np.array_equal(S3, oracle.np_similarity_dense(sl))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# packed 4-bit (e2m1) genotype storage: same Gram, half the HBM/L2 bytes per cell
+# ---------------------------------------------------------------------------------------------------------------
+def _pack_e2m1(X):
+    """(n, nv) multiplicities in {0,1,2} -> packed (n, ld/2) uint8, ld = nv rounded up to 128."""
+    n, nv = X.shape
+    ld = ((nv + 127) // 128) * 128
+    codes = np.zeros((n, ld), np.uint8)
+    codes[:, :nv] = 2 * X.astype(np.uint8)
+    return (codes[:, 0::2] | (codes[:, 1::2] << 4)).astype(np.uint8)
+
+
+def test_encode_tile_e2m1(oracle):
+    from spark_examples_b200 import native
+    rng = np.random.default_rng(8)
+    n, nv = 77, 300
+    off, idx, rows = _random_rows(rng, n, nv, 0.3, dup_every=6)
+    want = np.zeros((n, nv), np.int64)
+    for v, r in enumerate(rows):
+        np.add.at(want[:, v], r, 1)
+    with _native(n, dtype=native.DTYPE_E2M1) as nat:
+        got = nat.encodeCalls(off, idx)
+    assert np.array_equal(got, _pack_e2m1(want))
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gram_e2m1_dense_and_calls(oracle, monkeypatch, cta_group):
+    _set_env(monkeypatch, cta_group, kb_window=8)
+    from spark_examples_b200 import native
+    n, nv = 700, 5003
+    X = oracle.c_synth_dense(SEED, n, 0, nv, mode=1)           # dosage 0/1/2: all three codes
+    want = oracle.np_similarity_dense(X)
+    with _native(n, dtype=native.DTYPE_E2M1) as nat:
+        nat.accumulateDense(_pack_e2m1(X), nv)
+        nat.finalizeGram()
+        assert np.array_equal(nat.getGram(), want)
+    off, idx = oracle.dense_to_calls(X)
+    with _native(n, dtype=native.DTYPE_E2M1) as nat:
+        nat.accumulateCalls(-1, off, idx)
+        nat.finalizeGram()
+        assert np.array_equal(nat.getGram(), want)
+
+
+def test_synth_device_e2m1_matches_oracle(oracle):
+    import torch
+    from spark_examples_b200 import native
+    n, v0, nv = 333, 4096, 1003
+    ld = 1024
+    for mode in (0, 1):
+        want = _pack_e2m1(oracle.c_synth_dense(SEED, n, v0, nv, mode))
+        buf = torch.full((n, ld // 2), 0xEE, dtype=torch.uint8, device="cuda")
+        with _native(n, dtype=native.DTYPE_E2M1) as nat:
+            nat.synthDenseDevice(SEED, v0, nv, mode, buf.data_ptr(), ld)
+            torch.cuda.synchronize()
+        assert np.array_equal(buf.cpu().numpy(), want)            # includes the zeroed padding cells
+
+
+def test_gram_e2m1_resident_matches_int8(oracle):
+    import torch
+    from spark_examples_b200 import native
+    n, nv = 2504, 262_144
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    X8 = torch.empty((n, nv), dtype=torch.int8, device="cuda")
+    X4 = torch.empty((n, nv // 2), dtype=torch.uint8, device="cuda")
+    with _native(n, stream=stream.cuda_stream, max_multiplicity=1) as a, \
+            _native(n, dtype=native.DTYPE_E2M1, stream=stream.cuda_stream, max_multiplicity=1) as b:
+        a.synthDenseDevice(SEED, 0, nv, 0, X8.data_ptr(), nv)
+        b.synthDenseDevice(SEED, 0, nv, 0, X4.data_ptr(), nv)
+        a.accumulateDenseDevice(X8.data_ptr(), nv, nv)
+        b.accumulateDenseDevice(X4.data_ptr(), nv, nv)
+        a.finalizeGram()
+        b.finalizeGram()
+        assert np.array_equal(a.getGram(), b.getGram())

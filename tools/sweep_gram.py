@@ -11,38 +11,48 @@ def main():
     n = int(os.environ.get("SWEEP_N", "2504"))
     vs = [int(v) for v in os.environ.get("SWEEP_V", "1000000").split(",")]
     cgs = [int(v) for v in os.environ.get("SWEEP_CG", "2,1").split(",")]
-    kbws = [int(v) for v in os.environ.get("SWEEP_KBW", "0,18,37,74,148,296").split(",")]
+    kbws = [int(v) for v in os.environ.get("SWEEP_KBW", "0,37,74,148").split(",")]
+    leads = [int(v) for v in os.environ.get("SWEEP_LEAD", "0,1,2,4").split(",")]
+    os.environ["VPCA_GRAM_PROF"] = "1"
     dt = os.environ.get("SWEEP_DTYPE", "i8")
-    eb = 1 if dt == "i8" else 2
+    eb = {"i8": 1, "bf16": 2, "e2m1": 0.5}[dt]
+    ndt = {"i8": native.DTYPE_I8, "bf16": native.DTYPE_BF16, "e2m1": native.DTYPE_E2M1}[dt]
     reps = int(os.environ.get("SWEEP_REPS", "10"))
     vmax = max(vs)
     ld = ((vmax + 127) // 128) * 128
-    X = torch.empty((n, ld), dtype=torch.int8 if eb == 1 else torch.bfloat16, device="cuda")
+    X = torch.empty((n, ld // 2 if dt == "e2m1" else ld), dtype=torch.bfloat16 if dt == "bf16" else torch.uint8, device="cuda")
     ts = torch.cuda.Stream()
     torch.cuda.set_stream(ts)
     stream = ts.cuda_stream
-    with native.NativePca(n, dtype=native.DTYPE_I8 if eb == 1 else native.DTYPE_BF16, stream=stream, max_multiplicity=1) as g:
+    with native.NativePca(n, dtype=ndt, stream=stream, max_multiplicity=1) as g:
         g.synthDenseDevice(20240901, 0, vmax, 0, X.data_ptr(), ld)
     torch.cuda.synchronize()
     ref = None
-    for v, cg, kbw in itertools.product(vs, cgs, kbws):
+    for v, cg, kbw, lead in itertools.product(vs, cgs, kbws, leads):
         os.environ["VPCA_CTA_GROUP"] = str(cg)
+        os.environ["VPCA_SYNC_LEAD"] = str(lead)
         if kbw > 0: os.environ["VPCA_KB_WINDOW"] = str(kbw)
         else: os.environ.pop("VPCA_KB_WINDOW", None)
-        with native.NativePca(n, dtype=native.DTYPE_I8 if eb == 1 else native.DTYPE_BF16, stream=stream, max_multiplicity=1) as nat:
+        with native.NativePca(n, dtype=ndt, stream=stream, max_multiplicity=1) as nat:
             ts = []
             for r in range(reps + 2):
                 nat.reset()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); nat.accumulateDenseDevice(X.data_ptr(), v, ld); b.record(); b.synchronize()
                 if r >= 2: ts.append(a.elapsed_time(b))
+            pr = nat.gramProfile()
+            t0 = pr[:, 0].min()
+            starts, mma, ends = pr[:, 0] - t0, pr[:, 2][pr[:, 2] > 0] - t0, pr[:, 3] - t0
+            prof = {"start_spread_us": round(float(starts.max()) / 1e3, 1),
+                    "mma_done_us_min_med_max": [round(float(x) / 1e3, 1) for x in (mma.min(), sorted(mma)[len(mma) // 2], mma.max())],
+                    "end_us_min_max": [round(float(ends.min()) / 1e3, 1), round(float(ends.max()) / 1e3, 1)]}
             nat.finalizeGram()
             S = torch.from_numpy(nat.getGram())
             chk = int(S.to(torch.int64).sum().item())
             ts.sort()
             ms = ts[len(ts) // 2]
             ops = n * (n + 1) * v
-            print(json.dumps({"n": n, "v": v, "cg": cg, "kbw": kbw, "ms_med": round(ms, 4), "ms_min": round(ts[0], 4),
+            print(json.dumps({"n": n, "v": v, "cg": cg, "kbw": kbw, "lead": lead, "prof": prof, "ms_med": round(ms, 4), "ms_min": round(ts[0], 4),
                               "tops_syrk": round(ops / ms / 1e9, 1), "cells_per_s": round(n * v / ms * 1e3 / 1e9, 2),
                               "checksum": chk}), flush=True)
 main()
