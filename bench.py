@@ -49,6 +49,11 @@ def parse_args():
     ap.add_argument("--variants-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--dtype", choices=["i8", "bf16", "e2m1"], default="i8")
     ap.add_argument("--no-alt", action="store_true", help="skip the packed-e2m1 comparison leg")
+    ap.add_argument("--panel-variants", type=int, default=int(os.environ.get("VPCA_BENCH_PANEL", "8192")),
+                    help="resident cohort layout: panels of this many variants (vpca_accumulate_panels); 0 = row-major")
+    ap.add_argument("--reduce", choices=["nccl", "fused"], default=os.environ.get("VPCA_BENCH_REDUCE", "nccl"),
+                    help="N > 1: 'nccl' = one all-reduce after the Gram kernel; 'fused' = the Gram epilogue adds into every "
+                         "rank's Gram over NVLink peer memory (vpca_gram_set_peers)")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 5); 0 disables the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eig-check", action="store_true")
@@ -243,17 +248,41 @@ def run_b200(args):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
+    fused = world > 1 and args.reduce == "fused"
     S = torch.zeros((n, n), dtype=torch.int32, device=dev)
-    nat = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=S.data_ptr(), max_multiplicity=1)
-    X = torch.empty((n, ld // 2 if args.dtype == "e2m1" else ld), dtype=tdtype, device=dev)
-    nat.synthDenseDevice(SEED, rank * vpg, vpg, 0, X.data_ptr(), ld)
+    nat = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=0 if fused else S.data_ptr(),
+                           max_multiplicity=1)
+    if fused:
+        handles = [None] * world
+        dist.all_gather_object(handles, nat.exportIpcHandle())
+        nat.setPeers(handles, rank)
+    P = args.panel_variants
+    if P > 0:
+        npan = (vpg + P - 1) // P
+        X = torch.empty(nat.panelBytes(vpg, P), dtype=torch.uint8, device=dev)
+        nat.synthPanelsDevice(SEED, rank * vpg, vpg, 0, X.data_ptr(), P)
+        Xv = (X.view(npan, n, P // 2) if args.dtype == "e2m1" else X.view(tdtype).view(npan, n, P))
+    else:
+        X = torch.empty((n, ld // 2 if args.dtype == "e2m1" else ld), dtype=tdtype, device=dev)
+        nat.synthDenseDevice(SEED, rank * vpg, vpg, 0, X.data_ptr(), ld)
     torch.cuda.synchronize()
+
+    def gram_launch(nt, x):
+        if P > 0:
+            nt.accumulatePanels(x.data_ptr(), vpg, P)
+        else:
+            nt.accumulateDenseDevice(x.data_ptr(), vpg, ld)
 
     def step():
         nat.reset()
-        nat.accumulateDenseDevice(X.data_ptr(), vpg, ld)
-        if world > 1:
-            dist.all_reduce(S)                 # reduceByKey(_ + _) (VariantsPca.scala:190) = one NCCL all-reduce
+        if fused:
+            nat.peerBarrier()                  # every rank's Gram is zeroed before anyone adds into it
+            gram_launch(nat, X)                # epilogue reds go to all ranks' Grams over NVLink
+            nat.peerBarrier()                  # all contributions have landed
+        else:
+            gram_launch(nat, X)
+            if world > 1:
+                dist.all_reduce(S)             # reduceByKey(_ + _) (VariantsPca.scala:190) = one NCCL all-reduce
         nat.finalizeGram()
 
     def barrier():
@@ -289,7 +318,7 @@ def run_b200(args):
         nat.reset()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        nat.accumulateDenseDevice(X.data_ptr(), vpg, ld)
+        gram_launch(nat, X)
         b.record()
         b.synchronize()
         kt.append(a.elapsed_time(b))
@@ -318,16 +347,35 @@ def run_b200(args):
     checks = {}
     step()
     torch.cuda.synchronize()
+    if fused:
+        S.copy_(torch.from_numpy(nat.getGram()))
+        Sref = S.clone()                       # the same cohort reduced with NCCL must give the same matrix
+        with native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=Sref.data_ptr(),
+                              max_multiplicity=1) as natr:
+            Sref.zero_()
+            gram_launch(natr, X)
+            dist.all_reduce(Sref)
+            natr.finalizeGram()
+            torch.cuda.synchronize()
+        checks["fused_reduce_equals_nccl_allreduce"] = bool(torch.equal(S, Sref))
     checks["gram_symmetric"] = bool(torch.equal(S, S.t()))
     def cells(c0, c1):
-        """binary carrier block X[:, c0:c1] as int32, whatever the storage dtype"""
-        if args.dtype == "e2m1":
-            b = X[:, c0 // 2:c1 // 2]
-            out = torch.empty((n, c1 - c0), dtype=torch.int32, device=dev)
-            out[:, 0::2] = ((b & 0x0F) != 0).to(torch.int32)
-            out[:, 1::2] = ((b >> 4) != 0).to(torch.int32)
-            return out
-        return (X[:, c0:c1].to(torch.float32) > 0).to(torch.int32)
+        """binary carrier block of variants [c0, c1) as int32 (n, c1 - c0), whatever the storage dtype / layout"""
+        def block(view, lo, hi):                      # columns [lo, hi) of a row-major (n, width) view
+            if args.dtype == "e2m1":
+                b = view[:, lo // 2:hi // 2]
+                out = torch.empty((n, hi - lo), dtype=torch.int32, device=dev)
+                out[:, 0::2] = ((b & 0x0F) != 0).to(torch.int32)
+                out[:, 1::2] = ((b >> 4) != 0).to(torch.int32)
+                return out
+            return (view[:, lo:hi].to(torch.float32) > 0).to(torch.int32)
+        if P == 0:
+            return block(X, c0, c1)
+        parts = []
+        for pn in range(c0 // P, (c1 - 1) // P + 1):
+            lo, hi = max(c0, pn * P) - pn * P, min(c1, (pn + 1) * P) - pn * P
+            parts.append(block(Xv[pn], lo, hi))
+        return torch.cat(parts, dim=1)
 
     if world == 1:
         carriers = torch.zeros(n, dtype=torch.int64, device=dev)
@@ -343,6 +391,7 @@ def run_b200(args):
             c1 = min(vpg, c0 + 100_000)
             s1 += cells(c0, c1).to(torch.float64) @ colsum[c0:c1]
         checks["S_times_ones_equals_X_Xt1"] = bool(torch.equal(S.sum(dim=1).to(torch.float64), s1))
+    nat.computePca(2)                      # first call builds the CUDA graph of the tridiagonalisation loop (one-off)
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record()
     vecs, evals, nz = nat.computePca(2)
@@ -409,16 +458,20 @@ def run_b200(args):
     alt = None
     if args.dtype == "i8" and not args.no_alt:
         S4 = torch.zeros((n, n), dtype=torch.int32, device=dev)
-        X4 = torch.empty((n, ld // 2), dtype=torch.uint8, device=dev)
         with native.NativePca(n, device=local_rank, dtype=native.DTYPE_E2M1, stream=stream, d_gram=S4.data_ptr(),
                               max_multiplicity=1) as nat4:
-            nat4.synthDenseDevice(SEED, rank * vpg, vpg, 0, X4.data_ptr(), ld)
+            if P > 0:
+                X4 = torch.empty(nat4.panelBytes(vpg, P), dtype=torch.uint8, device=dev)
+                nat4.synthPanelsDevice(SEED, rank * vpg, vpg, 0, X4.data_ptr(), P)
+            else:
+                X4 = torch.empty((n, ld // 2), dtype=torch.uint8, device=dev)
+                nat4.synthDenseDevice(SEED, rank * vpg, vpg, 0, X4.data_ptr(), ld)
             t4 = []
             for _ in range(max(5, min(args.steps, 20)) + 2):
                 nat4.reset()
                 a4, b4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a4.record()
-                nat4.accumulateDenseDevice(X4.data_ptr(), vpg, ld)
+                gram_launch(nat4, X4)
                 b4.record()
                 b4.synchronize()
                 t4.append(a4.elapsed_time(b4))
@@ -449,6 +502,10 @@ def run_b200(args):
                                    f"{' + NCCL all-reduce' if world > 1 else ''} + symmetrize "
                                    "(BASELINE configs[1] per GPU; 8 x 5M is configs[2])",
                        "samples": n, "variants_per_gpu": vpg, "parallelism": f"variant-sharded x{world}",
+                       "hbm_layout": (f"panels of {P} variants x {n} samples (vpca_accumulate_panels)" if P > 0
+                                      else "row-major samples x variants"),
+                       "reduce": ("fused: Gram epilogue red.add into every rank's Gram over NVLink peer memory" if fused
+                                  else ("nccl all-reduce" if world > 1 else "none (1 GPU)")),
                        "l2_policy": f"input ({n * vpg * eb / 1e9:.2f} GB per rank) larger than L2; no flush between iterations"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
             "eig_ms": eig_ms, "checks": checks,

@@ -106,6 +106,11 @@ int vpca_encode_calls(vpca_ctx* ctx, const int64_t* offsets, const int32_t* samp
  * partition_id < 0 means "no staging": accumulate straight into the Gram (single-shot callers). */
 int vpca_accumulate_calls(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const int32_t* sample_idx,
                           int64_t nv);
+/* Same, with 16-bit sample indices -- halves the host->device bytes of the dominant e2e cost.  Valid whenever
+ * n_samples <= 65536, which covers every cohort the reference itself can process (MLlib's RowMatrix refuses more
+ * than 65535 columns at VariantsPca.scala:226). */
+int vpca_accumulate_calls_u16(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const uint16_t* sample_idx,
+                              int64_t nv);
 int vpca_commit(vpca_ctx* ctx, int64_t partition_id);
 int vpca_abort(vpca_ctx* ctx, int64_t partition_id);
 
@@ -115,11 +120,30 @@ int vpca_abort(vpca_ctx* ctx, int64_t partition_id);
  * host memory and is staged through the device in chunks.  Accumulates straight into the Gram. */
 int vpca_accumulate_dense(vpca_ctx* ctx, const void* x, int64_t nv, int64_t ld, int on_device);
 
+/* Device-resident input in PANEL layout -- the layout to keep a whole cohort in HBM: the nv variants are cut into
+ * panels of `panel_variants` (a multiple of 128); panel p is a contiguous n_samples x panel_variants row-major block,
+ * panels follow each other:  cell (s, v) at  (v / P) * n_samples * P + s * P + v % P  (cells; e2m1: two per byte),
+ * cells after nv in the last panel are zero, d_x 32-byte aligned.  One Gram launch consumes everything.  Why: with a
+ * row-major tile whose rows are megabytes apart every sample row sits on its own 2 MB page and each 128-row TMA box
+ * touches 128 pages; panels keep the pages live per L2 window to a few dozen (measured 2x on 2504 x 5M int8). */
+int vpca_accumulate_panels(vpca_ctx* ctx, const void* d_x, int64_t nv, int64_t panel_variants);
+
 /* `reduceByKey(_ + _)` (:190) across GPUs is ONE all-reduce of the raw Gram buffer, driven by the host
  * (torch.distributed / NCCL in this repo): all-reduce the n_samples^2 int32 at
  * vpca_gram_device_ptr() between the last commit and vpca_finalize_gram().  Until finalize only the
  * lower triangle (row >= col) of the buffer is meaningful. */
 int vpca_gram_device_ptr(vpca_ctx* ctx, void** d_gram);
+/* Fused alternative to the host-driven all-reduce (one process per GPU, all GPUs of one NVLink box): once every
+ * rank has exchanged the 64-byte handle of vpca_gram_export_ipc() and called vpca_gram_set_peers() with the handles
+ * of all ranks (rank order; needs a library-owned Gram, vpca_config.d_gram == NULL), the epilogue of the Gram
+ * kernel adds every flushed accumulator straight into the Gram of EVERY rank (red.global.add.s32 on peer-mapped
+ * memory), so compute and reduceByKey (:190) are one kernel.  Protocol per pass, on every rank:
+ *   vpca_reset -> vpca_peer_barrier -> accumulate ... (commit) -> vpca_peer_barrier -> vpca_finalize_gram.
+ * vpca_peer_barrier enqueues an all-rank barrier over peer-mapped flags on the context's stream. */
+int vpca_gram_export_ipc(vpca_ctx* ctx, void* handle64);
+int vpca_gram_set_peers(vpca_ctx* ctx, const void* handles, int32_t world, int32_t rank);
+int vpca_peer_barrier(vpca_ctx* ctx);
+
 /* Mirror the lower triangle into the upper one: after this the buffer equals the reference's
  * similarity matrix with all N^2 entries present (:189-190). */
 int vpca_finalize_gram(vpca_ctx* ctx);
@@ -148,6 +172,10 @@ int vpca_get_tridiagonal(vpca_ctx* ctx, double* diag, double* offdiag);
  * Fill a dense sample-major device tile d_x[s * ld + (v - v0)] for variants [v0, v0+nv).
  * mode 0: binary carrier x = (dosage > 0) (reference encode rule); mode 1: dosage 0/1/2. */
 int vpca_synth_dense_device(vpca_ctx* ctx, uint64_t seed, int64_t v0, int64_t nv, int mode, void* d_x, int64_t ld);
+
+/* Same generator, writing the panel layout of vpca_accumulate_panels (buffer: ceil(nv / P) * n_samples * P cells). */
+int vpca_synth_panels_device(vpca_ctx* ctx, uint64_t seed, int64_t v0, int64_t nv, int mode, void* d_x,
+                             int64_t panel_variants);
 
 /* ---- introspection ---------------------------------------------------------------------------------- */
 typedef struct vpca_stats {

@@ -111,25 +111,42 @@ __global__ void __launch_bounds__(kSmallThreads) tridiag_small_kernel(double* __
                                                                        double* __restrict__ off, double* __restrict__ tau,
                                                                        double* __restrict__ scal) {
     __shared__ double red[33];
+    __shared__ double bcast[2];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int j = step[0];
     if (j >= n) return;
     const double* vprev = v2 + (size_t)((j + 1) & 1) * n;
     double* vcur = v2 + (size_t)(j & 1) * n;
     double* rowj = A + (size_t)j * n;
+    double acc = 0.0;
     if (j > 0) {
+        // (a) + (b) in two passes: the dot product, then w and the updated row together (w[j] is recomputed locally)
         const double tau_prev = tau[j - 1];
-        double acc = 0.0;
         for (int t = j + tid; t < n; t += nt) acc += p[t] * vprev[t];
-        const double pv = block_sum(acc, red);
-        const double alpha = 0.5 * tau_prev * pv;
-        for (int t = j + tid; t < n; t += nt) w[t] = p[t] - alpha * vprev[t];
-        __syncthreads();
-        const double vj = vprev[j], wj = w[j];
-        for (int t = j + tid; t < n; t += nt) rowj[t] -= vj * w[t] + wj * vprev[t];
-        __syncthreads();
+        const double alpha = 0.5 * tau_prev * block_sum(acc, red);
+        const double vj = vprev[j];
+        const double wj = p[j] - alpha * vj;
+        acc = 0.0;
+        for (int t = j + tid; t < n; t += nt) {
+            const double vt = vprev[t];
+            const double wt = p[t] - alpha * vt;
+            w[t] = wt;
+            const double r = rowj[t] - (vj * wt + wj * vt);
+            rowj[t] = r;
+            if (t >= j + 2) acc += r * r;
+            if (t == j) bcast[0] = r;
+            if (t == j + 1) bcast[1] = r;
+        }
+    } else {
+        for (int t = tid; t < n; t += nt) {
+            const double r = rowj[t];
+            if (t >= 2) acc += r * r;
+            if (t == 0) bcast[0] = r;
+            if (t == 1) bcast[1] = r;
+        }
     }
-    if (tid == 0) diag[j] = rowj[j];
+    const double xnorm2 = block_sum(acc, red);     // its barriers also publish bcast[]
+    if (tid == 0) diag[j] = bcast[0];
     if (j >= n - 1) {
         if (tid == 0) {
             step[1] = j;
@@ -137,23 +154,17 @@ __global__ void __launch_bounds__(kSmallThreads) tridiag_small_kernel(double* __
         }
         return;
     }
-    // reflector from x = rowj[j+1 .. n)
-    const double alpha = rowj[j + 1];
-    double acc = 0.0;
-    for (int t = j + 2 + tid; t < n; t += nt) {
-        const double x = rowj[t];
-        acc += x * x;
-    }
-    const double xnorm2 = block_sum(acc, red);
+    // (c) reflector from x = rowj[j+1 .. n)
+    const double alpha1 = bcast[1];
     double beta, tj, scale;
     if (xnorm2 == 0.0) {
-        beta = alpha;
+        beta = alpha1;
         tj = 0.0;
         scale = 0.0;
     } else {
-        beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
-        tj = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
+        beta = -copysign(sqrt(alpha1 * alpha1 + xnorm2), alpha1);
+        tj = (beta - alpha1) / beta;
+        scale = 1.0 / (alpha1 - beta);
     }
     for (int t = j + 1 + tid; t < n; t += nt) {
         const double v = (t == j + 1) ? 1.0 : rowj[t] * scale;
@@ -169,10 +180,12 @@ __global__ void __launch_bounds__(kSmallThreads) tridiag_small_kernel(double* __
     }
 }
 
-// Step j, grid-wide: for every trailing row i in [j+1, n) (one warp per row)
+// Step j, grid-wide: for every trailing row i in [j+1, n) (one warp per row, 4 rows per block)
 //   A[i][t] -= vprev[i] w[t] + w[i] vprev[t]      (pending rank-2 update of step j-1),  t in [j+1, n)
 //   p[i]     = tau_j * sum_t A[i][t] vcur[t]      (symmetric matrix-vector product of step j, full rows)
-__global__ void __launch_bounds__(256) tridiag_big_kernel(double* __restrict__ A, int n, const int* __restrict__ step,
+// The loop is unrolled by 4 so that every lane keeps four independent 8-byte loads of the (L2-resident) matrix in
+// flight; the three vectors are L1 hits.
+__global__ void __launch_bounds__(128) tridiag_big_kernel(double* __restrict__ A, int n, const int* __restrict__ step,
                                                           const double* __restrict__ v2,
                                                           const double* __restrict__ w, const double* __restrict__ tau,
                                                           double* __restrict__ p) {
@@ -180,22 +193,36 @@ __global__ void __launch_bounds__(256) tridiag_big_kernel(double* __restrict__ A
     const int j = step[1];
     const int i = j + 1 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
-    const double* vprev = v2 + (size_t)((j + 1) & 1) * n;
-    const double* vcur = v2 + (size_t)(j & 1) * n;
+    const double* __restrict__ vprev = v2 + (size_t)((j + 1) & 1) * n;
+    const double* __restrict__ vcur = v2 + (size_t)(j & 1) * n;
     const double tj = tau[j];
     double* row = A + (size_t)i * n;
     const double vi = vprev[i], wi = w[i];
-    double acc = 0.0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int t = j + 1 + lane;
     if (j > 0) {
-        for (int t = j + 1 + lane; t < n; t += 32) {
+        for (; t + 96 < n; t += 128) {
+            const double r0 = row[t], r1 = row[t + 32], r2 = row[t + 64], r3 = row[t + 96];
+            const double a0 = r0 - (vi * w[t] + wi * vprev[t]);
+            const double a1 = r1 - (vi * w[t + 32] + wi * vprev[t + 32]);
+            const double a2 = r2 - (vi * w[t + 64] + wi * vprev[t + 64]);
+            const double a3 = r3 - (vi * w[t + 96] + wi * vprev[t + 96]);
+            row[t] = a0; row[t + 32] = a1; row[t + 64] = a2; row[t + 96] = a3;
+            acc0 += a0 * vcur[t]; acc1 += a1 * vcur[t + 32]; acc2 += a2 * vcur[t + 64]; acc3 += a3 * vcur[t + 96];
+        }
+        for (; t < n; t += 32) {
             const double a = row[t] - (vi * w[t] + wi * vprev[t]);
             row[t] = a;
-            acc += a * vcur[t];
+            acc0 += a * vcur[t];
         }
     } else {
-        for (int t = j + 1 + lane; t < n; t += 32) acc += row[t] * vcur[t];
+        for (; t + 96 < n; t += 128) {
+            acc0 += row[t] * vcur[t]; acc1 += row[t + 32] * vcur[t + 32];
+            acc2 += row[t + 64] * vcur[t + 64]; acc3 += row[t + 96] * vcur[t + 96];
+        }
+        for (; t < n; t += 32) acc0 += row[t] * vcur[t];
     }
-    acc = warp_sum(acc);
+    const double acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
     if (lane == 0) p[i] = tj * acc;
 }
 
@@ -483,7 +510,7 @@ cudaError_t eig_alloc(EigWork& w, int n, int kmax) {
     VPCA_TRY(cudaMalloc(&w.d_evecs, (size_t)n * kmax * sizeof(double)));
     VPCA_TRY(cudaMalloc(&w.d_lu, 8 * (size_t)n * sizeof(double)));
     VPCA_TRY(cudaMalloc(&w.d_nz, sizeof(int)));
-    VPCA_TRY(cudaMalloc(&w.d_step, 2 * sizeof(int)));
+    VPCA_TRY(cudaMalloc(&w.d_step, 4 * sizeof(int)));   // {next, current step, ticket counter, -}
 #undef VPCA_TRY
     return cudaSuccess;
 }
@@ -515,11 +542,11 @@ cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) 
     cudaMemsetAsync(w.d_tau, 0, (size_t)n * sizeof(double), stream);
     cudaMemsetAsync(w.d_off, 0, 2 * (size_t)n * sizeof(double), stream);
     int64_t nl = 0;
-    cudaMemsetAsync(w.d_step, 0, 2 * sizeof(int), stream);
+    cudaMemsetAsync(w.d_step, 0, 4 * sizeof(int), stream);
     // One CUDA graph holds kGraphSteps identical (small, big) launch pairs; it is replayed until all n steps ran.
     // Blocks of the big kernel beyond the shrinking trailing matrix exit at once, launches past step n are no-ops.
     constexpr int kGraphSteps = 64;
-    const int big_blocks = (n - 1 + 7) / 8 > 0 ? (n - 1 + 7) / 8 : 1;
+    const int big_blocks = (n - 1 + 3) / 4 > 0 ? (n - 1 + 3) / 4 : 1;
     if (w.graph_exec == nullptr || w.graph_n != n) {
         if (w.graph_exec != nullptr) cudaGraphExecDestroy(w.graph_exec);
         w.graph_exec = nullptr;
@@ -529,7 +556,7 @@ cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) 
         for (int g = 0; g < kGraphSteps; ++g) {
             tridiag_small_kernel<<<1, kSmallThreads, 0, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_p, w.d_w, w.d_diag, w.d_off,
                                                                   w.d_tau, w.d_scal);
-            tridiag_big_kernel<<<big_blocks, 256, 0, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_w, w.d_tau, w.d_p);
+            tridiag_big_kernel<<<big_blocks, 128, 0, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_w, w.d_tau, w.d_p);
         }
         e = cudaStreamEndCapture(stream, &graph);
         if (e != cudaSuccess) return e;

@@ -20,21 +20,29 @@
 namespace vpca {
 namespace {
 
-__global__ void encode_i8_kernel(const int64_t* __restrict__ off, int64_t base, const int32_t* __restrict__ idx,
+// cell (s, v) of a row-major tile (panel == 0) or of the panel layout (see vpca_internal.h)
+__device__ __forceinline__ int64_t cell_index(int s, int64_t v, int64_t ld, int64_t panel, int n) {
+    if (panel == 0) return (int64_t)s * ld + v;
+    const int64_t pnl = v / panel;
+    return pnl * (int64_t)n * panel + (int64_t)s * panel + (v - pnl * panel);
+}
+
+template <typename IdxT>
+__global__ void encode_i8_kernel(const int64_t* __restrict__ off, int64_t base, const IdxT* __restrict__ idx,
                                  int64_t nv, int n, int max_mult, uint32_t* __restrict__ xw, int64_t ld,
-                                 int* __restrict__ flags) {
+                                 int64_t panel, int* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int bad = 0;
     for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nv; v += warps) {
         const int64_t e0 = off[v] - base, e1 = off[v + 1] - base;
         for (int64_t e = e0 + lane; e < e1; e += 32) {
-            const int s = idx[e];
+            const int s = (int)idx[e];
             if (s < 0 || s >= n) {
                 bad |= 1;
                 continue;
             }
-            const int64_t byte = (int64_t)s * ld + v;
+            const int64_t byte = cell_index(s, v, ld, panel, n);
             const uint32_t shift = (uint32_t)(byte & 3) * 8u;
             const uint32_t old = atomicAdd(xw + (byte >> 2), 1u << shift);
             if ((int)((old >> shift) & 0xFFu) >= max_mult) bad |= 2;
@@ -43,21 +51,22 @@ __global__ void encode_i8_kernel(const int64_t* __restrict__ off, int64_t base, 
     if (bad) atomicOr(flags, bad);
 }
 
-__global__ void encode_bf16_kernel(const int64_t* __restrict__ off, int64_t base, const int32_t* __restrict__ idx,
+template <typename IdxT>
+__global__ void encode_bf16_kernel(const int64_t* __restrict__ off, int64_t base, const IdxT* __restrict__ idx,
                                    int64_t nv, int n, int max_mult, __nv_bfloat162* __restrict__ x2, int64_t ld,
-                                   int* __restrict__ flags) {
+                                   int64_t panel, int* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int bad = 0;
     for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nv; v += warps) {
         const int64_t e0 = off[v] - base, e1 = off[v + 1] - base;
         for (int64_t e = e0 + lane; e < e1; e += 32) {
-            const int s = idx[e];
+            const int s = (int)idx[e];
             if (s < 0 || s >= n) {
                 bad |= 1;
                 continue;
             }
-            const int64_t el = (int64_t)s * ld + v;
+            const int64_t el = cell_index(s, v, ld, panel, n);
             const bool hi = (el & 1) != 0;
             const __nv_bfloat162 one = __floats2bfloat162_rn(hi ? 0.f : 1.f, hi ? 1.f : 0.f);
             const __nv_bfloat162 old = atomicAdd(x2 + (el >> 1), one);
@@ -70,21 +79,22 @@ __global__ void encode_bf16_kernel(const int64_t* __restrict__ off, int64_t base
 
 // packed e2m1 cells: multiplicity m in {0, 1, 2} is the code 2 m (0b0000, 0b0010 = 1.0, 0b0100 = 2.0), so one
 // occurrence adds 2 to the nibble of cell (s, v); eight cells per 32-bit word.
-__global__ void encode_e2m1_kernel(const int64_t* __restrict__ off, int64_t base, const int32_t* __restrict__ idx,
+template <typename IdxT>
+__global__ void encode_e2m1_kernel(const int64_t* __restrict__ off, int64_t base, const IdxT* __restrict__ idx,
                                    int64_t nv, int n, int max_mult, uint32_t* __restrict__ xw, int64_t ld,
-                                   int* __restrict__ flags) {
+                                   int64_t panel, int* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int bad = 0;
     for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nv; v += warps) {
         const int64_t e0 = off[v] - base, e1 = off[v + 1] - base;
         for (int64_t e = e0 + lane; e < e1; e += 32) {
-            const int s = idx[e];
+            const int s = (int)idx[e];
             if (s < 0 || s >= n) {
                 bad |= 1;
                 continue;
             }
-            const int64_t cell = (int64_t)s * ld + v;
+            const int64_t cell = cell_index(s, v, ld, panel, n);
             const uint32_t shift = (uint32_t)(cell & 7) * 4u;
             const uint32_t old = atomicAdd(xw + (cell >> 3), 2u << shift);
             if ((int)((old >> shift) & 0xFu) >= 2 * max_mult) bad |= 2;
@@ -95,30 +105,51 @@ __global__ void encode_e2m1_kernel(const int64_t* __restrict__ off, int64_t base
 
 }  // namespace
 
-cudaError_t encode_calls(const int64_t* d_off, int64_t base, const int32_t* d_idx, int64_t nv, int n, int elem_bits,
-                         int max_mult, void* d_x, int64_t ld, int* d_flags, cudaStream_t stream) {
-    // zero the nv columns (rounded up to the k-block of 128 cells / 128 bytes the Gram kernel reads) of every row
-    const size_t pitch = (size_t)ld * elem_bits / 8;
-    size_t width = elem_bits == 4 ? (((size_t)nv + 127) / 128) * 64 : ((((size_t)nv * elem_bits / 8) + 127) / 128) * 128;
-    if (width > pitch) width = pitch;
+template <typename IdxT>
+static cudaError_t encode_launch(const int64_t* d_off, int64_t base, const IdxT* d_idx, int64_t nv, int n, int elem_bits,
+                                 int max_mult, void* d_x, int64_t ld, int64_t panel, int* d_flags, cudaStream_t stream);
+
+cudaError_t encode_calls(const int64_t* d_off, int64_t base, const void* d_idx, int idx_bytes, int64_t nv, int n,
+                         int elem_bits, int max_mult, void* d_x, int64_t ld, int64_t panel, int* d_flags,
+                         cudaStream_t stream) {
+    if (idx_bytes == 2)
+        return encode_launch(d_off, base, static_cast<const uint16_t*>(d_idx), nv, n, elem_bits, max_mult, d_x, ld, panel,
+                             d_flags, stream);
+    return encode_launch(d_off, base, static_cast<const int32_t*>(d_idx), nv, n, elem_bits, max_mult, d_x, ld, panel, d_flags,
+                         stream);
+}
+
+template <typename IdxT>
+static cudaError_t encode_launch(const int64_t* d_off, int64_t base, const IdxT* d_idx, int64_t nv, int n, int elem_bits,
+                                 int max_mult, void* d_x, int64_t ld, int64_t panel, int* d_flags, cudaStream_t stream) {
     cudaError_t e = cudaSuccess;
-    if (width > 0) e = cudaMemset2DAsync(d_x, pitch, 0, width, (size_t)n, stream);
+    if (panel > 0) {
+        // whole panels are contiguous: zero every panel the rows touch
+        const size_t npanels = (size_t)((nv + panel - 1) / panel);
+        if (npanels > 0) e = cudaMemsetAsync(d_x, 0, npanels * (size_t)n * (size_t)panel * elem_bits / 8, stream);
+    } else {
+        // zero the nv columns (rounded up to the k-block of 128 cells / 128 bytes the Gram kernel reads) of every row
+        const size_t pitch = (size_t)ld * elem_bits / 8;
+        size_t width = elem_bits == 4 ? (((size_t)nv + 127) / 128) * 64 : ((((size_t)nv * elem_bits / 8) + 127) / 128) * 128;
+        if (width > pitch) width = pitch;
+        if (width > 0) e = cudaMemset2DAsync(d_x, pitch, 0, width, (size_t)n, stream);
+    }
     if (e != cudaSuccess || nv <= 0) return e;
     const int threads = 256;
     const int64_t want = (nv * 32 + threads - 1) / threads;
     const int blocks = (int)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
     if (elem_bits == 4) {
         const int cap = max_mult > 2 ? 2 : max_mult;
-        encode_e2m1_kernel<<<blocks, threads, 0, stream>>>(d_off, base, d_idx, nv, n, cap, reinterpret_cast<uint32_t*>(d_x),
-                                                           ld, d_flags);
+        encode_e2m1_kernel<IdxT><<<blocks, threads, 0, stream>>>(d_off, base, d_idx, nv, n, cap, reinterpret_cast<uint32_t*>(d_x),
+                                                           ld, panel, d_flags);
     } else if (elem_bits == 8) {
         const int cap = max_mult > 127 ? 127 : max_mult;
-        encode_i8_kernel<<<blocks, threads, 0, stream>>>(d_off, base, d_idx, nv, n, cap, reinterpret_cast<uint32_t*>(d_x), ld,
-                                                         d_flags);
+        encode_i8_kernel<IdxT><<<blocks, threads, 0, stream>>>(d_off, base, d_idx, nv, n, cap, reinterpret_cast<uint32_t*>(d_x), ld,
+                                                         panel, d_flags);
     } else {
         const int cap = max_mult > 256 ? 256 : max_mult;   // bf16 holds integers exactly up to 256
-        encode_bf16_kernel<<<blocks, threads, 0, stream>>>(d_off, base, d_idx, nv, n, cap,
-                                                           reinterpret_cast<__nv_bfloat162*>(d_x), ld, d_flags);
+        encode_bf16_kernel<IdxT><<<blocks, threads, 0, stream>>>(d_off, base, d_idx, nv, n, cap,
+                                                           reinterpret_cast<__nv_bfloat162*>(d_x), ld, panel, d_flags);
     }
     return cudaGetLastError();
 }

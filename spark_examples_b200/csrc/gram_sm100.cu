@@ -57,8 +57,12 @@ struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + slack for 1024 B alignment
 };
 
+constexpr int kMaxPeers = 16;
+
 struct GramArgs {
     int32_t* S;
+    int32_t* peer[kMaxPeers];   // num_peers > 0: every flush is added into ALL of these Grams (own included) over NVLink
+    int num_peers;
     const int2* tiles;
     int* err;          // mapped host memory: watchdog diagnostics
     int n;
@@ -68,10 +72,12 @@ struct GramArgs {
     int num_workers;
     int resident;
     int elems_per_kb;  // 128 / sizeof(element)
+    int kb_per_panel;  // k-blocks per panel of the genotype matrix (row-major input = one panel)
     int sync_lead;     // > 0: a worker may run at most this many windows ahead of the slowest one (soft barrier)
     int active_workers;
     int* win_done;     // win_done[w] = number of workers whose producer has issued every load of window w
     long long* prof;   // optional per-CTA timestamps (globaltimer ns): start, first MMA, MMA done, end
+    const double* cum; // cum[w] = fraction of every window's units owned by workers < w (cum[0] = 0, cum[W] = 1)
     int tx_shift;      // TMA transaction bytes per stage = STAGE_BYTES >> tx_shift (1 for packed 4-bit sources: the
                        // mbarrier counts the 8 data bytes of every 16-byte shared-memory chunk, not the gap)
 };
@@ -91,8 +97,9 @@ struct Sched {
         resident = a.resident;
         nwin = (kb_total + kbw - 1) / kbw;
         const long long uw = (long long)a.num_tiles * kbw;
-        u_begin = uw * worker / a.num_workers;
-        u_end = uw * (worker + 1) / a.num_workers;
+        // speed-weighted split (equal shares until the first launches have been timed, see rebalance_kernel)
+        u_begin = (long long)((double)uw * a.cum[worker]);
+        u_end = (worker + 1 == a.num_workers) ? uw : (long long)((double)uw * a.cum[worker + 1]);
         u = u_begin;
         win = 0;
         seg_in_win = 0;
@@ -177,8 +184,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 template <int CG, int KIND>
-__device__ __forceinline__ uint32_t make_instr_desc() {
-    constexpr uint32_t M = 128 * CG, N = kUmmaN;
+__device__ __forceinline__ uint32_t make_instr_desc(uint32_t N) {
+    constexpr uint32_t M = 128 * CG;
     // c_format [4,6): 1 = F32, 2 = S32; a/b_format [7,10)/[10,13): kind::i8 -> 1 (signed int8), kind::f16 -> 1 (BF16),
     // kind::f8f6f4 -> 5 (E2M1); a/b major bits 15/16 = 0 (K-major); n_dim [17,23) = N >> 3; m_dim [24,29) = M >> 4.
     constexpr uint32_t cfmt = (KIND == 0) ? 2u : 1u;
@@ -244,7 +251,10 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
             while (sc.next(s)) {
                 const int2 t = a.tiles[s.tile];
                 const int rowA = t.x * C::BM + (int)cta_rank * kBoxRows;
-                const int rowB = t.y * C::BN + ((CG == 2) ? (int)cta_rank * kBoxRows : 0);
+                // Edge tiles issue a narrower MMA (N = rows of S that exist, rounded up to 16); with cta_group::2 each CTA
+                // supplies half of those N rows, so its box starts at half * N / 2 (= half * 128 for full tiles).
+                const int n_eff = min(C::BN, ((a.n - t.y * C::BN) + 15) & ~15);
+                const int rowB = t.y * C::BN + ((CG == 2) ? (int)cta_rank * (n_eff / 2) : 0);
                 if (a.sync_lead > 0 && leader && s.win != synced_win) {
                     synced_win = s.win;
                     if (s.win >= a.sync_lead) wait_window(a.win_done, s.win - a.sync_lead, a.active_workers);
@@ -252,15 +262,16 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                 for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
                     const uint32_t st = it % C::STAGES, ph = (it / C::STAGES) & 1u;
                     mbar_wait(empty_bar(st), ph ^ 1u, a.err, 1);
-                    const int kc = kb * a.elems_per_kb;
+                    const int pnl = kb / a.kb_per_panel;
+                    const int kc = (kb - pnl * a.kb_per_panel) * a.elems_per_kb;
                     if constexpr (CG == 1) {
                         ptx::mbar_arrive_expect_tx(full_bar(st), (uint32_t)C::STAGE_BYTES >> a.tx_shift);
-                        ptx::tma_load_2d(sA(st), &tmap, full_bar(st), kc, rowA);
-                        ptx::tma_load_2d(sB(st), &tmap, full_bar(st), kc, rowB);
-                        ptx::tma_load_2d(sB(st) + kBoxBytes, &tmap, full_bar(st), kc, rowB + kBoxRows);
+                        ptx::tma_load_3d(sA(st), &tmap, full_bar(st), kc, rowA, pnl);
+                        ptx::tma_load_3d(sB(st), &tmap, full_bar(st), kc, rowB, pnl);
+                        ptx::tma_load_3d(sB(st) + kBoxBytes, &tmap, full_bar(st), kc, rowB + kBoxRows, pnl);
                     } else {
-                        ptx::tma_load_2d_2sm(sA(st), &tmap, full_bar(st), kc, rowA);
-                        ptx::tma_load_2d_2sm(sB(st), &tmap, full_bar(st), kc, rowB);
+                        ptx::tma_load_3d_2sm(sA(st), &tmap, full_bar(st), kc, rowA, pnl);
+                        ptx::tma_load_3d_2sm(sB(st), &tmap, full_bar(st), kc, rowB, pnl);
                         if (leader) ptx::mbar_arrive_expect_tx(full_bar(st), (uint32_t)(2 * C::STAGE_BYTES) >> a.tx_shift);
                         else ptx::mbar_arrive_cluster(full_bar(st), 0);
                     }
@@ -271,7 +282,6 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
         }
     } else if (warp == 1 && leader) {
         // ===================================== MMA issuer =======================================
-        const uint32_t idesc = make_instr_desc<CG, KIND>();
         Sched sc;
         sc.init(a, worker);
         Seg s;
@@ -282,6 +292,8 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                 ptx::tc_fence_after();
             }
             const uint32_t d_tmem = tmem_base + (uint32_t)s.slot * kUmmaN;
+            const int by = a.tiles[s.tile].y;
+            const uint32_t idesc = make_instr_desc<CG, KIND>((uint32_t)min(C::BN, ((a.n - by * C::BN) + 15) & ~15));
             for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
                 const uint32_t st = it % C::STAGES, ph = (it / C::STAGES) & 1u;
                 mbar_wait(full_bar(st), ph, a.err, 3);
@@ -335,9 +347,17 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                         int v;
                         if constexpr (KIND == 0) v = (int)r[j];
                         else v = __float2int_rn(__uint_as_float(r[j]));
-                        if (v != 0)
-                            asm volatile("red.global.add.s32 [%0], %1;" ::"l"(out + (size_t)row * (size_t)a.n), "r"(v)
-                                         : "memory");
+                        if (v != 0) {
+                            const size_t o = (size_t)row * (size_t)a.n;
+                            if (a.num_peers == 0) {
+                                asm volatile("red.global.add.s32 [%0], %1;" ::"l"(out + o), "r"(v) : "memory");
+                            } else {
+                                // fused reduceByKey: the same red, once per rank, on peer-mapped Gram buffers
+                                for (int d = 0; d < a.num_peers; ++d)
+                                    asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(a.peer[d] + col + o), "r"(v)
+                                                 : "memory");
+                            }
+                        }
                     }
                 }
             }
@@ -354,6 +374,74 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Adaptive stream-K split.  Workers do not all run at the same speed: with int8 operands the kernel needs ~64 B/clk
+// per SM from L2 and the SMs of some GPCs get visibly less (measured: per-worker MMA time 1.7 .. 2.4 ms for equal
+// shares), so an equal split waits for the slowest pair.  After every sufficiently long launch this kernel turns the
+// per-worker timestamps into speeds (units / time) and moves the shares of the next launch towards them.  The Gram
+// stays exact whatever the split is (integer atomics); shares are clamped so that a worker never spans more than
+// the two tiles it has TMEM accumulators for.
+__global__ void rebalance_kernel(const long long* __restrict__ prof, double* __restrict__ cum, int workers, int cta_group,
+                                 double max_share, long long min_ns, int* __restrict__ gen) {
+    __shared__ double sh[1024];
+    __shared__ double red_sum, red_min;
+    const int w = threadIdx.x;
+    const bool active = w < workers;
+    double t = 0.0, share_old = 0.0;
+    if (active) {
+        const long long t0 = prof[(size_t)w * cta_group * 4 + 0], t1 = prof[(size_t)w * cta_group * 4 + 2];
+        t = (double)(t1 - t0);
+        share_old = cum[w + 1] - cum[w];
+    }
+    sh[w] = active ? t : 1e30;
+    __syncthreads();
+    if (w == 0) {
+        double mn = 1e30, mx = 0.0;
+        for (int i = 0; i < workers; ++i) {
+            mn = fmin(mn, sh[i]);
+            mx = fmax(mx, sh[i]);
+        }
+        // too short to time, or already balanced to within 3 %: keep the shares (hysteresis against noise)
+        red_min = (mn < (double)min_ns || (mx - mn) < 0.03 * mx) ? -1.0 : mn;
+    }
+    __syncthreads();
+    if (red_min < 0.0) return;
+    const double speed = active ? share_old / t : 0.0;
+    sh[w] = speed;
+    __syncthreads();
+    if (w == 0) {
+        double sum = 0.0;
+        for (int i = 0; i < workers; ++i) sum += sh[i];
+        red_sum = sum;
+    }
+    __syncthreads();
+    double share = 0.0;
+    if (active) {
+        const double est = speed / red_sum;
+        share = 0.5 * share_old + 0.5 * est;
+        const double avg = 1.0 / workers;
+        share = fmin(fmax(share, 0.5 * avg), max_share * avg);
+    }
+    __syncthreads();
+    sh[w] = share;
+    __syncthreads();
+    if (w == 0) {
+        double sum = 0.0;
+        for (int i = 0; i < workers; ++i) sum += sh[i];
+        double acc = 0.0;
+        cum[0] = 0.0;
+        for (int i = 0; i < workers; ++i) {
+            acc += sh[i] / sum;
+            cum[i + 1] = (i + 1 == workers) ? 1.0 : acc;
+        }
+        *gen += 1;
+    }
+}
+
+__global__ void init_cum_kernel(double* __restrict__ cum, int workers) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= workers) cum[i] = (double)i / (double)workers;
+}
+
 __global__ void symmetrize_kernel(int32_t* __restrict__ S, int n) {
     // block (bx >= by): read lower tile (bx, by), write it transposed into the upper tile (by, bx)
     __shared__ int32_t tile[32][33];
@@ -375,6 +463,37 @@ __global__ void add_i32_kernel(int32_t* __restrict__ dst, const int32_t* __restr
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < count; i += stride) dst[i] += src[i];
+}
+
+struct PeerPtrs {
+    int32_t* p[kMaxPeers];
+};
+
+__global__ void add_i32_peers_kernel(PeerPtrs dst, int npeers, const int32_t* __restrict__ src, int64_t count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) {
+        const int v = src[i];
+        if (v != 0)
+            for (int d = 0; d < npeers; ++d)
+                asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(dst.p[d] + i), "r"(v) : "memory");
+    }
+}
+
+// All-rank barrier over peer-mapped flag words: rank r publishes `epoch` in slot r of every rank's flag array, then
+// waits until every slot of its own array shows it.  One thread per peer.
+__global__ void peer_barrier_kernel(PeerPtrs flags, int npeers, int rank, int epoch) {
+    const int d = threadIdx.x;
+    if (d < npeers) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flags.p[d] + rank), "r"(epoch) : "memory");
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags.p[rank] + d) : "memory");
+        } while (v < epoch);
+    }
+    __syncthreads();
+    __threadfence_system();
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -425,6 +544,8 @@ void gram_plan_free(GramPlan& plan) {
     if (plan.d_err) cudaFreeHost(plan.d_err);
     if (plan.d_win_done) cudaFree(plan.d_win_done);
     if (plan.d_prof) cudaFree(plan.d_prof);
+    if (plan.d_cum) cudaFree(plan.d_cum);
+    plan.d_cum = nullptr;
     plan.d_win_done = nullptr;
     plan.d_prof = nullptr;
     plan.d_tiles = nullptr;
@@ -462,7 +583,7 @@ static cudaError_t build_tiles(GramPlan& plan, int n, cudaStream_t stream) {
     return e;
 }
 
-cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int n, int64_t nv, int64_t ld,
+cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int n, int64_t nv, int64_t ld, int64_t panel,
                             int32_t* d_S, cudaStream_t stream, std::string* err) {
     if (nv <= 0) return cudaSuccess;
     EncodeTiledFn encode = get_encode_fn();
@@ -482,13 +603,17 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         if (sl != nullptr) plan.sync_lead = atoi(sl);
         const char* pf = getenv("VPCA_GRAM_PROF");
         plan.profile = (pf != nullptr && atoi(pf) != 0);
+        const char* ad = getenv("VPCA_ADAPTIVE");
+        if (ad != nullptr) plan.adaptive = atoi(ad) != 0;
     }
     if (plan.d_win_done == nullptr) {
         cudaError_t e = cudaMalloc(&plan.d_win_done, GramPlan::kMaxWindows * sizeof(int));
         if (e != cudaSuccess) return e;
     }
-    if (plan.profile && plan.d_prof == nullptr) {
+    if ((plan.profile || plan.adaptive) && plan.d_prof == nullptr) {
         cudaError_t e = cudaMalloc(&plan.d_prof, 1024 * 4 * sizeof(long long));
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(plan.d_prof, 0, 1024 * 4 * sizeof(long long), stream);
         if (e != cudaSuccess) return e;
     }
     if (plan.d_err == nullptr) {
@@ -500,6 +625,13 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         cudaError_t e = build_tiles(plan, n, stream);
         if (e != cudaSuccess) return e;
     }
+    if (panel > 0) {
+        if ((panel % 128) != 0) {
+            if (err) *err = "panel_variants must be a multiple of 128";
+            return cudaErrorInvalidValue;
+        }
+        ld = panel;   // rows of a panel are `panel` cells apart, panels n * panel cells apart
+    }
     const uintptr_t align = (elem_bits == 4) ? 31 : 15;
     if ((reinterpret_cast<uintptr_t>(d_x) & align) != 0 || (((ld * elem_bits) / 8) & align) != 0 ||
         (elem_bits == 4 && (ld % 128) != 0)) {
@@ -509,21 +641,35 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
 
     const int cgp = plan.cta_group;
     const int workers = (cgp == 2) ? plan.num_sms / 2 : plan.num_sms;
+    if (plan.d_cum == nullptr || plan.cum_workers != workers || plan.cum_tiles != plan.num_tiles) {
+        if (plan.d_cum) cudaFree(plan.d_cum);
+        cudaError_t e = cudaMalloc(&plan.d_cum, (size_t)(workers + 2) * sizeof(double) + sizeof(int));
+        if (e != cudaSuccess) return e;
+        init_cum_kernel<<<(workers + 256) / 256, 256, 0, stream>>>(plan.d_cum, workers);
+        e = cudaMemsetAsync(plan.d_cum + workers + 2, 0, sizeof(int), stream);
+        if (e != cudaSuccess) return e;
+        plan.cum_workers = workers;
+        plan.cum_tiles = plan.num_tiles;
+    }
     // one k-block = one 128-byte swizzle atom of shared memory: 128 int8, 64 bf16 or 128 e2m1 cells (TMA expands
     // 4-bit cells to one byte each, CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B)
     const int elems_per_kb = (elem_bits == 16) ? 64 : 128;
     const int kind = (elem_bits == 8) ? 0 : (elem_bits == 16 ? 1 : 2);
 
     CUtensorMap tmap;
-    // e2m1: globalDim[0] must be a multiple of 128 (the caller guarantees zero cells up to there)
-    const cuuint64_t gdim[2] = {(cuuint64_t)(elem_bits == 4 ? ((nv + 127) / 128) * 128 : nv), (cuuint64_t)n};
-    const cuuint64_t gstride[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bits / 8};
-    const cuuint32_t box[2] = {(cuuint32_t)elems_per_kb, (cuuint32_t)kBoxRows};
-    const cuuint32_t estr[2] = {1, 1};
+    // Panel layout: dim0 = cells of one panel row, dim1 = samples, dim2 = panels.  Row-major input is one panel as
+    // wide as the tile.  e2m1: globalDim[0] must be a multiple of 128 (the caller guarantees zero cells up to there).
+    const int64_t npanels = panel > 0 ? (nv + panel - 1) / panel : 1;
+    const int64_t dim0 = panel > 0 ? panel : (elem_bits == 4 ? ((nv + 127) / 128) * 128 : nv);
+    const cuuint64_t gdim[3] = {(cuuint64_t)dim0, (cuuint64_t)n, (cuuint64_t)npanels};
+    const cuuint64_t gstride[2] = {(cuuint64_t)ld * (cuuint64_t)elem_bits / 8,
+                                   (cuuint64_t)n * (cuuint64_t)ld * (cuuint64_t)elem_bits / 8};
+    const cuuint32_t box[3] = {(cuuint32_t)elems_per_kb, (cuuint32_t)kBoxRows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
     const CUtensorMapDataType tmtype = elem_bits == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                        : (elem_bits == 16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                           : CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B);
-    CUresult r = encode(&tmap, tmtype, 2,
+    CUresult r = encode(&tmap, tmtype, 3,
                         const_cast<void*>(d_x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -534,16 +680,20 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
 
     GramArgs args{};
     args.S = d_S;
+    args.num_peers = (plan.num_peers > 1 && d_S == plan.peer_S[plan.peer_rank]) ? plan.num_peers : 0;
+    for (int d = 0; d < kMaxPeers; ++d) args.peer[d] = d < plan.num_peers ? plan.peer_S[d] : nullptr;
     args.tiles = plan.d_tiles;
     cudaHostGetDevicePointer(reinterpret_cast<void**>(&args.err), plan.d_err, 0);
     args.n = n;
     args.num_tiles = plan.num_tiles;
     args.kb_total = (int)((nv + elems_per_kb - 1) / elems_per_kb);
+    args.kb_per_panel = panel > 0 ? (int)(panel / elems_per_kb) : args.kb_total;
     args.num_workers = workers;
     args.resident = plan.num_tiles <= workers ? 1 : 0;
     args.elems_per_kb = elems_per_kb;
     if (args.resident) {
         int kbw = plan.kb_window;
+        if (kbw <= 0 && panel > 0) kbw = args.kb_per_panel;   // one L2 window per panel
         if (kbw <= 0) {
             // window of X sized to ~32 MiB so that every tile re-reads it from L2 (126 MB) rather than HBM
             const long long target = 32ll << 20;
@@ -559,7 +709,10 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     args.active_workers = (int)std::min<long long>(workers, uw);
     args.sync_lead = (args.resident && nwin <= GramPlan::kMaxWindows) ? plan.sync_lead : 0;
     args.win_done = plan.d_win_done;
-    args.prof = plan.profile ? plan.d_prof : nullptr;
+    const bool adapt = plan.adaptive && args.resident && workers <= 1024 && plan.num_tiles < workers &&
+                       args.active_workers == workers;
+    args.prof = (plan.profile || adapt) ? plan.d_prof : nullptr;
+    args.cum = plan.d_cum;
     args.tx_shift = (elem_bits == 4 && getenv("VPCA_E2M1_TX_FULL") == nullptr) ? 1 : 0;
     if (args.sync_lead > 0) {
         cudaError_t e = cudaMemsetAsync(plan.d_win_done, 0, (size_t)nwin * sizeof(int), stream);
@@ -567,11 +720,22 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     }
 
     const int grid = workers * cgp;
+    cudaError_t le;
     if (cgp == 2)
-        return kind == 0 ? launch<2, 0>(tmap, args, grid, stream)
-                         : (kind == 1 ? launch<2, 1>(tmap, args, grid, stream) : launch<2, 2>(tmap, args, grid, stream));
-    return kind == 0 ? launch<1, 0>(tmap, args, grid, stream)
-                     : (kind == 1 ? launch<1, 1>(tmap, args, grid, stream) : launch<1, 2>(tmap, args, grid, stream));
+        le = kind == 0 ? launch<2, 0>(tmap, args, grid, stream)
+                       : (kind == 1 ? launch<2, 1>(tmap, args, grid, stream) : launch<2, 2>(tmap, args, grid, stream));
+    else
+        le = kind == 0 ? launch<1, 0>(tmap, args, grid, stream)
+                       : (kind == 1 ? launch<1, 1>(tmap, args, grid, stream) : launch<1, 2>(tmap, args, grid, stream));
+    if (le != cudaSuccess) return le;
+    if (adapt) {
+        // a worker may own at most one tile's worth of units per window (two resident accumulators)
+        const double max_share = std::min(1.35, 0.98 * (double)workers / (double)plan.num_tiles);
+        rebalance_kernel<<<1, 1024, 0, stream>>>(plan.d_prof, plan.d_cum, workers, cgp, max_share, 300000,
+                                                 reinterpret_cast<int*>(plan.d_cum + workers + 2));
+        le = cudaGetLastError();
+    }
+    return le;
 }
 
 cudaError_t gram_symmetrize(int32_t* d_S, int n, cudaStream_t stream) {
@@ -582,6 +746,21 @@ cudaError_t gram_symmetrize(int32_t* d_S, int n, cudaStream_t stream) {
 
 cudaError_t gram_add(int32_t* d_dst, const int32_t* d_src, int64_t count, cudaStream_t stream) {
     add_i32_kernel<<<592, 256, 0, stream>>>(d_dst, d_src, count);
+    return cudaGetLastError();
+}
+
+cudaError_t gram_add_peers(GramPlan& plan, const int32_t* d_src, int64_t count, cudaStream_t stream) {
+    PeerPtrs pp{};
+    for (int d = 0; d < plan.num_peers; ++d) pp.p[d] = plan.peer_S[d];
+    add_i32_peers_kernel<<<592, 256, 0, stream>>>(pp, plan.num_peers, d_src, count);
+    return cudaGetLastError();
+}
+
+cudaError_t gram_peer_barrier(GramPlan& plan, cudaStream_t stream) {
+    PeerPtrs pp{};
+    for (int d = 0; d < plan.num_peers; ++d) pp.p[d] = plan.peer_flags[d];
+    plan.peer_epoch += 1;
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(pp, plan.num_peers, plan.peer_rank, plan.peer_epoch);
     return cudaGetLastError();
 }
 

@@ -113,6 +113,24 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const void* d
         : "memory");
 }
 
+// 3D variants (the genotype matrix is stored as panels: coordinate 2 selects the panel)
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* desc, uint32_t bar, int32_t c0, int32_t c1,
+                                            int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const void* desc, uint32_t bar, int32_t c0,
+                                                int32_t c1, int32_t c2) {
+    const uint32_t leader_bar = bar & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4, %5}], [%2];" ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(desc)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {

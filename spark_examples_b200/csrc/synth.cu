@@ -74,9 +74,17 @@ __device__ __forceinline__ int pop_of(int s, const PopBounds& pb) {
 
 // One thread = one sample pair (rows 2p, 2p+1) x 16 consecutive variants.  Lanes run along the variant axis so
 // a warp writes 512 contiguous bytes (int8) of each of its two rows.
+// Tile column jt = jbase + j of the cell; row-major (panel == 0): x[s * ld + jt]; panel layout: see vpca_internal.h.
+__device__ __forceinline__ int64_t tile_index(int s, int64_t jt, int64_t ld, int64_t panel, int n) {
+    if (panel == 0) return (int64_t)s * ld + jt;
+    const int64_t pnl = jt / panel;
+    return pnl * (int64_t)n * panel + (int64_t)s * panel + (jt - pnl * panel);
+}
+
 template <typename T>
 __global__ void synth_dense_kernel(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, const PopBounds pb,
-                                   const uint32_t* __restrict__ thr, T* __restrict__ x, int64_t ld) {
+                                   const uint32_t* __restrict__ thr, T* __restrict__ x, int64_t ld, int64_t panel,
+                                   int64_t jbase) {
     const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // 16-variant chunk
     const int pair = blockIdx.y * blockDim.y + threadIdx.y;
     const int64_t j0 = chunk * 16;
@@ -109,8 +117,8 @@ __global__ void synth_dense_kernel(uint64_t seed, int n, int64_t v0, int64_t nv,
             v1row[i] = __float2bfloat16_rn((float)g1);
         }
     }
-    T* r0 = x + (int64_t)s0 * ld + j0;
-    T* r1 = r0 + ld;
+    T* r0 = x + tile_index(s0, jbase + j0, ld, panel, n);
+    T* r1 = x + tile_index(has1 ? s0 + 1 : s0, jbase + j0, ld, panel, n);
     if (j0 + 16 <= nv) {
         constexpr int nvec = 16 * (int)sizeof(T) / 16;
         const uint4* p0 = reinterpret_cast<const uint4*>(v0row);
@@ -131,7 +139,8 @@ __global__ void synth_dense_kernel(uint64_t seed, int n, int64_t v0, int64_t nv,
 // packed e2m1 variant: one thread = one sample pair x 16 consecutive variants = 8 bytes per row (cell j of a row in
 // nibble j & 1 of byte j / 2; dosage m is the code 2 m).  Cells in [nv, round_up(nv, 128)) are written as zero.
 __global__ void synth_e2m1_kernel(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, const PopBounds pb,
-                                  const uint32_t* __restrict__ thr, uint8_t* __restrict__ x, int64_t pitch_bytes) {
+                                  const uint32_t* __restrict__ thr, uint8_t* __restrict__ x, int64_t ld, int64_t panel,
+                                  int64_t jbase) {
     const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int pair = blockIdx.y * blockDim.y + threadIdx.y;
     const int64_t j0 = chunk * 16;
@@ -159,19 +168,34 @@ __global__ void synth_e2m1_kernel(uint64_t seed, int n, int64_t v0, int64_t nv, 
             w1[i >> 3] |= (2u * g1) << (4 * (i & 7));
         }
     }
-    uint2* r0 = reinterpret_cast<uint2*>(x + (int64_t)s0 * pitch_bytes + j0 / 2);
-    *r0 = make_uint2(w0[0], w0[1]);
-    if (has1) *reinterpret_cast<uint2*>(x + (int64_t)(s0 + 1) * pitch_bytes + j0 / 2) = make_uint2(w1[0], w1[1]);
+    *reinterpret_cast<uint2*>(x + tile_index(s0, jbase + j0, ld, panel, n) / 2) = make_uint2(w0[0], w0[1]);
+    if (has1) *reinterpret_cast<uint2*>(x + tile_index(s0 + 1, jbase + j0, ld, panel, n) / 2) = make_uint2(w1[0], w1[1]);
 }
 
 }  // namespace
 
 cudaError_t synth_dense(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, int elem_bits, void* d_x, int64_t ld,
-                        cudaStream_t stream) {
+                        int64_t panel, cudaStream_t stream) {
     if (nv <= 0 || n <= 0) return cudaSuccess;
     const int elem_bytes = elem_bits / 8;
+    if (panel > 0) {
+        if ((panel % 128) != 0) return cudaErrorInvalidValue;
+        ld = panel;
+        // zero the cells after nv in the last panel (the Gram kernel reads whole k-blocks of it)
+        const int64_t npanels = (nv + panel - 1) / panel, tail = npanels * panel - nv;
+        if (tail > 0 && elem_bits != 4) {
+            const size_t bytes = (size_t)elem_bytes;
+            cudaError_t em = cudaMemset2DAsync(static_cast<char*>(d_x) + ((size_t)(npanels - 1) * n * panel + (size_t)(panel - tail)) * bytes,
+                                               (size_t)panel * bytes, 0, (size_t)tail * bytes, (size_t)n, stream);
+            if (em != cudaSuccess) return em;
+        } else if (tail > 0) {
+            cudaError_t em = cudaMemsetAsync(static_cast<char*>(d_x) + (size_t)(npanels - 1) * n * panel / 2, 0,
+                                             (size_t)n * panel / 2, stream);   // e2m1: clear the whole last panel first
+            if (em != cudaSuccess) return em;
+        }
+    }
     if (elem_bits == 4) {
-        if ((reinterpret_cast<uintptr_t>(d_x) & 31) != 0 || (ld % 128) != 0 || ld < ((nv + 127) / 128) * 128)
+        if ((reinterpret_cast<uintptr_t>(d_x) & 31) != 0 || (ld % 128) != 0 || (panel == 0 && ld < ((nv + 127) / 128) * 128))
             return cudaErrorInvalidValue;
     } else if ((reinterpret_cast<uintptr_t>(d_x) & 15) != 0 || ((ld * elem_bytes) & 15) != 0) {
         return cudaErrorInvalidValue;
@@ -194,13 +218,13 @@ cudaError_t synth_dense(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, 
             const int64_t chunks4 = (((cnt + 127) / 128) * 128) / 16;
             const dim3 grid4((unsigned)((chunks4 + 31) / 32), grid.y);
             synth_e2m1_kernel<<<grid4, block, 0, stream>>>(seed, n, v0 + b, cnt, mode, pb, d_thr,
-                                                           reinterpret_cast<uint8_t*>(d_x) + b / 2, ld / 2);
+                                                           reinterpret_cast<uint8_t*>(d_x), ld, panel, b);
         } else if (elem_bytes == 1)
             synth_dense_kernel<int8_t><<<grid, block, 0, stream>>>(seed, n, v0 + b, cnt, mode, pb, d_thr,
-                                                                   reinterpret_cast<int8_t*>(d_x) + b, ld);
+                                                                   reinterpret_cast<int8_t*>(d_x), ld, panel, b);
         else
             synth_dense_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(seed, n, v0 + b, cnt, mode, pb, d_thr,
-                                                                          reinterpret_cast<__nv_bfloat16*>(d_x) + b, ld);
+                                                                          reinterpret_cast<__nv_bfloat16*>(d_x), ld, panel, b);
         e = cudaGetLastError();
     }
     cudaFreeAsync(d_thr, stream);

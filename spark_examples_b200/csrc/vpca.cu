@@ -46,7 +46,8 @@ struct vpca_ctx {
     std::vector<Slot> slots;
 
     // CSR / dense staging, double buffered
-    int64_t chunk_variants = 0, chunk_nnz = 0, ld_chunk = 0;
+    int64_t chunk_variants = 0, chunk_nnz = 0;
+    int64_t panel = 8192;   // cells per panel row of the internal dense staging tiles (VPCA_PANEL)
     int64_t* d_off[2] = {nullptr, nullptr};
     int32_t* d_idx[2] = {nullptr, nullptr};
     void* d_x[2] = {nullptr, nullptr};
@@ -101,13 +102,16 @@ int ensure_staging(vpca_ctx* ctx) {
         cv = (256ll << 20) * 8 / ((int64_t)n * bits);
         cv = std::max<int64_t>(1024, std::min<int64_t>(cv, 1 << 20));
     }
-    cv = ((cv + 127) / 128) * 128;
+    if (const char* pe = getenv("VPCA_PANEL")) {
+        const int64_t pv = atoll(pe);
+        if (pv >= 128 && pv % 128 == 0) ctx->panel = pv;
+    }
+    cv = std::max<int64_t>(ctx->panel, (cv / ctx->panel) * ctx->panel);   // whole panels
     int64_t cz = ctx->cfg.chunk_nnz;
     if (cz <= 0) cz = 64ll << 20;
     cz = std::max<int64_t>(cz, 1024);
     ctx->chunk_variants = cv;
     ctx->chunk_nnz = cz;
-    ctx->ld_chunk = cv;
     for (int b = 0; b < 2; ++b) {
         CUDA_OK(ctx, cudaMalloc(&ctx->d_off[b], (size_t)(cv + 1) * sizeof(int64_t)));
         CUDA_OK(ctx, cudaMalloc(&ctx->d_idx[b], (size_t)cz * sizeof(int32_t)));
@@ -119,19 +123,23 @@ int ensure_staging(vpca_ctx* ctx) {
     return VPCA_OK;
 }
 
-int launch_gram(vpca_ctx* ctx, const void* d_x, int64_t nv, int64_t ld, int32_t* d_target) {
-    // fp32 TMEM accumulation (bf16) is exact only below 2^24: bound the variants one launch may fold
+int launch_gram(vpca_ctx* ctx, const void* d_x, int64_t nv, int64_t ld, int64_t panel, int32_t* d_target) {
+    // fp32 TMEM accumulation (bf16 / e2m1) is exact only below 2^24: bound the variants one launch may fold
     int64_t limit = nv;
-    if (ctx->elem_bits != 8) {   // bf16 / e2m1 accumulate in fp32
+    if (ctx->elem_bits != 8) {
         limit = (int64_t)(16777216ll / ((int64_t)ctx->max_mult * ctx->max_mult));
-        limit = std::max<int64_t>(128, (limit / 128) * 128);
+        const int64_t q = panel > 0 ? panel : 128;
+        limit = std::max<int64_t>(q, (limit / q) * q);
     }
     for (int64_t v0 = 0; v0 < nv; v0 += limit) {
         const int64_t cnt = std::min<int64_t>(limit, nv - v0);
         std::string msg;
         cudaEventRecord(ctx->ev_t0, ctx->stream);
-        cudaError_t e = gram_accumulate(ctx->plan, static_cast<const char*>(d_x) + (size_t)v0 * ctx->elem_bits / 8,
-                                        ctx->elem_bits, ctx->n, cnt, ld, d_target, ctx->stream, &msg);
+        // sub-launches start on a panel boundary (panel layout) or at column v0 (row-major)
+        const size_t byte_off = panel > 0 ? (size_t)(v0 / panel) * (size_t)ctx->n * (size_t)panel * ctx->elem_bits / 8
+                                          : (size_t)v0 * ctx->elem_bits / 8;
+        cudaError_t e = gram_accumulate(ctx->plan, static_cast<const char*>(d_x) + byte_off, ctx->elem_bits, ctx->n, cnt, ld,
+                                        panel, d_target, ctx->stream, &msg);
         cudaEventRecord(ctx->ev_t1, ctx->stream);
         if (e != cudaSuccess)
             return fail(ctx, VPCA_ERR_CUDA, "Gram launch failed: %s %s", cudaGetErrorString(e), msg.c_str());
@@ -174,8 +182,8 @@ vpca_ctx::Slot* find_slot(vpca_ctx* ctx, int64_t pid, bool create, int* rc) {
 }
 
 // CSR rows -> encode -> (optionally) Gram.  out_tile != nullptr: copy the encoded tile back instead of the Gram.
-int process_calls(vpca_ctx* ctx, const int64_t* offsets, const int32_t* sample_idx, int64_t nv, int32_t* d_target,
-                  void* out_tile, int64_t out_ld) {
+int process_calls(vpca_ctx* ctx, const int64_t* offsets, const void* sample_idx, int idx_bytes, int64_t nv,
+                  int32_t* d_target, void* out_tile, int64_t out_ld) {
     int rc = ensure_staging(ctx);
     if (rc != VPCA_OK) return rc;
     const int bits = ctx->elem_bits;
@@ -204,22 +212,29 @@ int process_calls(vpca_ctx* ctx, const int64_t* offsets, const int32_t* sample_i
         CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_off[b], offsets + v, (size_t)(nvc + 1) * sizeof(int64_t),
                                      cudaMemcpyHostToDevice, ctx->copy_stream));
         if (nnz > 0)
-            CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_idx[b], sample_idx + offsets[v], (size_t)nnz * sizeof(int32_t),
-                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+            CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_idx[b], static_cast<const char*>(sample_idx) + (size_t)offsets[v] * idx_bytes,
+                                         (size_t)nnz * idx_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
-        ctx->st.h2d_bytes += (nvc + 1) * 8 + nnz * 4;
+        ctx->st.h2d_bytes += (nvc + 1) * 8 + nnz * idx_bytes;
         CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
-        CUDA_OK(ctx, encode_calls(ctx->d_off[b], offsets[v], ctx->d_idx[b], nvc, ctx->n, bits, ctx->max_mult, ctx->d_x[b],
-                                  ctx->ld_chunk, ctx->d_flags, ctx->stream));
+        const int64_t P = ctx->panel;
+        CUDA_OK(ctx, encode_calls(ctx->d_off[b], offsets[v], ctx->d_idx[b], idx_bytes, nvc, ctx->n, bits, ctx->max_mult, ctx->d_x[b], P,
+                                  P, ctx->d_flags, ctx->stream));
         ctx->st.kernel_launches += 2;
         if (out_tile != nullptr) {
-            // (chunk boundaries are multiples of 128 variants, so 4-bit rows split on byte boundaries)
-            CUDA_OK(ctx, cudaMemcpy2DAsync(static_cast<char*>(out_tile) + (size_t)v * bits / 8, (size_t)out_ld * bits / 8,
-                                           ctx->d_x[b], (size_t)ctx->ld_chunk * bits / 8, (size_t)(nvc * bits + 7) / 8,
-                                           (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+            // panel layout -> the caller's row-major tile, one 2-D copy per panel (chunk boundaries are multiples of
+            // 128 variants, so 4-bit rows split on byte boundaries)
+            for (int64_t pv = 0; pv < nvc; pv += P) {
+                const int64_t wv = std::min(P, nvc - pv);
+                CUDA_OK(ctx, cudaMemcpy2DAsync(static_cast<char*>(out_tile) + (size_t)(v + pv) * bits / 8,
+                                               (size_t)out_ld * bits / 8,
+                                               static_cast<const char*>(ctx->d_x[b]) + (size_t)(pv / P) * ctx->n * P * bits / 8,
+                                               (size_t)P * bits / 8, (size_t)(wv * bits + 7) / 8, (size_t)ctx->n,
+                                               cudaMemcpyDeviceToHost, ctx->stream));
+            }
             ctx->st.d2h_bytes += (nvc * bits + 7) / 8 * (int64_t)ctx->n;
         } else {
-            rc = launch_gram(ctx, ctx->d_x[b], nvc, ctx->ld_chunk, d_target);
+            rc = launch_gram(ctx, ctx->d_x[b], nvc, P, P, d_target);
             if (rc != VPCA_OK) return rc;
         }
         CUDA_OK(ctx, cudaEventRecord(ctx->ev_done[b], ctx->stream));
@@ -291,8 +306,9 @@ int vpca_create(const vpca_config* cfg, vpca_ctx** out) {
         if (cfg->d_gram != nullptr) {
             ctx->d_S = static_cast<int32_t*>(cfg->d_gram);
         } else {
-            e = cudaMalloc(&ctx->d_S, gram_bytes);
+            e = cudaMalloc(&ctx->d_S, gram_bytes + 64 * sizeof(int32_t));   // + barrier flags of the peer-reduce mode
             ctx->own_S = true;
+            if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_S + (size_t)ctx->n * ctx->n, 0, 64 * sizeof(int32_t), ctx->stream);
         }
     }
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_S, 0, gram_bytes, ctx->stream);
@@ -329,6 +345,8 @@ int vpca_destroy(vpca_ctx* ctx) {
         if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
     }
     for (auto& s : ctx->slots) cudaFree(s.d_S);
+    for (int d = 0; d < ctx->plan.num_peers; ++d)
+        if (d != ctx->plan.peer_rank && ctx->plan.peer_S[d] != nullptr) cudaIpcCloseMemHandle(ctx->plan.peer_S[d]);
     if (ctx->own_S) cudaFree(ctx->d_S);
     cudaFree(ctx->d_flags);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
@@ -362,11 +380,25 @@ int vpca_encode_calls(vpca_ctx* ctx, const int64_t* offsets, const int32_t* samp
         return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_encode_calls: bad argument");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     if (nv == 0) return VPCA_OK;
-    return process_calls(ctx, offsets, sample_idx, nv, nullptr, out, ld);
+    return process_calls(ctx, offsets, sample_idx, 4, nv, nullptr, out, ld);
 }
+
+static int accumulate_calls_impl(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const void* sample_idx,
+                                 int idx_bytes, int64_t nv);
 
 int vpca_accumulate_calls(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const int32_t* sample_idx,
                           int64_t nv) {
+    return accumulate_calls_impl(ctx, partition_id, offsets, sample_idx, 4, nv);
+}
+
+int vpca_accumulate_calls_u16(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const uint16_t* sample_idx,
+                              int64_t nv) {
+    if (ctx != nullptr && ctx->n > 65536) return fail(ctx, VPCA_ERR_BAD_ARG, "16-bit sample indices need n_samples <= 65536");
+    return accumulate_calls_impl(ctx, partition_id, offsets, sample_idx, 2, nv);
+}
+
+static int accumulate_calls_impl(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const void* sample_idx,
+                                 int idx_bytes, int64_t nv) {
     if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (offsets == nullptr || nv < 0 || (nv > 0 && sample_idx == nullptr && offsets[nv] > offsets[0]))
@@ -383,7 +415,7 @@ int vpca_accumulate_calls(vpca_ctx* ctx, int64_t partition_id, const int64_t* of
         if (slot == nullptr) return rc;
         target = slot->d_S;
     }
-    rc = process_calls(ctx, offsets, sample_idx, nv, target, nullptr, 0);
+    rc = process_calls(ctx, offsets, sample_idx, idx_bytes, nv, target, nullptr, 0);
     if (rc != VPCA_OK) {
         // a failed batch poisons the partition (its staging Gram may be partially updated): drop it
         if (slot) slot->used = false;
@@ -407,7 +439,10 @@ int vpca_commit(vpca_ctx* ctx, int64_t partition_id) {
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     rc = check_overflow(ctx, 0);
     if (rc != VPCA_OK) return rc;
-    CUDA_OK(ctx, gram_add(ctx->d_S, s->d_S, (int64_t)ctx->n * ctx->n, ctx->stream));
+    if (ctx->plan.num_peers > 1)
+        CUDA_OK(ctx, gram_add_peers(ctx->plan, s->d_S, (int64_t)ctx->n * ctx->n, ctx->stream));
+    else
+        CUDA_OK(ctx, gram_add(ctx->d_S, s->d_S, (int64_t)ctx->n * ctx->n, ctx->stream));
     ctx->st.kernel_launches += 1;
     ctx->total_variants += s->nv;
     s->used = false;
@@ -443,7 +478,7 @@ int vpca_accumulate_dense(vpca_ctx* ctx, const void* x, int64_t nv, int64_t ld, 
         if ((reinterpret_cast<uintptr_t>(x) & align) != 0 || ((ld * bits / 8) & align) != 0)
             return fail(ctx, VPCA_ERR_BAD_ARG, "device tile must be %d-byte aligned with a %d-byte multiple row pitch",
                         align + 1, align + 1);
-        rc = launch_gram(ctx, x, nv, ld, ctx->d_S);
+        rc = launch_gram(ctx, x, nv, ld, 0, ctx->d_S);
         if (rc != VPCA_OK) return rc;
     } else {
         rc = ensure_staging(ctx);
@@ -453,17 +488,22 @@ int vpca_accumulate_dense(vpca_ctx* ctx, const void* x, int64_t nv, int64_t ld, 
             const int64_t nvc = std::min(ctx->chunk_variants, nv - v);
             const int b = chunk & 1;
             CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
-            if (bits == 4 && (nvc % 128) != 0)   // the tail k-block of a packed tile must be zero beyond nv
-                CUDA_OK(ctx, cudaMemset2DAsync(ctx->d_x[b], (size_t)ctx->ld_chunk / 2, 0, (size_t)((nvc + 127) / 128) * 64,
-                                               (size_t)ctx->n, ctx->copy_stream));
-            CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->d_x[b], (size_t)ctx->ld_chunk * bits / 8,
-                                           static_cast<const char*>(x) + (size_t)v * bits / 8, (size_t)ld * bits / 8,
-                                           (size_t)(nvc * bits + 7) / 8, (size_t)ctx->n, cudaMemcpyHostToDevice,
-                                           ctx->copy_stream));
+            // the caller's row-major tile -> panel layout, one 2-D copy per panel; a partial last panel is zeroed first
+            const int64_t P = ctx->panel;
+            if ((nvc % P) != 0)
+                CUDA_OK(ctx, cudaMemsetAsync(static_cast<char*>(ctx->d_x[b]) + (size_t)(nvc / P) * ctx->n * P * bits / 8, 0,
+                                             (size_t)ctx->n * P * bits / 8, ctx->copy_stream));
+            for (int64_t pv = 0; pv < nvc; pv += P) {
+                const int64_t wv = std::min(P, nvc - pv);
+                CUDA_OK(ctx, cudaMemcpy2DAsync(static_cast<char*>(ctx->d_x[b]) + (size_t)(pv / P) * ctx->n * P * bits / 8,
+                                               (size_t)P * bits / 8, static_cast<const char*>(x) + (size_t)(v + pv) * bits / 8,
+                                               (size_t)ld * bits / 8, (size_t)(wv * bits + 7) / 8, (size_t)ctx->n,
+                                               cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
             CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
             ctx->st.h2d_bytes += (nvc * bits + 7) / 8 * (int64_t)ctx->n;
             CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
-            rc = launch_gram(ctx, ctx->d_x[b], nvc, ctx->ld_chunk, ctx->d_S);
+            rc = launch_gram(ctx, ctx->d_x[b], nvc, P, P, ctx->d_S);
             if (rc != VPCA_OK) return rc;
             CUDA_OK(ctx, cudaEventRecord(ctx->ev_done[b], ctx->stream));
         }
@@ -471,6 +511,38 @@ int vpca_accumulate_dense(vpca_ctx* ctx, const void* x, int64_t nv, int64_t ld, 
     }
     ctx->total_variants += nv;
     ctx->st.variants_accumulated += nv;
+    return VPCA_OK;
+}
+
+int vpca_accumulate_panels(vpca_ctx* ctx, const void* d_x, int64_t nv, int64_t panel_variants) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (d_x == nullptr || nv < 0 || panel_variants < 128 || (panel_variants % 128) != 0)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_accumulate_panels: panel_variants must be a positive multiple of 128");
+    if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
+    if ((reinterpret_cast<uintptr_t>(d_x) & 31) != 0) return fail(ctx, VPCA_ERR_BAD_ARG, "panels must be 32-byte aligned");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    if (nv == 0) return VPCA_OK;
+    int rc = check_overflow(ctx, nv);
+    if (rc != VPCA_OK) return rc;
+    rc = launch_gram(ctx, d_x, nv, panel_variants, panel_variants, ctx->d_S);
+    if (rc != VPCA_OK) return rc;
+    ctx->total_variants += nv;
+    ctx->st.variants_accumulated += nv;
+    return VPCA_OK;
+}
+
+int vpca_synth_panels_device(vpca_ctx* ctx, uint64_t seed, int64_t v0, int64_t nv, int mode, void* d_x,
+                             int64_t panel_variants) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (d_x == nullptr || nv < 0 || v0 < 0 || (mode != 0 && mode != 1) || panel_variants < 128 || (panel_variants % 128) != 0)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_synth_panels_device: bad argument");
+    if (mode == 1 && ctx->max_mult < 2) return fail(ctx, VPCA_ERR_BAD_ARG, "dosage mode needs max_multiplicity >= 2");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaError_t e = synth_dense(seed, ctx->n, v0, nv, mode, ctx->elem_bits, d_x, panel_variants, panel_variants, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, VPCA_ERR_CUDA, "synthetic generator: %s", cudaGetErrorString(e));
+    ctx->st.kernel_launches += 2 * ((nv + (1 << 22) - 1) >> 22);
     return VPCA_OK;
 }
 
@@ -594,7 +666,7 @@ int vpca_synth_dense_device(vpca_ctx* ctx, uint64_t seed, int64_t v0, int64_t nv
     if (mode == 1 && ctx->max_mult < 2)
         return fail(ctx, VPCA_ERR_BAD_ARG, "dosage mode needs max_multiplicity >= 2");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    cudaError_t e = synth_dense(seed, ctx->n, v0, nv, mode, ctx->elem_bits, d_x, ld, ctx->stream);
+    cudaError_t e = synth_dense(seed, ctx->n, v0, nv, mode, ctx->elem_bits, d_x, ld, 0, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, VPCA_ERR_CUDA, "synthetic generator: %s", cudaGetErrorString(e));
     ctx->st.kernel_launches += 2 * ((nv + (1 << 22) - 1) >> 22);
     return VPCA_OK;
@@ -613,6 +685,58 @@ int vpca_get_stats(vpca_ctx* ctx, vpca_stats* out) {
         if (cudaEventElapsedTime(&ms, ctx->ev_e0, ctx->ev_e1) == cudaSuccess) ctx->st.last_eig_ms = ms;
     }
     *out = ctx->st;
+    return VPCA_OK;
+}
+
+int vpca_gram_export_ipc(vpca_ctx* ctx, void* handle64) {
+    if (ctx == nullptr || handle64 == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->own_S) return fail(ctx, VPCA_ERR_STATE, "the peer-reduce mode needs a library-owned Gram (vpca_config.d_gram == NULL)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaIpcMemHandle_t h;
+    CUDA_OK(ctx, cudaIpcGetMemHandle(&h, ctx->d_S));
+    memcpy(handle64, &h, sizeof(h));
+    return VPCA_OK;
+}
+
+int vpca_gram_set_peers(vpca_ctx* ctx, const void* handles, int32_t world, int32_t rank) {
+    if (ctx == nullptr || handles == nullptr || world < 1 || world > 16 || rank < 0 || rank >= world)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_gram_set_peers: bad argument (world <= 16)");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->own_S) return fail(ctx, VPCA_ERR_STATE, "the peer-reduce mode needs a library-owned Gram");
+    if (ctx->plan.num_peers != 0) return fail(ctx, VPCA_ERR_STATE, "peers already set");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t nn = (size_t)ctx->n * ctx->n;
+    for (int d = 0; d < world; ++d) {
+        int32_t* base = ctx->d_S;
+        if (d != rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, static_cast<const char*>(handles) + (size_t)d * sizeof(h), sizeof(h));
+            void* ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                for (int q = 0; q < d; ++q)
+                    if (q != rank) cudaIpcCloseMemHandle(ctx->plan.peer_S[q]);
+                return fail(ctx, VPCA_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", d, cudaGetErrorString(e));
+            }
+            base = static_cast<int32_t*>(ptr);
+        }
+        ctx->plan.peer_S[d] = base;
+        ctx->plan.peer_flags[d] = base + nn;
+    }
+    ctx->plan.peer_rank = rank;
+    ctx->plan.num_peers = world;
+    return VPCA_OK;
+}
+
+int vpca_peer_barrier(vpca_ctx* ctx) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->plan.num_peers < 2) return VPCA_OK;
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    CUDA_OK(ctx, gram_peer_barrier(ctx->plan, ctx->stream));
+    ctx->st.kernel_launches += 1;
     return VPCA_OK;
 }
 

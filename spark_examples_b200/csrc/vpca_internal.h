@@ -23,6 +23,13 @@ struct GramPlan {
     int sync_lead = 0;        // VPCA_SYNC_LEAD: windows a worker may lead the slowest one by (0 = no pacing; measured
                               // on B200: pacing only slows every worker to the slowest one)
     int* d_win_done = nullptr;
+    bool adaptive = true;     // VPCA_ADAPTIVE=0 keeps the stream-K split equal instead of speed-weighted
+    double* d_cum = nullptr;  // cumulative worker shares (workers + 1 doubles) + update counter
+    int cum_workers = 0, cum_tiles = 0;
+    // fused multi-GPU reduction: Gram buffers / barrier flags of all ranks, peer-mapped through CUDA IPC
+    int num_peers = 0, peer_rank = 0, peer_epoch = 0;
+    int32_t* peer_S[16] = {};
+    int32_t* peer_flags[16] = {};
     bool profile = false;     // VPCA_GRAM_PROF=1: per-CTA timestamps in d_prof
     long long* d_prof = nullptr;
 };
@@ -34,18 +41,25 @@ int gram_read_profile(GramPlan& plan, long long* out, int max_ctas);
 //         byte, ld % 128 == 0 and zero cells up to the next multiple of 128 variants)
 //   d_S : device int32 n x n row-major
 // Returns cudaSuccess or the first CUDA error; never synchronises.
-cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int n, int64_t nv, int64_t ld,
+// panel > 0: the tile is stored as ceil(nv / panel) consecutive panels of `panel` variants, each panel n rows of
+// `panel` cells (cell (s, v) at (v / panel) * n * panel + s * panel + v % panel, zero cells after nv in the last
+// panel); `ld` is ignored.  Keeps the pages touched per L2 window few (a row-major tile with a multi-MB pitch puts
+// every sample row on its own 2 MB page and thrashes the TLBs).
+cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int n, int64_t nv, int64_t ld, int64_t panel,
                             int32_t* d_S, cudaStream_t stream, std::string* err);
 cudaError_t gram_symmetrize(int32_t* d_S, int n, cudaStream_t stream);
 cudaError_t gram_add(int32_t* d_dst, const int32_t* d_src, int64_t count, cudaStream_t stream);
+cudaError_t gram_add_peers(GramPlan& plan, const int32_t* d_src, int64_t count, cudaStream_t stream);
+cudaError_t gram_peer_barrier(GramPlan& plan, cudaStream_t stream);
 void gram_plan_free(GramPlan& plan);
 
 // ---- encode (encode.cu) ------------------------------------------------------------------------
 // CSR rows [0, nv) (d_off has nv+1 entries; entry e of row v is d_idx[d_off[v] - base + ...]) -> dense
 // sample-major tile, zero-filled first.  d_flags[0] is OR-ed with 1 on an out-of-range index and 2 on a
 // multiplicity overflow.
-cudaError_t encode_calls(const int64_t* d_off, int64_t base, const int32_t* d_idx, int64_t nv, int n,
-                         int elem_bits, int max_mult, void* d_x, int64_t ld, int* d_flags, cudaStream_t stream);
+cudaError_t encode_calls(const int64_t* d_off, int64_t base, const void* d_idx, int idx_bytes, int64_t nv, int n,
+                         int elem_bits, int max_mult, void* d_x, int64_t ld, int64_t panel, int* d_flags,
+                         cudaStream_t stream);   // idx_bytes: 4 (int32) or 2 (uint16)
 
 // ---- centering + eigensolve (eig.cu) ---------------------------------------------------------------
 struct EigWork {
@@ -75,6 +89,6 @@ cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches);
 
 // ---- synthetic generator (synth.cu) ----------------------------------------------------------------
 cudaError_t synth_dense(uint64_t seed, int n, int64_t v0, int64_t nv, int mode, int elem_bits, void* d_x,
-                        int64_t ld, cudaStream_t stream);
+                        int64_t ld, int64_t panel, cudaStream_t stream);
 
 }  // namespace vpca

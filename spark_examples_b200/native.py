@@ -39,6 +39,8 @@ EXPORTED_SYMBOLS = (
     "vpca_accumulate_calls", "vpca_commit", "vpca_abort", "vpca_accumulate_dense", "vpca_gram_device_ptr",
     "vpca_finalize_gram", "vpca_get_gram", "vpca_set_gram", "vpca_compute_pca", "vpca_get_centered",
     "vpca_get_tridiagonal", "vpca_synth_dense_device", "vpca_get_stats", "vpca_debug_gram_profile",
+    "vpca_gram_export_ipc", "vpca_gram_set_peers", "vpca_peer_barrier", "vpca_accumulate_panels",
+    "vpca_synth_panels_device", "vpca_accumulate_calls_u16",
 )
 
 
@@ -119,6 +121,8 @@ def load_library() -> ctypes.CDLL:
     L.vpca_encode_calls.argtypes = [vp, vp, vp, i64, vp, i64]
     L.vpca_accumulate_calls.restype = ctypes.c_int
     L.vpca_accumulate_calls.argtypes = [vp, i64, vp, vp, i64]
+    L.vpca_accumulate_calls_u16.restype = ctypes.c_int
+    L.vpca_accumulate_calls_u16.argtypes = [vp, i64, vp, vp, i64]
     L.vpca_commit.restype = ctypes.c_int
     L.vpca_commit.argtypes = [vp, i64]
     L.vpca_abort.restype = ctypes.c_int
@@ -143,6 +147,16 @@ def load_library() -> ctypes.CDLL:
     L.vpca_synth_dense_device.argtypes = [vp, ctypes.c_uint64, i64, i64, ctypes.c_int, vp, i64]
     L.vpca_get_stats.restype = ctypes.c_int
     L.vpca_get_stats.argtypes = [vp, ctypes.POINTER(VpcaStats)]
+    L.vpca_accumulate_panels.restype = ctypes.c_int
+    L.vpca_accumulate_panels.argtypes = [vp, vp, i64, i64]
+    L.vpca_synth_panels_device.restype = ctypes.c_int
+    L.vpca_synth_panels_device.argtypes = [vp, ctypes.c_uint64, i64, i64, ctypes.c_int, vp, i64]
+    L.vpca_gram_export_ipc.restype = ctypes.c_int
+    L.vpca_gram_export_ipc.argtypes = [vp, vp]
+    L.vpca_gram_set_peers.restype = ctypes.c_int
+    L.vpca_gram_set_peers.argtypes = [vp, vp, i32, i32]
+    L.vpca_peer_barrier.restype = ctypes.c_int
+    L.vpca_peer_barrier.argtypes = [vp]
     L.vpca_debug_gram_profile.restype = ctypes.c_int
     L.vpca_debug_gram_profile.argtypes = [vp, vp, i32]
     _lib = L
@@ -232,9 +246,17 @@ class NativePca:
         self._check(self._lib.vpca_accumulate_calls(self._h, int(partition_id), _host_ptr(off),
                                                     _host_ptr(idx) if len(idx) else None, len(off) - 1))
 
-    def accumulateCallsRaw(self, partition_id: int, off_ptr: int, idx_ptr: int, nv: int):
-        """Same, from raw host addresses (e.g. pinned torch tensors) -- no copies on the Python side."""
-        self._check(self._lib.vpca_accumulate_calls(self._h, int(partition_id), off_ptr, idx_ptr, int(nv)))
+    def accumulateCallsRaw(self, partition_id: int, off_ptr: int, idx_ptr: int, nv: int, idx_bytes: int = 4):
+        """Same, from raw host addresses (e.g. pinned torch tensors) -- no copies on the Python side.
+        idx_bytes = 2: the indices are uint16 (vpca_accumulate_calls_u16)."""
+        fn = self._lib.vpca_accumulate_calls if idx_bytes == 4 else self._lib.vpca_accumulate_calls_u16
+        self._check(fn(self._h, int(partition_id), off_ptr, idx_ptr, int(nv)))
+
+    def accumulateCalls16(self, partition_id: int, offsets, sample_idx):
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        idx = np.ascontiguousarray(sample_idx, dtype=np.uint16)
+        self._check(self._lib.vpca_accumulate_calls_u16(self._h, int(partition_id), _host_ptr(off),
+                                                        _host_ptr(idx) if len(idx) else None, len(off) - 1))
 
     def commit(self, partition_id: int):
         self._check(self._lib.vpca_commit(self._h, int(partition_id)))
@@ -263,10 +285,35 @@ class NativePca:
     def accumulateDenseDevice(self, d_ptr: int, nv: int, ld: int):
         self._check(self._lib.vpca_accumulate_dense(self._h, d_ptr, int(nv), int(ld), 1))
 
+    def accumulatePanels(self, d_ptr: int, nv: int, panel_variants: int):
+        """Device-resident cohort in panel layout (see vpca.h): one Gram launch over all nv variants."""
+        self._check(self._lib.vpca_accumulate_panels(self._h, d_ptr, int(nv), int(panel_variants)))
+
+    def synthPanelsDevice(self, seed: int, v0: int, nv: int, mode: int, d_ptr: int, panel_variants: int):
+        self._check(self._lib.vpca_synth_panels_device(self._h, ctypes.c_uint64(seed), int(v0), int(nv), int(mode),
+                                                       d_ptr, int(panel_variants)))
+
+    def panelBytes(self, nv: int, panel_variants: int) -> int:
+        npanels = (int(nv) + panel_variants - 1) // panel_variants
+        return npanels * self.n * panel_variants * self.elem_bits // 8
+
     def gramDevicePtr(self) -> int:
         p = ctypes.c_void_p()
         self._check(self._lib.vpca_gram_device_ptr(self._h, ctypes.byref(p)))
         return int(p.value)
+
+    def exportIpcHandle(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self._check(self._lib.vpca_gram_export_ipc(self._h, buf))
+        return buf.raw
+
+    def setPeers(self, handles, rank: int):
+        """handles: list of 64-byte handles of all ranks, in rank order."""
+        blob = ctypes.create_string_buffer(b"".join(handles), 64 * len(handles))
+        self._check(self._lib.vpca_gram_set_peers(self._h, blob, len(handles), int(rank)))
+
+    def peerBarrier(self):
+        self._check(self._lib.vpca_peer_barrier(self._h))
 
     def finalizeGram(self):
         self._check(self._lib.vpca_finalize_gram(self._h))

@@ -319,13 +319,12 @@ class VariantsPcaDriver:
                                      d_gram=d_gram)
         return self._nat
 
-    def _accumulate_synthetic(self, nat: native.NativePca, part: SyntheticSlice):
+    def _accumulate_synthetic(self, nat: native.NativePca, part: SyntheticSlice, panel: int = 8192):
+        """Synthetic partitions are born on the device, directly in the panel layout the Gram kernel streams."""
         import torch
-        eb = nat.elem_bytes
-        ld = ((part.nv + 127) // 128) * 128
-        buf = torch.empty((nat.n, ld), dtype=torch.int8 if eb == 1 else torch.bfloat16, device=self._gram_tensor.device)
-        nat.synthDenseDevice(part.seed, part.v0, part.nv, 0, buf.data_ptr(), ld)
-        nat.accumulateDenseDevice(buf.data_ptr(), part.nv, ld)
+        buf = torch.empty(nat.panelBytes(part.nv, panel), dtype=torch.uint8, device=self._gram_tensor.device)
+        nat.synthPanelsDevice(part.seed, part.v0, part.nv, 0, buf.data_ptr(), panel)
+        nat.accumulatePanels(buf.data_ptr(), part.nv, panel)
         torch.cuda.current_stream().synchronize()      # `buf` must outlive the kernels that read it
 
 

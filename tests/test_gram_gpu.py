@@ -342,3 +342,79 @@ def test_gram_e2m1_resident_matches_int8(oracle):
         a.finalizeGram()
         b.finalizeGram()
         assert np.array_equal(a.getGram(), b.getGram())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# panel layout (the resident-cohort layout of vpca_accumulate_panels)
+# ---------------------------------------------------------------------------------------------------------------
+def _to_panels(X, P):
+    """(n, nv) row-major -> flat panel layout, zero padded to whole panels."""
+    n, nv = X.shape
+    npan = (nv + P - 1) // P
+    out = np.zeros((npan, n, P), X.dtype)
+    for p in range(npan):
+        w = min(P, nv - p * P)
+        out[p, :, :w] = X[:, p * P:p * P + w]
+    return out.reshape(-1)
+
+
+@pytest.mark.parametrize("dtype_name", ["i8", "e2m1", "bf16"])
+def test_synth_and_gram_panel_layout(oracle, monkeypatch, dtype_name):
+    import torch
+    from spark_examples_b200 import native
+    _set_env(monkeypatch, 2)
+    dt = {"i8": native.DTYPE_I8, "e2m1": native.DTYPE_E2M1, "bf16": native.DTYPE_BF16}[dtype_name]
+    n, v0, nv, P = 515, 256, 3000, 1024                       # 3 panels, the last one partial
+    Xr = oracle.c_synth_dense(SEED, n, v0, nv, mode=1)
+    want = oracle.np_similarity_dense(Xr)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    with _native(n, dtype=dt, stream=stream.cuda_stream) as nat:
+        buf = torch.full((nat.panelBytes(nv, P),), 0x5A, dtype=torch.uint8, device="cuda")
+        nat.synthPanelsDevice(SEED, v0, nv, 1, buf.data_ptr(), P)
+        stream.synchronize()
+        got = buf.cpu().numpy()
+        if dtype_name == "i8":
+            assert np.array_equal(got.view(np.int8), _to_panels(Xr, P))
+        elif dtype_name == "e2m1":
+            codes = _to_panels((2 * Xr).astype(np.uint8), P)
+            assert np.array_equal(got, (codes[0::2] | (codes[1::2] << 4)).astype(np.uint8))
+        else:
+            bits = np.array([0x0000, 0x3F80, 0x4000], np.uint16)[_to_panels(Xr.astype(np.int64), P)]
+            assert np.array_equal(got.view(np.uint16), bits)
+        nat.accumulatePanels(buf.data_ptr(), nv, P)
+        nat.finalizeGram()
+        assert np.array_equal(nat.getGram(), want)
+
+
+def test_calls_path_spans_several_panels_and_chunks(oracle, monkeypatch):
+    """CSR input larger than one staging chunk and one panel (chunk_variants forced small)."""
+    monkeypatch.setenv("VPCA_PANEL", "512")
+    n, nv = 300, 5000
+    off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
+    want = oracle.c_similarity(n, off, idx, 2)
+    with _native(n, chunk_variants=1536, chunk_nnz=200_000) as nat:
+        nat.accumulateCalls(-1, off, idx)
+        nat.finalizeGram()
+        assert np.array_equal(nat.getGram(), want)
+        tile = nat.encodeCalls(off[:1301], idx[:off[1300]])
+    X = np.zeros((n, 1300), np.int8)
+    for v in range(1300):
+        X[idx[off[v]:off[v + 1]], v] = 1
+    assert np.array_equal(tile, X)
+
+
+def test_calls_u16_wire_format(oracle):
+    n, nv = 640, 3000
+    off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
+    want = oracle.c_similarity(n, off, idx, 2)
+    with _native(n) as nat:
+        nat.accumulateCalls16(0, off, idx.astype(np.uint16))
+        nat.commit(0)
+        nat.finalizeGram()
+        assert np.array_equal(nat.getGram(), want)
+        st = nat.stats()
+    assert st["h2d_bytes"] == (len(off)) * 8 + len(idx) * 2
+    with _native(n) as nat:
+        with pytest.raises(IndexError):
+            nat.accumulateCalls16(-1, np.array([0, 1], np.int64), np.array([n], np.uint16))

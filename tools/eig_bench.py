@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Time centering + eigensolve (vpca_compute_pca) alone on structured Grams of several sizes."""
+import json, os, sys, time
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch
+from spark_examples_b200 import native
+
+def main():
+    sizes = [int(x) for x in os.environ.get("EIG_N", "1092,2504,4096").split(",")]
+    reps = int(os.environ.get("EIG_REPS", "5"))
+    ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
+    for n in sizes:
+        nv = 200_000
+        X = torch.empty((n, nv), dtype=torch.int8, device="cuda")
+        with native.NativePca(n, stream=ts.cuda_stream, max_multiplicity=1) as nat:
+            nat.synthDenseDevice(20240901, 0, nv, 0, X.data_ptr(), nv)
+            nat.accumulateDenseDevice(X.data_ptr(), nv, nv)
+            nat.finalizeGram()
+            times = []
+            for r in range(reps + 1):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); vecs, evals, nz = nat.computePca(2); b.record(); b.synchronize()
+                if r: times.append(a.elapsed_time(b))
+            S = torch.from_numpy(nat.getGram()).cuda().double()
+            rs = S.sum(1); C = S - (rs / n)[:, None] - (rs / n)[None, :] + rs.sum() / n / n
+            w, V = torch.linalg.eigh(C)
+            Vt = V[:, [-1, -2]].cpu().numpy()
+            import numpy as np
+            for c in range(2):
+                i = int(np.argmax(np.abs(Vt[:, c])));  Vt[:, c] *= (1 if Vt[i, c] > 0 else -1)
+            err = float((np.abs(vecs - Vt).max(0) / np.abs(Vt).max(0)).max())
+            times.sort()
+            print(json.dumps({"n": n, "eig_ms_med": round(times[len(times)//2], 3), "eig_ms_min": round(times[0], 3),
+                              "us_per_step": round(times[len(times)//2] * 1e3 / n, 2), "max_rel_err": err}), flush=True)
+        del X
+main()
