@@ -42,15 +42,17 @@ constexpr int kKBytes = 128;                    // bytes of K per k-block: one S
 constexpr int kBoxRows = 128;                   // rows per TMA box
 constexpr int kBoxBytes = kBoxRows * kKBytes;   // 16 KiB
 constexpr int kUmmaN = 256;
+constexpr int kUmmaNScaled = 240;               // kind::mxf4: 2 x 240 accumulator columns + 16 scale-factor columns
+constexpr uint32_t kSfCol = 480;                // TMEM column of the (constant 1.0) block scale factors
 constexpr uint32_t kTmemCols = 512;             // two 256-column accumulators
 constexpr long long kWatchdogCycles = 20000000000LL;   // ~10 s: a stuck barrier traps instead of hanging the box
 
-template <int CG>
+template <int CG, int KIND = 0>
 struct Cfg {
     static constexpr int BM = 128 * CG;
-    static constexpr int BN = kUmmaN;
+    static constexpr int BN = (KIND == 3) ? kUmmaNScaled : kUmmaN;
     static constexpr int A_BYTES = kBoxBytes;                  // per CTA per stage
-    static constexpr int B_BYTES = (BN / CG) * kKBytes;        // per CTA per stage (32 KiB / 16 KiB)
+    static constexpr int B_BYTES = (kUmmaN / CG) * kKBytes;    // per CTA per stage (32 KiB / 16 KiB): whole 128-row boxes
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = CG == 1 ? 4 : 6;
     static constexpr int BAR_BYTES = 256;
@@ -188,6 +190,10 @@ __device__ __forceinline__ uint32_t make_instr_desc(uint32_t N) {
     constexpr uint32_t M = 128 * CG;
     // c_format [4,6): 1 = F32, 2 = S32; a/b_format [7,10)/[10,13): kind::i8 -> 1 (signed int8), kind::f16 -> 1 (BF16),
     // kind::f8f6f4 -> 5 (E2M1); a/b major bits 15/16 = 0 (K-major); n_dim [17,23) = N >> 3; m_dim [24,29) = M >> 4.
+    if constexpr (KIND == 3) {
+        // block-scaled descriptor (kind::mxf4): a/b_format 1 = E2M1, bit 23 scale_format 1 = UE8M0, sf ids 0, K = 64
+        return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
+    }
     constexpr uint32_t cfmt = (KIND == 0) ? 2u : 1u;
     constexpr uint32_t abfmt = (KIND == 2) ? 5u : 1u;
     return (cfmt << 4) | (abfmt << 7) | (abfmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -195,7 +201,7 @@ __device__ __forceinline__ uint32_t make_instr_desc(uint32_t N) {
 
 template <int CG, int KIND>
 __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
-    using C = Cfg<CG>;
+    using C = Cfg<CG, KIND>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = ptx::smem_u32(smem);
@@ -238,6 +244,17 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
     if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if constexpr (KIND == 3) {
+        // kind::mxf4 multiplies every 32-cell block by a UE8M0 scale read from TMEM; genotype cells are unscaled, so
+        // the 16 scale columns of both CTAs are filled once with 0x7F = 2^0 (any scale-factor id / layout reads 1.0).
+        if (warp >= 4) {
+            ptx::tmem_st_32x32b_x16_const(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kSfCol, 0x7F7F7F7Fu);
+            ptx::tmem_st_wait();
+        }
+        ptx::tc_fence_before();
+        if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+        ptx::tc_fence_after();
+    }
     if (a.prof != nullptr && threadIdx.x == 0) a.prof[(size_t)blockIdx.x * 4 + 0] = globaltimer_ns();
 
     if (warp == 0) {
@@ -291,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                 mbar_wait(tempty_bar(s.slot), (uint32_t)(s.use & 1) ^ 1u, a.err, 2);
                 ptx::tc_fence_after();
             }
-            const uint32_t d_tmem = tmem_base + (uint32_t)s.slot * kUmmaN;
+            const uint32_t d_tmem = tmem_base + (uint32_t)s.slot * C::BN;
             const int by = a.tiles[s.tile].y;
             const uint32_t idesc = make_instr_desc<CG, KIND>((uint32_t)min(C::BN, ((a.n - by * C::BN) + 15) & ~15));
             for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
@@ -304,7 +321,11 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                     uint32_t acc = (s.first && kb == s.kb0) ? 0u : 1u;
 #pragma unroll
                     for (int k = 0; k < kKBytes / 32; ++k) {           // UMMA_K = 32 bytes of K
-                        ptx::umma_ss<CG, KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                        if constexpr (KIND == 3)
+                            ptx::umma_ss_mxf4<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc, tmem_base + kSfCol,
+                                                  tmem_base + kSfCol + 4);
+                        else
+                            ptx::umma_ss<CG, KIND>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
                         acc = 1u;
                     }
                     ptx::umma_commit<CG>(empty_bar(st));               // frees the smem stage (both CTAs)
@@ -331,19 +352,20 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
             const int col = t.x * C::BM + (int)cta_rank * kBoxRows + q * 32 + (int)lane;   // sample of the A row
             const int col_warp_min = col - (int)lane;
             const int row0 = t.y * C::BN;                                                  // samples of the B rows
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s.slot * kUmmaN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s.slot * C::BN;
             int32_t* out = a.S + col;
+            const int row_end = min(a.n, row0 + C::BN);                    // rows this tile owns (BN may be 240)
 #pragma unroll 1
-            for (int c = 0; c < C::BN / 32; ++c) {
+            for (int c = 0; c < (C::BN + 31) / 32; ++c) {
                 const int rbase = row0 + c * 32;
-                if (rbase >= a.n || rbase + 31 < col_warp_min) continue;   // outside S or strictly above the diagonal
+                if (rbase >= row_end || rbase + 31 < col_warp_min) continue;   // outside the tile or above the diagonal
                 uint32_t r[32];
                 ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int row = rbase + j;
-                    if (row < a.n && col < a.n && row >= col) {
+                    if (row < row_end && col < a.n && row >= col) {
                         int v;
                         if constexpr (KIND == 0) v = (int)r[j];
                         else v = __float2int_rn(__uint_as_float(r[j]));
@@ -514,7 +536,7 @@ EncodeTiledFn get_encode_fn() {
 
 template <int CG, int KIND>
 cudaError_t launch(const CUtensorMap& tmap, const GramArgs& args, int grid, cudaStream_t stream) {
-    using C = Cfg<CG>;
+    using C = Cfg<CG, KIND>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gram_kernel<CG, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -560,8 +582,8 @@ int gram_read_profile(GramPlan& plan, long long* out, int max_ctas) {
     return ctas;
 }
 
-static cudaError_t build_tiles(GramPlan& plan, int n, cudaStream_t stream) {
-    const int BM = 128 * plan.cta_group, BN = kUmmaN;
+static cudaError_t build_tiles(GramPlan& plan, int n, int BN, cudaStream_t stream) {
+    const int BM = 128 * plan.cta_group;
     std::vector<int2> tiles;
     const int nbn = (n + BN - 1) / BN, nbm = (n + BM - 1) / BM;
     for (int b = 0; b < nbn; ++b)
@@ -580,6 +602,7 @@ static cudaError_t build_tiles(GramPlan& plan, int n, cudaStream_t stream) {
     plan.num_tiles = (int)tiles.size();
     plan.tiles_for_n = n;
     plan.tiles_for_cg = plan.cta_group;
+    plan.tiles_for_bn = BN;
     return e;
 }
 
@@ -605,6 +628,8 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         plan.profile = (pf != nullptr && atoi(pf) != 0);
         const char* ad = getenv("VPCA_ADAPTIVE");
         if (ad != nullptr) plan.adaptive = atoi(ad) != 0;
+        const char* mx = getenv("VPCA_E2M1_MXF4");
+        if (mx != nullptr) plan.e2m1_mxf4 = atoi(mx) != 0;
     }
     if (plan.d_win_done == nullptr) {
         cudaError_t e = cudaMalloc(&plan.d_win_done, GramPlan::kMaxWindows * sizeof(int));
@@ -621,8 +646,10 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         if (e != cudaSuccess) return e;
         for (int i = 0; i < 4; ++i) plan.d_err[i] = 0;
     }
-    if (plan.tiles_for_n != n || plan.tiles_for_cg != plan.cta_group) {
-        cudaError_t e = build_tiles(plan, n, stream);
+    const bool mxf4 = (elem_bits == 4 && plan.e2m1_mxf4);
+    const int tile_bn = mxf4 ? kUmmaNScaled : kUmmaN;
+    if (plan.tiles_for_n != n || plan.tiles_for_cg != plan.cta_group || plan.tiles_for_bn != tile_bn) {
+        cudaError_t e = build_tiles(plan, n, tile_bn, stream);
         if (e != cudaSuccess) return e;
     }
     if (panel > 0) {
@@ -653,14 +680,18 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     }
     // one k-block = one 128-byte swizzle atom of shared memory: 128 int8, 64 bf16 or 128 e2m1 cells (TMA expands
     // 4-bit cells to one byte each, CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B)
-    const int elems_per_kb = (elem_bits == 16) ? 64 : 128;
-    const int kind = (elem_bits == 8) ? 0 : (elem_bits == 16 ? 1 : 2);
+    const int elems_per_kb = (elem_bits == 16) ? 64 : (mxf4 ? 256 : 128);
+    const int kind = (elem_bits == 8) ? 0 : (elem_bits == 16 ? 1 : (mxf4 ? 3 : 2));
+    if (mxf4 && panel > 0 && (panel % 256) != 0) {
+        if (err) *err = "kind::mxf4 needs panel_variants % 256 == 0";
+        return cudaErrorInvalidValue;
+    }
 
     CUtensorMap tmap;
     // Panel layout: dim0 = cells of one panel row, dim1 = samples, dim2 = panels.  Row-major input is one panel as
     // wide as the tile.  e2m1: globalDim[0] must be a multiple of 128 (the caller guarantees zero cells up to there).
     const int64_t npanels = panel > 0 ? (nv + panel - 1) / panel : 1;
-    const int64_t dim0 = panel > 0 ? panel : (elem_bits == 4 ? ((nv + 127) / 128) * 128 : nv);
+    const int64_t dim0 = panel > 0 ? panel : (elem_bits == 4 ? (mxf4 ? ((nv + 1) / 2) * 2 : ((nv + 127) / 128) * 128) : nv);
     const cuuint64_t gdim[3] = {(cuuint64_t)dim0, (cuuint64_t)n, (cuuint64_t)npanels};
     const cuuint64_t gstride[2] = {(cuuint64_t)ld * (cuuint64_t)elem_bits / 8,
                                    (cuuint64_t)n * (cuuint64_t)ld * (cuuint64_t)elem_bits / 8};
@@ -668,7 +699,8 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUtensorMapDataType tmtype = elem_bits == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                        : (elem_bits == 16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                                          : CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B);
+                                                          : (mxf4 ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN8B
+                                                                  : CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B));
     CUresult r = encode(&tmap, tmtype, 3,
                         const_cast<void*>(d_x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -713,7 +745,7 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
                        args.active_workers == workers;
     args.prof = (plan.profile || adapt) ? plan.d_prof : nullptr;
     args.cum = plan.d_cum;
-    args.tx_shift = (elem_bits == 4 && getenv("VPCA_E2M1_TX_FULL") == nullptr) ? 1 : 0;
+    args.tx_shift = (elem_bits == 4 && !mxf4 && getenv("VPCA_E2M1_TX_FULL") == nullptr) ? 1 : 0;
     if (args.sync_lead > 0) {
         cudaError_t e = cudaMemsetAsync(plan.d_win_done, 0, (size_t)nwin * sizeof(int), stream);
         if (e != cudaSuccess) return e;
@@ -723,10 +755,12 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     cudaError_t le;
     if (cgp == 2)
         le = kind == 0 ? launch<2, 0>(tmap, args, grid, stream)
-                       : (kind == 1 ? launch<2, 1>(tmap, args, grid, stream) : launch<2, 2>(tmap, args, grid, stream));
+                       : (kind == 1 ? launch<2, 1>(tmap, args, grid, stream)
+                                    : (kind == 2 ? launch<2, 2>(tmap, args, grid, stream) : launch<2, 3>(tmap, args, grid, stream)));
     else
         le = kind == 0 ? launch<1, 0>(tmap, args, grid, stream)
-                       : (kind == 1 ? launch<1, 1>(tmap, args, grid, stream) : launch<1, 2>(tmap, args, grid, stream));
+                       : (kind == 1 ? launch<1, 1>(tmap, args, grid, stream)
+                                    : (kind == 2 ? launch<1, 2>(tmap, args, grid, stream) : launch<1, 3>(tmap, args, grid, stream)));
     if (le != cudaSuccess) return le;
     if (adapt) {
         // a worker may own at most one tile's worth of units per window (two resident accumulators)

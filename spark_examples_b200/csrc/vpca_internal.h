@@ -17,6 +17,8 @@ struct GramPlan {
     int num_tiles = 0;
     int tiles_for_n = -1;     // n_samples the tile list was built for
     int tiles_for_cg = 0;
+    int tiles_for_bn = 0;
+    bool e2m1_mxf4 = false;   // VPCA_E2M1_MXF4=1: run packed e2m1 cells through kind::mxf4 (2x MMA rate, unit block scales)
     int last_resident = 0;
     int* d_err = nullptr;     // device debug words written before a watchdog trap
     static constexpr int kMaxWindows = 1 << 16;
