@@ -233,12 +233,16 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     n, vpg = args.samples, args.variants_per_gpu
     dtype = {"i8": native.DTYPE_I8, "bf16": native.DTYPE_BF16, "e2m1": native.DTYPE_E2M1}[args.dtype]
     eb = {"i8": 1, "bf16": 2, "e2m1": 0.5}[args.dtype]
     tdtype = {"i8": torch.int8, "bf16": torch.bfloat16, "e2m1": torch.uint8}[args.dtype]
     dname = {"i8": "int8", "bf16": "bf16", "e2m1": "e2m1 (4-bit packed cells, fp32 tensor accumulation, exact)"}[args.dtype]
+    if args.dtype == "e2m1" and args.panel_variants % 256:
+        raise SystemExit("--dtype e2m1 needs --panel-variants % 256 == 0")
     ld = ((vpg + 127) // 128) * 128
     peaks = load_peaks()
 
@@ -325,7 +329,9 @@ def run_b200(args):
     kernel_ms = sum(kt) / len(kt)
     ops = float(n) * (n + 1) * vpg                       # SYRK-minimal ops per launch
     achieved_tops = ops / (kernel_ms * 1e-3) / 1e12
-    peak = peaks["bf16_tflops"] if args.dtype == "bf16" else 2.0 * peaks["bf16_tflops"]
+    mxf4 = args.dtype == "e2m1" and os.environ.get("VPCA_E2M1_MXF4", "1") != "0"
+    peak_mult = 1.0 if args.dtype == "bf16" else (4.0 if mxf4 else 2.0)      # dense nominal: bf16 2.25, int8/fp8 4.5, fp4 9 PF
+    peak = peak_mult * peaks["bf16_tflops"]
     traffic = None
     tp = ROOT / "profiles" / "gram_traffic.json"
     if tp.exists():
@@ -338,8 +344,8 @@ def run_b200(args):
                 "frac": achieved_tops / peak, "traffic": traffic,
                 "kernel": "gram_kernel<cta_group=%d>" % st1["gram_cta_group"], "kernel_ms": kernel_ms,
                 "ops_per_launch": ops, "ops_definition": "SYRK-minimal N(N+1)V (int8 MAC = 2 ops)",
-                "peak_source": ("2 x %s bf16 burst TFLOP/s of MEASURED_PEAKS.json (int8 / fp8-path dense = 2 x bf16 nominal)"
-                                if args.dtype != "bf16" else "%s bf16 burst TFLOP/s of MEASURED_PEAKS.json") % peaks["source"],
+                "peak_source": "%g x %s bf16 burst TFLOP/s of MEASURED_PEAKS.json (nominal dense ratios: int8/fp8 = 2 x bf16, "
+                               "fp4 = 4 x bf16)" % (peak_mult, peaks["source"]),
                 "hbm_gbs_algorithmic": (n * vpg * eb + 4.0 * n * n) / (kernel_ms * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
 
@@ -479,9 +485,13 @@ def run_b200(args):
             ms4 = sum(t4) / len(t4)
             nat4.finalizeGram()
             torch.cuda.synchronize()
-            alt = {"dtype": "e2m1 (4-bit packed cells in HBM, tcgen05 kind::f8f6f4, fp32 accumulation flushed to int32)",
+            mx = os.environ.get("VPCA_E2M1_MXF4", "1") != "0"
+            alt = {"dtype": "e2m1 (4-bit packed cells in HBM, tcgen05 %s, fp32 accumulation flushed to int32; exact)"
+                            % ("kind::mxf4 with unit block scales" if mx else "kind::f8f6f4"),
                    "kernel_ms": ms4, "cells_per_s_kernel": n * vpg / (ms4 * 1e-3),
-                   "achieved_tflops_syrk": ops / (ms4 * 1e-3) / 1e12, "frac_of_2x_bf16_peak": ops / (ms4 * 1e-3) / 1e12 / (2.0 * peaks["bf16_tflops"]),
+                   "achieved_tflops_syrk": ops / (ms4 * 1e-3) / 1e12,
+                   "frac_of_fp4_peak_4x_bf16" if mx else "frac_of_2x_bf16_peak":
+                       ops / (ms4 * 1e-3) / 1e12 / ((4.0 if mx else 2.0) * peaks["bf16_tflops"]),
                    "gram_bit_identical_to_int8_path": bool(torch.equal(S4, S)) if world == 1 else None}
         del X4, S4
 

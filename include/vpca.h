@@ -49,11 +49,13 @@ typedef enum vpca_dtype {
     VPCA_DTYPE_I8 = 0,  /* int8 genotype encoding, tcgen05 kind::i8, exact int32 accumulation   */
     VPCA_DTYPE_BF16 = 1, /* bf16 genotype encoding, tcgen05 kind::f16, fp32 TMEM accumulation flushed
                             into the int32 Gram before 2^24 could be reached (exact)              */
-    VPCA_DTYPE_E2M1 = 2  /* 4-bit e2m1 cells (0, 1, 2 exact), two per byte in HBM, expanded by TMA
-                            (16U4_ALIGN16B) on the way to shared memory; tcgen05 kind::f8f6f4 with
-                            fp32 accumulation, flushed like bf16 (exact).  Halves the HBM/L2 bytes
-                            per cell; dense tiles need ld % 128 == 0, 32-byte alignment and zero
-                            cells up to the next multiple of 128 variants; max_multiplicity <= 2.   */
+    VPCA_DTYPE_E2M1 = 2  /* 4-bit e2m1 cells (0, 1, 2 exact), two per byte in HBM and in shared memory;
+                            tcgen05 kind::mxf4 (block-scaled FP4 MMA, unit UE8M0 scales kept in TMEM:
+                            twice the int8 MMA rate) with fp32 accumulation, flushed like bf16 (exact).
+                            Half the HBM/L2 bytes per cell.  Dense tiles need ld % 128 == 0 (panels:
+                            % 256), 32-byte alignment and zero cells up to the next multiple of 128
+                            variants; max_multiplicity <= 2.  VPCA_E2M1_MXF4=0 selects kind::f8f6f4
+                            (cells expanded to bytes by TMA, int8 rate) instead.                     */
 } vpca_dtype;
 
 typedef struct vpca_ctx vpca_ctx;

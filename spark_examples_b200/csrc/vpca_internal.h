@@ -18,7 +18,8 @@ struct GramPlan {
     int tiles_for_n = -1;     // n_samples the tile list was built for
     int tiles_for_cg = 0;
     int tiles_for_bn = 0;
-    bool e2m1_mxf4 = false;   // VPCA_E2M1_MXF4=1: run packed e2m1 cells through kind::mxf4 (2x MMA rate, unit block scales)
+    bool e2m1_mxf4 = true;    // packed e2m1 cells run through kind::mxf4 (2x MMA rate, unit block scales);
+                              // VPCA_E2M1_MXF4=0 selects kind::f8f6f4 (TMA-expanded cells, int8 rate)
     int last_resident = 0;
     int* d_err = nullptr;     // device debug words written before a watchdog trap
     static constexpr int kMaxWindows = 1 << 16;

@@ -293,9 +293,12 @@ def test_encode_tile_e2m1(oracle):
     assert np.array_equal(got, _pack_e2m1(want))
 
 
+@pytest.mark.parametrize("mxf4", [1, 0])
 @pytest.mark.parametrize("cta_group", [1, 2])
-def test_gram_e2m1_dense_and_calls(oracle, monkeypatch, cta_group):
+def test_gram_e2m1_dense_and_calls(oracle, monkeypatch, cta_group, mxf4):
+    """Packed 4-bit cells through kind::mxf4 (block-scaled, unit scales) and through kind::f8f6f4: same exact Gram."""
     _set_env(monkeypatch, cta_group, kb_window=8)
+    monkeypatch.setenv("VPCA_E2M1_MXF4", str(mxf4))
     from spark_examples_b200 import native
     n, nv = 700, 5003
     X = oracle.c_synth_dense(SEED, n, 0, nv, mode=1)           # dosage 0/1/2: all three codes
@@ -418,3 +421,28 @@ def test_calls_u16_wire_format(oracle):
     with _native(n) as nat:
         with pytest.raises(IndexError):
             nat.accumulateCalls16(-1, np.array([0, 1], np.int64), np.array([n], np.uint16))
+
+
+@pytest.mark.parametrize("dtype_name", ["i8", "bf16"])
+def test_gram_large_n_stream_k_vs_torch(oracle, dtype_name):
+    """N = 9000 (hundreds of tiles, far more than CTA pairs): the double-buffered stream-K path, panel layout.
+    Checker: fp32 torch matmul on the same device (exact: every count < 2^24)."""
+    import torch
+    from spark_examples_b200 import native
+    dt = {"i8": native.DTYPE_I8, "bf16": native.DTYPE_BF16}[dtype_name]
+    n, nv, P = 9000, 6000, 2048
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    with _native(n, dtype=dt, stream=stream.cuda_stream, max_multiplicity=1) as nat:
+        buf = torch.empty(nat.panelBytes(nv, P), dtype=torch.uint8, device="cuda")
+        nat.synthPanelsDevice(SEED, 0, nv, 0, buf.data_ptr(), P)
+        nat.accumulatePanels(buf.data_ptr(), nv, P)
+        nat.finalizeGram()
+        S = torch.from_numpy(nat.getGram()).cuda()
+        st = nat.stats()
+    assert st["gram_resident"] == 0
+    npan = (nv + P - 1) // P
+    view = buf.view(torch.int8 if dtype_name == "i8" else torch.bfloat16).view(npan, n, P)
+    Xf = torch.cat([view[p].to(torch.float32) for p in range(npan)], dim=1)[:, :nv]
+    want = (Xf @ Xf.t()).to(torch.int32)
+    assert torch.equal(S, want)
