@@ -89,25 +89,68 @@ struct Seg {
 };
 
 // Every role of a worker (TMA producer, MMA issuer, epilogue) replays the same deterministic schedule.
+//   resident (tiles <= workers):  window-synchronous stream-K, both accumulators live for the whole launch;
+//   otherwise:  full tiles in waves (wave i = tiles [i W, (i+1) W), one per worker, whole K) -- the tile list is ordered
+//               so that a wave is a compact 2-D block of S and shares few row panels of X -- then the < W leftover
+//               tiles are split stream-K style over all workers; accumulators double-buffered against the epilogue.
 struct Sched {
     long long u_begin, u_end, u;
     int kbw, nwin, kb_total, resident, win, seg_in_win, nflush;
+    int worker, workers, num_tiles, wave, full_waves;
 
-    __device__ void init(const GramArgs& a, int worker) {
+    __device__ void init(const GramArgs& a, int w) {
         kbw = a.kb_window;
         kb_total = a.kb_total;
         resident = a.resident;
+        worker = w;
+        workers = a.num_workers;
+        num_tiles = a.num_tiles;
         nwin = (kb_total + kbw - 1) / kbw;
-        const long long uw = (long long)a.num_tiles * kbw;
-        // speed-weighted split (equal shares until the first launches have been timed, see rebalance_kernel)
-        u_begin = (long long)((double)uw * a.cum[worker]);
-        u_end = (worker + 1 == a.num_workers) ? uw : (long long)((double)uw * a.cum[worker + 1]);
-        u = u_begin;
         win = 0;
         seg_in_win = 0;
         nflush = 0;
+        wave = 0;
+        if (resident) {
+            const long long uw = (long long)a.num_tiles * kbw;
+            // speed-weighted split (equal shares until the first launches have been timed, see rebalance_kernel)
+            u_begin = (long long)((double)uw * a.cum[worker]);
+            u_end = (worker + 1 == a.num_workers) ? uw : (long long)((double)uw * a.cum[worker + 1]);
+        } else {
+            full_waves = num_tiles / workers;
+            const long long tail_units = (long long)(num_tiles - full_waves * workers) * kb_total;
+            u_begin = tail_units * worker / workers;       // units of the leftover tiles, relative to the first of them
+            u_end = tail_units * (worker + 1) / workers;
+        }
+        u = u_begin;
     }
     __device__ bool next(Seg& s) {
+        if (!resident) {
+            s.win = 0;
+            s.last_in_win = 0;
+            s.first = 1;
+            s.flush = 1;
+            s.slot = nflush & 1;
+            s.use = nflush >> 1;
+            if (wave < full_waves) {                        // one whole tile of the current wave
+                s.tile = wave * workers + worker;
+                s.kb0 = 0;
+                s.kb1 = kb_total;
+                ++wave;
+                ++nflush;
+                return true;
+            }
+            if (u >= u_end) return false;                   // stream-K tail
+            const int t = (int)(u / kb_total);
+            const int lo = (int)(u - (long long)t * kb_total);
+            const long long rem = u_end - u;
+            const int hi = rem < (long long)(kb_total - lo) ? lo + (int)rem : kb_total;
+            u += hi - lo;
+            s.tile = full_waves * workers + t;
+            s.kb0 = lo;
+            s.kb1 = hi;
+            ++nflush;
+            return true;
+        }
         if (u_begin >= u_end) return false;
         if (u >= u_end) {
             ++win;
@@ -127,18 +170,10 @@ struct Sched {
         s.kb1 = base + min(hi, cnt);
         s.win = win;
         s.last_in_win = (u >= u_end);
-        if (resident) {
-            s.slot = seg_in_win;
-            s.first = (win == 0);
-            s.flush = (win == nwin - 1);
-            s.use = 0;
-        } else {
-            s.slot = nflush & 1;
-            s.first = 1;
-            s.flush = 1;
-            s.use = nflush >> 1;
-            ++nflush;
-        }
+        s.slot = seg_in_win;
+        s.first = (win == 0);
+        s.flush = (win == nwin - 1);
+        s.use = 0;
         ++seg_in_win;
         return true;
     }
@@ -586,12 +621,16 @@ static cudaError_t build_tiles(GramPlan& plan, int n, int BN, cudaStream_t strea
     const int BM = 128 * plan.cta_group;
     std::vector<int2> tiles;
     const int nbn = (n + BN - 1) / BN, nbm = (n + BM - 1) / BM;
-    for (int b = 0; b < nbn; ++b)
-        for (int am = 0; am < nbm; ++am) {
-            // tile covers output rows [b*BN, b*BN+BN) x cols [am*BM, am*BM+BM); keep it if it touches row >= col
-            const int max_row = std::min(n, b * BN + BN) - 1;
-            if (am * BM <= max_row) tiles.push_back(make_int2(am, b));
-        }
+    // Strips of 8 row-blocks, walked column by column: any run of ~num_sms/2 consecutive tiles (one wave of the
+    // large-N schedule) is a compact 8 x 9 patch of S that needs 17 row panels of X instead of 75.
+    constexpr int kStrip = 8;
+    for (int bb = 0; bb < nbn; bb += kStrip)
+        for (int am = 0; am < nbm; ++am)
+            for (int b = bb; b < std::min(nbn, bb + kStrip); ++b) {
+                // tile covers output rows [b*BN, b*BN+BN) x cols [am*BM, am*BM+BM); keep it if it touches row >= col
+                const int max_row = std::min(n, b * BN + BN) - 1;
+                if (am * BM <= max_row) tiles.push_back(make_int2(am, b));
+            }
     if (plan.d_tiles) cudaFree(plan.d_tiles);
     plan.d_tiles = nullptr;
     cudaError_t e = cudaMalloc(&plan.d_tiles, tiles.size() * sizeof(int2));
