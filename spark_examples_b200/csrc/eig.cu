@@ -14,7 +14,9 @@
 // contiguous so every pass is coalesced; one warp owns one row in the trailing update.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <cmath>
 #include <cstdint>
 
@@ -224,6 +226,137 @@ __global__ void __launch_bounds__(128) tridiag_big_kernel(double* __restrict__ A
     }
     const double acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
     if (lane == 0) p[i] = tj * acc;
+}
+
+// One launch per Householder step (used when 3 n doubles fit in shared memory).  Every block redundantly redoes the
+// O(n) serial part of the step in its own shared memory -- w of the previous step, the updated row j, reflector j --
+// and then applies the pending rank-2 update to ITS rows fused with the mat-vec of step j.  No single-block kernel
+// sits on the critical path any more; the redundant vector reads are ~10 % of the matrix traffic at 1 block per SM.
+//   p2 : two length-n buffers, step j reads p_{j-1} from p2[(j+1)&1] and writes p_j to p2[j&1]
+//   v2 : two length-n buffers, block 0 publishes v_j in v2[j&1]; v_{j-1} is read from v2[(j+1)&1]
+// Reflector j-1 is copied into row j-1 of A by block 0 of step j (row j-1 has no readers any more by then).
+__global__ void __launch_bounds__(512) tridiag_fused_kernel(double* __restrict__ A, int n, int* __restrict__ step,
+                                                            double* __restrict__ v2, double* __restrict__ p2,
+                                                            double* __restrict__ diag, double* __restrict__ off,
+                                                            double* __restrict__ tau) {
+    extern __shared__ double fsm[];
+    __shared__ double red[33];
+    __shared__ double bc[2];
+    __shared__ int is_last;
+    double* vp = fsm;             // v_{j-1}
+    double* w = fsm + n;          // w_{j-1}
+    double* v = fsm + 2 * (size_t)n;   // row j after the pending update, then v_j
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int j = step[1];
+    if (j >= n) return;
+    const double* vprev_g = v2 + (size_t)((j + 1) & 1) * n;
+    const double* p_in = p2 + (size_t)((j + 1) & 1) * n;
+    double* p_out = p2 + (size_t)(j & 1) * n;
+    double* rowj = A + (size_t)j * n;
+    // ---- serial part, redundantly per block
+    double acc = 0.0;
+    if (j > 0) {
+        for (int t = j + tid; t < n; t += nt) {
+            const double a = vprev_g[t], b = p_in[t];
+            vp[t] = a;
+            w[t] = b;                      // p for now
+            acc += a * b;
+        }
+    }
+    const double pv = block_sum(acc, red);                       // (barriers also publish vp / w)
+    const double alpha = (j > 0) ? 0.5 * tau[j - 1] * pv : 0.0;
+    const double vj = (j > 0) ? vp[j] : 0.0;
+    const double wj = (j > 0) ? w[j] - alpha * vj : 0.0;
+    __syncthreads();                                             // everyone has read w[j] before it is overwritten
+    acc = 0.0;
+    for (int t = j + tid; t < n; t += nt) {
+        double r = rowj[t];
+        if (j > 0) {
+            const double vt = vp[t];
+            const double wt = w[t] - alpha * vt;
+            w[t] = wt;
+            r -= vj * wt + wj * vt;
+        } else {
+            vp[t] = 0.0;
+            w[t] = 0.0;
+        }
+        v[t] = r;
+        if (t >= j + 2) acc += r * r;
+        if (t == j) bc[0] = r;
+        if (t == j + 1) bc[1] = r;
+    }
+    const double xnorm2 = block_sum(acc, red);
+    double beta = 0.0, tj = 0.0, scale = 0.0;
+    if (j < n - 1) {
+        const double a1 = bc[1];
+        if (xnorm2 == 0.0) {
+            beta = a1;
+        } else {
+            beta = -copysign(sqrt(a1 * a1 + xnorm2), a1);
+            tj = (beta - a1) / beta;
+            scale = 1.0 / (a1 - beta);
+        }
+        for (int t = j + 1 + tid; t < n; t += nt) v[t] = (t == j + 1) ? 1.0 : v[t] * scale;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        if (tid == 0) {
+            diag[j] = bc[0];
+            if (j < n - 1) {
+                off[j] = beta;
+                tau[j] = tj;
+            }
+        }
+        double* vout = v2 + (size_t)(j & 1) * n;
+        for (int t = j + 1 + tid; t < n; t += nt) vout[t] = v[t];
+        if (j > 0) {
+            double* store = A + (size_t)(j - 1) * n;             // reflector j-1 for the back-transformation
+            for (int t = j + tid; t < n; t += nt) store[t] = vp[t];
+        }
+    }
+    // ---- this block's share of the trailing rows: pending update fused with the mat-vec of step j
+    if (j < n - 1) {
+        const int warps = nt >> 5;
+        for (int i = j + 1 + blockIdx.x * warps + (tid >> 5); i < n; i += gridDim.x * warps) {
+            double* row = A + (size_t)i * n;
+            const double vi = vp[i], wi = w[i];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int t = j + 1 + lane;
+            if (j > 0) {
+                for (; t + 96 < n; t += 128) {
+                    const double r0 = row[t], r1 = row[t + 32], r2 = row[t + 64], r3 = row[t + 96];
+                    const double u0 = r0 - (vi * w[t] + wi * vp[t]);
+                    const double u1 = r1 - (vi * w[t + 32] + wi * vp[t + 32]);
+                    const double u2 = r2 - (vi * w[t + 64] + wi * vp[t + 64]);
+                    const double u3 = r3 - (vi * w[t + 96] + wi * vp[t + 96]);
+                    row[t] = u0; row[t + 32] = u1; row[t + 64] = u2; row[t + 96] = u3;
+                    a0 += u0 * v[t]; a1 += u1 * v[t + 32]; a2 += u2 * v[t + 64]; a3 += u3 * v[t + 96];
+                }
+                for (; t < n; t += 32) {
+                    const double u = row[t] - (vi * w[t] + wi * vp[t]);
+                    row[t] = u;
+                    a0 += u * v[t];
+                }
+            } else {
+                for (; t + 96 < n; t += 128) {
+                    a0 += row[t] * v[t]; a1 += row[t + 32] * v[t + 32];
+                    a2 += row[t + 64] * v[t + 64]; a3 += row[t + 96] * v[t + 96];
+                }
+                for (; t < n; t += 32) a0 += row[t] * v[t];
+            }
+            const double sum = warp_sum((a0 + a1) + (a2 + a3));
+            if (lane == 0) p_out[i] = tj * sum;
+        }
+    }
+    // ---- the last block to finish advances the step (every block has read it by then)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(step + 2, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (is_last && tid == 0) {
+        step[2] = 0;
+        step[1] = j + 1;
+    }
 }
 
 // ------------------------------------------------------------------------- eigenvalues of T (bisection)
@@ -501,7 +634,7 @@ cudaError_t eig_alloc(EigWork& w, int n, int kmax) {
     VPCA_TRY(cudaMalloc(&w.d_rowsum, (size_t)n * sizeof(double)));
     VPCA_TRY(cudaMalloc(&w.d_v, 2 * (size_t)n * sizeof(double)));   // vprev / vcur ping-pong
     VPCA_TRY(cudaMalloc(&w.d_w, (size_t)n * sizeof(double)));
-    VPCA_TRY(cudaMalloc(&w.d_p, (size_t)n * sizeof(double)));
+    VPCA_TRY(cudaMalloc(&w.d_p, 2 * (size_t)n * sizeof(double)));   // p ping-pong (fused step kernel)
     VPCA_TRY(cudaMalloc(&w.d_diag, (size_t)n * sizeof(double)));
     VPCA_TRY(cudaMalloc(&w.d_off, 2 * (size_t)n * sizeof(double)));   // e and e^2
     VPCA_TRY(cudaMalloc(&w.d_tau, (size_t)n * sizeof(double)));
@@ -538,25 +671,40 @@ cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) 
     cudaError_t e = cudaMemsetAsync(w.d_v, 0, 2 * (size_t)n * sizeof(double), stream);
     if (e != cudaSuccess) return e;
     cudaMemsetAsync(w.d_w, 0, (size_t)n * sizeof(double), stream);
-    cudaMemsetAsync(w.d_p, 0, (size_t)n * sizeof(double), stream);
+    cudaMemsetAsync(w.d_p, 0, 2 * (size_t)n * sizeof(double), stream);
     cudaMemsetAsync(w.d_tau, 0, (size_t)n * sizeof(double), stream);
     cudaMemsetAsync(w.d_off, 0, 2 * (size_t)n * sizeof(double), stream);
     int64_t nl = 0;
     cudaMemsetAsync(w.d_step, 0, 4 * sizeof(int), stream);
-    // One CUDA graph holds kGraphSteps identical (small, big) launch pairs; it is replayed until all n steps ran.
-    // Blocks of the big kernel beyond the shrinking trailing matrix exit at once, launches past step n are no-ops.
+    // The step loop is replayed from ONE CUDA graph of kGraphSteps identical launches: the step index lives in device
+    // memory, so no launch has step-dependent arguments; launches past the last step return at once.
     constexpr int kGraphSteps = 64;
+    const size_t fused_smem = 3 * (size_t)n * sizeof(double);
+    const bool fused = fused_smem <= 200 * 1024 && getenv("VPCA_EIG_TWO_KERNELS") == nullptr;
     const int big_blocks = (n - 1 + 3) / 4 > 0 ? (n - 1 + 3) / 4 : 1;
-    if (w.graph_exec == nullptr || w.graph_n != n) {
+    if (w.graph_exec == nullptr || w.graph_n != n || w.graph_fused != fused) {
         if (w.graph_exec != nullptr) cudaGraphExecDestroy(w.graph_exec);
         w.graph_exec = nullptr;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (fused) {
+            e = cudaFuncSetAttribute(tridiag_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+        }
+        const int fused_blocks = std::max(1, std::min(sms, (n + 15) / 16));
         cudaGraph_t graph = nullptr;
         e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
         if (e != cudaSuccess) return e;
         for (int g = 0; g < kGraphSteps; ++g) {
-            tridiag_small_kernel<<<1, kSmallThreads, 0, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_p, w.d_w, w.d_diag, w.d_off,
-                                                                  w.d_tau, w.d_scal);
-            tridiag_big_kernel<<<big_blocks, 128, 0, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_w, w.d_tau, w.d_p);
+            if (fused) {
+                tridiag_fused_kernel<<<fused_blocks, 512, fused_smem, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_p, w.d_diag,
+                                                                                w.d_off, w.d_tau);
+            } else {
+                tridiag_small_kernel<<<1, kSmallThreads, 0, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_p, w.d_w, w.d_diag,
+                                                                      w.d_off, w.d_tau, w.d_scal);
+                tridiag_big_kernel<<<big_blocks, 128, 0, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_w, w.d_tau, w.d_p);
+            }
         }
         e = cudaStreamEndCapture(stream, &graph);
         if (e != cudaSuccess) return e;
@@ -564,11 +712,12 @@ cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) 
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return e;
         w.graph_n = n;
+        w.graph_fused = fused;
     }
     for (int j = 0; j < n; j += kGraphSteps) {
         e = cudaGraphLaunch(w.graph_exec, stream);
         if (e != cudaSuccess) return e;
-        nl += 2 * kGraphSteps;
+        nl += (fused ? 1 : 2) * kGraphSteps;
     }
     bisect_kernel<<<k, 256, 0, stream>>>(w.d_diag, w.d_off, n, w.d_off + n, w.d_evals, w.d_scal);
     const size_t invit_smem = 8 * (size_t)n * sizeof(double);

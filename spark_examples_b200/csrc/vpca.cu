@@ -613,6 +613,9 @@ int vpca_compute_pca(vpca_ctx* ctx, int32_t k, double* vecs, double* evals, int3
     if (vecs == nullptr || k < 1 || k > ctx->n || k > std::max(ctx->num_pc, 16))
         return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_compute_pca: k=%d out of range", k);
     if (!ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "call vpca_finalize_gram first");
+    if (ctx->n > 65535)
+        return fail(ctx, VPCA_ERR_UNSUPPORTED, "computePca is limited to 65535 samples, like the reference (MLlib RowMatrix "
+                    "behind VariantsPca.scala:226 refuses more columns); the Gram itself has no such limit");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     CUDA_OK(ctx, cudaEventRecord(ctx->ev_e0, ctx->stream));
     int rc = run_center(ctx);

@@ -83,6 +83,7 @@ struct EigWork {
     int* d_step = nullptr;               // {next step, step of the pending trailing update}
     cudaGraphExec_t graph_exec = nullptr; // kGraphSteps tridiagonalisation steps, replayed n / kGraphSteps times
     int graph_n = 0;
+    bool graph_fused = false;
     int kmax = 0;
 };
 cudaError_t eig_alloc(EigWork& w, int n, int kmax);

@@ -446,3 +446,31 @@ def test_gram_large_n_stream_k_vs_torch(oracle, dtype_name):
     Xf = torch.cat([view[p].to(torch.float32) for p in range(npan)], dim=1)[:, :nv]
     want = (Xf @ Xf.t()).to(torch.int32)
     assert torch.equal(S, want)
+
+
+def test_gram_biobank_scale_n(oracle):
+    """N = 70 000 samples (S = 19.6 GB int32 resident in HBM, > 65 535 so beyond what the reference's eigen step takes):
+    64-bit indexing of the tiled Gram, spot-checked on random rows against an fp32 matmul; computePca refuses like MLlib."""
+    import torch
+    from spark_examples_b200 import native
+    n, nv, P = 70_000, 4096, 4096
+    free, _ = torch.cuda.mem_get_info()
+    if free < 30 * 2 ** 30:
+        pytest.skip("needs 30 GB of free HBM")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    S = torch.zeros((n, n), dtype=torch.int32, device="cuda")
+    with _native(n, stream=stream.cuda_stream, d_gram=S.data_ptr(), max_multiplicity=1) as nat:
+        X = torch.empty(nat.panelBytes(nv, P), dtype=torch.uint8, device="cuda")
+        nat.synthPanelsDevice(SEED, 0, nv, 0, X.data_ptr(), P)
+        nat.accumulatePanels(X.data_ptr(), nv, P)
+        nat.finalizeGram()
+        stream.synchronize()
+        Xf = X.view(torch.int8).view(n, P).to(torch.float16)
+        rows = torch.tensor([0, 1, 255, 256, 2503, 32767, 32768, 46340, 46341, 65535, 65536, n - 2, n - 1], device="cuda")
+        want = (Xf[rows].to(torch.float32) @ Xf.to(torch.float32).t()).to(torch.int32)
+        assert torch.equal(S[rows], want)
+        assert torch.equal(S[:, rows].t().contiguous(), want)
+        with pytest.raises(native.VpcaError) as ei:
+            nat.computePca(2)
+        assert ei.value.code == native.VPCA_ERR_UNSUPPORTED
