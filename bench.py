@@ -143,6 +143,7 @@ def cpu_similarity_sample(n, seconds, threads=None):
     from oracle import oracle
     oracle.build()
     threads = threads or host_threads()
+    oracle.c_set_threads(threads)          # also for the sample generator (torchrun exports OMP_NUM_THREADS=1)
     # grow the sample geometrically until one pass costs about `seconds` (the fixed cost of allocating and summing
     # `threads` dense matrices makes small probes useless for extrapolation on many-core hosts)
     nv, dt = threads * 4, 0.0

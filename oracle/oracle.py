@@ -76,6 +76,8 @@ def lib() -> ctypes.CDLL:
         L.vo_synth_calls.argtypes = [ctypes.c_uint64, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
                                      i64p, i32p, i64p]
         L.vo_num_threads.restype = ctypes.c_int
+        L.vo_set_threads.restype = None
+        L.vo_set_threads.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -89,6 +91,10 @@ def _p(a: np.ndarray, ct):
 # ----------------------------------------------------------------------------------------------
 def c_num_threads() -> int:
     return int(lib().vo_num_threads())
+
+
+def c_set_threads(n: int) -> None:
+    lib().vo_set_threads(int(n))
 
 
 def c_encode_calls(n_samples, call_off, callset, gt_off, genotype):

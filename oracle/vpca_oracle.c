@@ -353,6 +353,16 @@ int64_t vo_synth_calls(uint64_t seed, int32_t n, int64_t v0, int64_t nv, int64_t
     return nnz;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU arm of bench.py raises the thread count explicitly. */
+void vo_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int vo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -323,14 +323,20 @@ __global__ void __launch_bounds__(512) tridiag_fused_kernel(double* __restrict__
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int t = j + 1 + lane;
             if (j > 0) {
-                for (; t + 96 < n; t += 128) {
-                    const double r0 = row[t], r1 = row[t + 32], r2 = row[t + 64], r3 = row[t + 96];
-                    const double u0 = r0 - (vi * w[t] + wi * vp[t]);
-                    const double u1 = r1 - (vi * w[t + 32] + wi * vp[t + 32]);
-                    const double u2 = r2 - (vi * w[t + 64] + wi * vp[t + 64]);
-                    const double u3 = r3 - (vi * w[t + 96] + wi * vp[t + 96]);
-                    row[t] = u0; row[t + 32] = u1; row[t + 64] = u2; row[t + 96] = u3;
-                    a0 += u0 * v[t]; a1 += u1 * v[t + 32]; a2 += u2 * v[t + 64]; a3 += u3 * v[t + 96];
+                // 8 independent 8-byte loads per lane in flight: one warp streams a whole (L2-resident) row, so the
+                // row time is set by load latency x iterations
+                for (; t + 224 < n; t += 256) {
+                    double r[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) r[q] = row[t + 32 * q];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) r[q] -= vi * w[t + 32 * q] + wi * vp[t + 32 * q];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) row[t + 32 * q] = r[q];
+                    a0 += r[0] * v[t] + r[4] * v[t + 128];
+                    a1 += r[1] * v[t + 32] + r[5] * v[t + 160];
+                    a2 += r[2] * v[t + 64] + r[6] * v[t + 192];
+                    a3 += r[3] * v[t + 96] + r[7] * v[t + 224];
                 }
                 for (; t < n; t += 32) {
                     const double u = row[t] - (vi * w[t] + wi * vp[t]);
@@ -680,7 +686,9 @@ cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) 
     // memory, so no launch has step-dependent arguments; launches past the last step return at once.
     constexpr int kGraphSteps = 64;
     const size_t fused_smem = 3 * (size_t)n * sizeof(double);
-    const bool fused = fused_smem <= 200 * 1024 && getenv("VPCA_EIG_TWO_KERNELS") == nullptr;
+    // one launch per step while every trailing row still gets its own warp (<= ~16 rows per SM-resident block);
+    // beyond that the two-kernel form (one warp per row over a larger grid) is faster (measured: 4096 -> 162 vs 133 ms)
+    const bool fused = n <= 3072 && fused_smem <= 200 * 1024 && getenv("VPCA_EIG_TWO_KERNELS") == nullptr;
     const int big_blocks = (n - 1 + 3) / 4 > 0 ? (n - 1 + 3) / 4 : 1;
     if (w.graph_exec == nullptr || w.graph_n != n || w.graph_fused != fused) {
         if (w.graph_exec != nullptr) cudaGraphExecDestroy(w.graph_exec);
@@ -722,12 +730,8 @@ cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) 
     bisect_kernel<<<k, 256, 0, stream>>>(w.d_diag, w.d_off, n, w.d_off + n, w.d_evals, w.d_scal);
     const size_t invit_smem = 8 * (size_t)n * sizeof(double);
     if (invit_smem <= 200 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            e = cudaFuncSetAttribute(invit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
+        e = cudaFuncSetAttribute(invit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;   // (per device: not cached)
         invit_kernel<true><<<1, 256, invit_smem, stream>>>(w.d_diag, w.d_off, n, k, w.d_evals, w.d_scal, w.d_lu,
                                                            w.d_evecs);
     } else {

@@ -572,13 +572,9 @@ EncodeTiledFn get_encode_fn() {
 template <int CG, int KIND>
 cudaError_t launch(const CUtensorMap& tmap, const GramArgs& args, int grid, cudaStream_t stream) {
     using C = Cfg<CG, KIND>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gram_kernel<CG, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // per launch, not cached: the attribute is per device and one process may drive several GPUs
+    cudaError_t ea = cudaFuncSetAttribute(gram_kernel<CG, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (ea != cudaSuccess) return ea;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kThreads);
