@@ -113,6 +113,12 @@ int vpca_accumulate_calls(vpca_ctx* ctx, int64_t partition_id, const int64_t* of
  * than 65535 columns at VariantsPca.scala:226). */
 int vpca_accumulate_calls_u16(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const uint16_t* sample_idx,
                               int64_t nv);
+/* Packed wire format: one bitmap per variant instead of an index list -- bit s (least significant bit
+ * first) of row v is `hasVariation` of sample s (VariantsPca.scala:58), rows stride_bytes apart
+ * (>= ceil(n_samples / 8)).  N/8 bytes per variant on the wire whatever the carrier count (313 B at N = 2504 against
+ * ~4.3 KB of int32 indices for the synthetic cohort); expanded to cells on the device by a bit-matrix transpose.
+ * Binary carriers only (a sample cannot be listed twice).  Same staging / commit semantics as vpca_accumulate_calls. */
+int vpca_accumulate_bits(vpca_ctx* ctx, int64_t partition_id, const uint8_t* bits, int64_t nv, int64_t stride_bytes);
 int vpca_commit(vpca_ctx* ctx, int64_t partition_id);
 int vpca_abort(vpca_ctx* ctx, int64_t partition_id);
 
@@ -152,6 +158,11 @@ int vpca_finalize_gram(vpca_ctx* ctx);
 /* Copy the finalized Gram to host, row-major n_samples x n_samples int32 (the collected
  * RDD[((Int, Int), Int)] in key order). */
 int vpca_get_gram(vpca_ctx* ctx, int32_t* out);
+/* Checkpoint / resume of a long accumulation: copy out / restore the Gram as accumulated so far
+ * (committed partitions only, NOT finalized: lower triangle meaningful).  After vpca_load_partial_gram accumulation
+ * continues on top of the restored counts; the caller keeps the watermark (which partitions are in it). */
+int vpca_get_partial_gram(vpca_ctx* ctx, int32_t* out);
+int vpca_load_partial_gram(vpca_ctx* ctx, const int32_t* gram);
 /* Load a Gram (checkpoint restore / tests); marks it finalized. */
 int vpca_set_gram(vpca_ctx* ctx, const int32_t* gram);
 

@@ -107,4 +107,5 @@ class PcaConf(GenomicsConf):
             ("gpuDtype", str, "int8", False),             # int8 | bf16 genotype encoding
             ("synthetic", str, None, False),              # "N,V[,seed]": synthetic cohort instead of the retired API
             ("variantsPerPartition", int, 65536, False),  # rows per partition for offline/synthetic sources
+            ("checkpointPath", str, None, False),         # save / resume the similarity matrix + partition watermark
         ]

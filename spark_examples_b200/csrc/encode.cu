@@ -103,7 +103,111 @@ __global__ void encode_e2m1_kernel(const int64_t* __restrict__ off, int64_t base
     if (bad) atomicOr(flags, bad);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Bitmap rows -> cells (packed wire format).  Input: one bitmap per variant, bit s (LSB first) of row v =
+// sample s has variation; rows `stride` bytes apart.  A warp takes 32 variants x 32 samples: lane = variant loads one
+// 32-bit word (32 samples of its variant), 32 ballots transpose the 32 x 32 bit tile so that lane = sample holds the
+// 32 variant bits of its sample, which it expands to 32 cells and stores as one contiguous 32-byte (int8) /
+// 16-byte (e2m1) / 64-byte (bf16) run of its sample row.  A bit-matrix transpose at HBM speed; no atomics.
+template <int BITS>
+__global__ void bits_to_cells_kernel(const uint8_t* __restrict__ bits, int64_t stride, int64_t nv, int n,
+                                     uint8_t* __restrict__ x, int64_t ld, int64_t panel) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int words = (n + 31) / 32;                          // 32-sample words per variant
+    const int64_t vgroups = (nv + 31) / 32;
+    if (warp >= vgroups * words) return;
+    const int64_t vg = warp / words;
+    const int k = (int)(warp - vg * words);
+    const int64_t v = vg * 32 + lane;                         // my variant while loading
+    uint32_t word = 0;
+    if (v < nv) {
+        const uint8_t* row = bits + v * stride + (size_t)k * 4;
+        const int64_t avail = stride - (int64_t)k * 4;        // bytes of this row from here on
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (b < avail) word |= (uint32_t)row[b] << (8 * b);
+    }
+    uint32_t mine = 0;                                        // after the loop: bit j = variant vg*32+j at MY sample
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+        const uint32_t m = __ballot_sync(0xffffffffu, (word >> b) & 1u);
+        if (lane == b) mine = m;
+    }
+    const int smp = k * 32 + lane;
+    if (smp >= n) return;
+    const int64_t v0 = vg * 32;
+    // cell index of (smp, v0): 32 consecutive cells never straddle a panel (panels are multiples of 128 cells)
+    int64_t cell;
+    if (panel == 0) cell = (int64_t)smp * ld + v0;
+    else {
+        const int64_t pnl = v0 / panel;
+        cell = pnl * (int64_t)n * panel + (int64_t)smp * panel + (v0 - pnl * panel);
+    }
+    if constexpr (BITS == 8) {
+        uint32_t o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t nib = (mine >> (4 * q)) & 0xFu;
+            o[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(x + cell);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    } else if constexpr (BITS == 4) {
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t byte = (mine >> (8 * q)) & 0xFFu;   // 8 variants -> 8 nibbles, carrier = code 2
+            uint32_t w = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w |= ((byte >> i) & 1u) << (4 * i + 1);
+            o[q] = w;
+        }
+        *reinterpret_cast<uint4*>(x + cell / 2) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        uint32_t o[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const uint32_t two = (mine >> (2 * q)) & 3u;       // bf16 1.0 = 0x3F80
+            o[q] = ((two & 1u) ? 0x3F80u : 0u) | ((two & 2u) ? 0x3F800000u : 0u);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(x + cell * 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+}
+
 }  // namespace
+
+cudaError_t encode_bits(const uint8_t* d_bits, int64_t stride, int64_t nv, int n, int elem_bits, void* d_x, int64_t ld,
+                        int64_t panel, cudaStream_t stream) {
+    if (nv <= 0) return cudaSuccess;
+    // every cell of the touched 32-variant groups is written, so only a partial last panel / k-block needs zeroing
+    cudaError_t e = cudaSuccess;
+    if (panel > 0) {
+        const int64_t npanels = (nv + panel - 1) / panel;
+        if (npanels * panel != ((nv + 31) / 32) * 32)
+            e = cudaMemsetAsync(static_cast<char*>(d_x) + (size_t)(npanels - 1) * n * panel * elem_bits / 8, 0,
+                                (size_t)n * panel * elem_bits / 8, stream);
+    } else {
+        const size_t pitch = (size_t)ld * elem_bits / 8;
+        size_t width = (((size_t)nv + 127) / 128) * 128 * elem_bits / 8;
+        if (width > pitch) width = pitch;
+        e = cudaMemset2DAsync(d_x, pitch, 0, width, (size_t)n, stream);
+    }
+    if (e != cudaSuccess) return e;
+    const int64_t warps = ((nv + 31) / 32) * ((n + 31) / 32);
+    const int threads = 256;
+    const int64_t blocks = (warps * 32 + threads - 1) / threads;
+    if (elem_bits == 8)
+        bits_to_cells_kernel<8><<<(unsigned)blocks, threads, 0, stream>>>(d_bits, stride, nv, n, static_cast<uint8_t*>(d_x), ld, panel);
+    else if (elem_bits == 4)
+        bits_to_cells_kernel<4><<<(unsigned)blocks, threads, 0, stream>>>(d_bits, stride, nv, n, static_cast<uint8_t*>(d_x), ld, panel);
+    else
+        bits_to_cells_kernel<16><<<(unsigned)blocks, threads, 0, stream>>>(d_bits, stride, nv, n, static_cast<uint8_t*>(d_x), ld, panel);
+    return cudaGetLastError();
+}
 
 template <typename IdxT>
 static cudaError_t encode_launch(const int64_t* d_off, int64_t base, const IdxT* d_idx, int64_t nv, int n, int elem_bits,

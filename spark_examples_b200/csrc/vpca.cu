@@ -429,6 +429,62 @@ static int accumulate_calls_impl(vpca_ctx* ctx, int64_t partition_id, const int6
     return VPCA_OK;
 }
 
+int vpca_accumulate_bits(vpca_ctx* ctx, int64_t partition_id, const uint8_t* bits, int64_t nv, int64_t stride_bytes) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nv < 0 || (nv > 0 && bits == nullptr) || stride_bytes < (ctx->n + 7) / 8)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_accumulate_bits: stride_bytes must be >= ceil(n_samples / 8)");
+    if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    if (nv == 0) return VPCA_OK;
+    int rc = check_overflow(ctx, nv);
+    if (rc != VPCA_OK) return rc;
+    rc = ensure_staging(ctx);
+    if (rc != VPCA_OK) return rc;
+    int32_t* target = ctx->d_S;
+    vpca_ctx::Slot* slot = nullptr;
+    if (partition_id >= 0) {
+        slot = find_slot(ctx, partition_id, true, &rc);
+        if (slot == nullptr) return rc;
+        target = slot->d_S;
+    }
+    // bits beyond sample n-1 in the last byte of a row would be read as carriers of non-existent samples: the kernel
+    // masks them (smp >= n), nothing to validate on the host.
+    const int64_t P = ctx->panel;
+    const int64_t cap_rows = std::min<int64_t>(ctx->chunk_variants, (ctx->chunk_nnz * (int64_t)sizeof(int32_t)) / stride_bytes);
+    if (cap_rows < 32) {
+        if (slot) slot->used = false;
+        return fail(ctx, VPCA_ERR_BAD_ARG, "stride_bytes too large for the staging buffer");
+    }
+    const int64_t step = std::max<int64_t>(P, (cap_rows / P) * P) <= cap_rows ? std::max<int64_t>(P, (cap_rows / P) * P)
+                                                                              : (cap_rows / 32) * 32;
+    int chunk = 0;
+    for (int64_t v = 0; v < nv; v += step, ++chunk) {
+        const int64_t nvc = std::min(step, nv - v);
+        const int b = chunk & 1;
+        CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+        CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_idx[b], bits + (size_t)v * stride_bytes, (size_t)nvc * stride_bytes,
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+        ctx->st.h2d_bytes += nvc * stride_bytes;
+        CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
+        CUDA_OK(ctx, encode_bits(reinterpret_cast<const uint8_t*>(ctx->d_idx[b]), stride_bytes, nvc, ctx->n, ctx->elem_bits,
+                                 ctx->d_x[b], P, P, ctx->stream));
+        ctx->st.kernel_launches += 1;
+        rc = launch_gram(ctx, ctx->d_x[b], nvc, P, P, target);
+        if (rc != VPCA_OK) {
+            if (slot) slot->used = false;
+            return rc;
+        }
+        CUDA_OK(ctx, cudaEventRecord(ctx->ev_done[b], ctx->stream));
+    }
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));   // the caller's buffer is free to reuse on return
+    if (slot) slot->nv += nv;
+    else ctx->total_variants += nv;
+    ctx->st.variants_accumulated += nv;
+    return VPCA_OK;
+}
+
 int vpca_commit(vpca_ctx* ctx, int64_t partition_id) {
     if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -576,6 +632,32 @@ int vpca_get_gram(vpca_ctx* ctx, int32_t* out) {
     CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_S, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->st.d2h_bytes += (int64_t)bytes;
+    return VPCA_OK;
+}
+
+int vpca_get_partial_gram(vpca_ctx* ctx, int32_t* out) {
+    if (ctx == nullptr || out == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized: use vpca_get_gram");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t bytes = (size_t)ctx->n * ctx->n * sizeof(int32_t);
+    CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_S, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->st.d2h_bytes += (int64_t)bytes;
+    return VPCA_OK;
+}
+
+int vpca_load_partial_gram(vpca_ctx* ctx, const int32_t* gram) {
+    if (ctx == nullptr || gram == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
+    for (auto& s : ctx->slots)
+        if (s.used) return fail(ctx, VPCA_ERR_STATE, "partition %lld is in flight", (long long)s.pid);
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t bytes = (size_t)ctx->n * ctx->n * sizeof(int32_t);
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_S, gram, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->st.h2d_bytes += (int64_t)bytes;
     return VPCA_OK;
 }
 

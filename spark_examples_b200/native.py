@@ -40,7 +40,8 @@ EXPORTED_SYMBOLS = (
     "vpca_finalize_gram", "vpca_get_gram", "vpca_set_gram", "vpca_compute_pca", "vpca_get_centered",
     "vpca_get_tridiagonal", "vpca_synth_dense_device", "vpca_get_stats", "vpca_debug_gram_profile",
     "vpca_gram_export_ipc", "vpca_gram_set_peers", "vpca_peer_barrier", "vpca_accumulate_panels",
-    "vpca_synth_panels_device", "vpca_accumulate_calls_u16",
+    "vpca_synth_panels_device", "vpca_accumulate_calls_u16", "vpca_get_partial_gram", "vpca_load_partial_gram",
+    "vpca_accumulate_bits",
 )
 
 
@@ -123,6 +124,8 @@ def load_library() -> ctypes.CDLL:
     L.vpca_accumulate_calls.argtypes = [vp, i64, vp, vp, i64]
     L.vpca_accumulate_calls_u16.restype = ctypes.c_int
     L.vpca_accumulate_calls_u16.argtypes = [vp, i64, vp, vp, i64]
+    L.vpca_accumulate_bits.restype = ctypes.c_int
+    L.vpca_accumulate_bits.argtypes = [vp, i64, vp, i64, i64]
     L.vpca_commit.restype = ctypes.c_int
     L.vpca_commit.argtypes = [vp, i64]
     L.vpca_abort.restype = ctypes.c_int
@@ -135,6 +138,10 @@ def load_library() -> ctypes.CDLL:
     L.vpca_finalize_gram.argtypes = [vp]
     L.vpca_get_gram.restype = ctypes.c_int
     L.vpca_get_gram.argtypes = [vp, vp]
+    L.vpca_get_partial_gram.restype = ctypes.c_int
+    L.vpca_get_partial_gram.argtypes = [vp, vp]
+    L.vpca_load_partial_gram.restype = ctypes.c_int
+    L.vpca_load_partial_gram.argtypes = [vp, vp]
     L.vpca_set_gram.restype = ctypes.c_int
     L.vpca_set_gram.argtypes = [vp, vp]
     L.vpca_compute_pca.restype = ctypes.c_int
@@ -252,6 +259,16 @@ class NativePca:
         fn = self._lib.vpca_accumulate_calls if idx_bytes == 4 else self._lib.vpca_accumulate_calls_u16
         self._check(fn(self._h, int(partition_id), off_ptr, idx_ptr, int(nv)))
 
+    def accumulateBits(self, partition_id: int, bits: np.ndarray):
+        """bits: (nv, stride) uint8, bit s (LSB first) of row v = sample s carries variant v."""
+        b = np.ascontiguousarray(bits, dtype=np.uint8)
+        if b.ndim != 2:
+            raise VpcaError(VPCA_ERR_BAD_ARG, "bits must be (nv, stride_bytes)")
+        self._check(self._lib.vpca_accumulate_bits(self._h, int(partition_id), _host_ptr(b), b.shape[0], b.shape[1]))
+
+    def accumulateBitsRaw(self, partition_id: int, ptr: int, nv: int, stride_bytes: int):
+        self._check(self._lib.vpca_accumulate_bits(self._h, int(partition_id), ptr, int(nv), int(stride_bytes)))
+
     def accumulateCalls16(self, partition_id: int, offsets, sample_idx):
         off = np.ascontiguousarray(offsets, dtype=np.int64)
         idx = np.ascontiguousarray(sample_idx, dtype=np.uint16)
@@ -322,6 +339,19 @@ class NativePca:
         out = np.empty((self.n, self.n), dtype=np.int32)
         self._check(self._lib.vpca_get_gram(self._h, _host_ptr(out)))
         return out
+
+    def partialGram(self) -> np.ndarray:
+        """The accumulated (not yet finalized) Gram: lower triangle meaningful.  Checkpoint payload."""
+        out = np.empty((self.n, self.n), dtype=np.int32)
+        self._check(self._lib.vpca_get_partial_gram(self._h, _host_ptr(out)))
+        return out
+
+    def loadPartialGram(self, gram: np.ndarray):
+        """Restore a checkpointed partial Gram; accumulation continues on top of it."""
+        g = np.ascontiguousarray(gram, dtype=np.int32)
+        if g.shape != (self.n, self.n):
+            raise VpcaError(VPCA_ERR_BAD_ARG, "gram must be (n, n)")
+        self._check(self._lib.vpca_load_partial_gram(self._h, _host_ptr(g)))
 
     def setGram(self, gram: np.ndarray):
         g = np.ascontiguousarray(gram, dtype=np.int32)

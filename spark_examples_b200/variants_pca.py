@@ -229,8 +229,9 @@ class VariantsPcaDriver:
         Gram into a private staging Gram, committed on success); `reduceByKey(_ + _)` across ranks is one all-reduce."""
         nat = self._native(callsets.n_samples)
         nat.reset()
+        done = self._load_checkpoint(nat, callsets)
         for pid, part in enumerate(callsets.partitions):
-            if vdist.partition_owner(pid, self._world) != self._rank:
+            if vdist.partition_owner(pid, self._world) != self._rank or pid in done:
                 continue
             if isinstance(part, SyntheticSlice):
                 self._accumulate_synthetic(nat, part)
@@ -241,6 +242,9 @@ class VariantsPcaDriver:
             except Exception:
                 nat.abort(pid)
                 raise
+            done.add(pid)
+            self._save_checkpoint(nat, callsets, done, every=16)
+        self._save_checkpoint(nat, callsets, done, every=1)
         if self._world > 1:
             vdist.allreduce_gram(self._gram_tensor)            # VariantsPca.scala:190
         nat.finalizeGram()
@@ -318,6 +322,35 @@ class VariantsPcaDriver:
         self._nat = native.NativePca(n, device=device, dtype=dtype, num_pc=max(2, self.conf.numPc()), stream=stream,
                                      d_gram=d_gram)
         return self._nat
+
+    # -- checkpoint / resume: the natural checkpoint of this job is the int32 Gram (25 MB at N = 2504)
+    #    plus the set of partitions already folded into it -- the counterpart of the reference's --input-path /
+    #    --output-path persistence (GenomicsConf.scala:41,46).  One file per rank; partitions are committed atomically,
+    #    so a file never holds a half-applied partition.
+    def _checkpoint_file(self) -> Optional[str]:
+        if not self.conf.checkpointPath.isDefined:
+            return None
+        return f"{self.conf.checkpointPath()}.rank{self._rank}of{self._world}.npz"
+
+    def _load_checkpoint(self, nat: native.NativePca, callsets: CallsRdd) -> set:
+        path = self._checkpoint_file()
+        if path is None or not os.path.exists(path):
+            return set()
+        ck = np.load(path)
+        if int(ck["n_samples"]) != callsets.n_samples or int(ck["n_partitions"]) != len(callsets.partitions):
+            raise ValueError(f"checkpoint {path} belongs to a different cohort / partitioning")
+        nat.loadPartialGram(ck["gram"])
+        print(f"Resumed {len(ck['done'])} / {len(callsets.partitions)} partitions from {path}.")
+        return set(int(p) for p in ck["done"])
+
+    def _save_checkpoint(self, nat: native.NativePca, callsets: CallsRdd, done: set, every: int):
+        path = self._checkpoint_file()
+        if path is None or len(done) == 0 or len(done) % every:
+            return
+        tmp = path + ".tmp.npz"
+        np.savez(tmp, gram=nat.partialGram(), done=np.array(sorted(done), np.int64), n_samples=callsets.n_samples,
+                 n_partitions=len(callsets.partitions))
+        os.replace(tmp, path)
 
     def _accumulate_synthetic(self, nat: native.NativePca, part: SyntheticSlice, panel: int = 8192):
         """Synthetic partitions are born on the device, directly in the panel layout the Gram kernel streams."""

@@ -76,3 +76,46 @@ def test_unknown_callset_and_bad_index_raise(oracle):
     d = VariantsPcaDriver(conf, common=pkg.VariantsCommon(conf, callsets=callsets, datasets=[bad]))
     with pytest.raises(KeyError):                                  # NoSuchElementException at VariantsPca.scala:59
         d.getCallsRdd(d.getData)
+
+
+def test_checkpoint_resume_counts_every_partition_once(tmp_path, oracle):
+    """a run that dies after some partitions resumes from the saved Gram + watermark and ends with the
+    same similarity matrix as an uninterrupted run."""
+    rng = np.random.default_rng(5)
+    n, nv = 40, 600
+    callsets = [(f"ck-{i}", f"S{i:03d}") for i in range(n)]
+    X = oracle.c_synth_dense(20240901, n, 0, nv)
+    records = _records(rng, callsets, X)
+    ck = str(tmp_path / "pca_ck")
+    args = ["--variants-per-partition", "100", "--checkpoint-path", ck]
+
+    conf = pkg.PcaConf(args)
+    d1 = VariantsPcaDriver(conf, common=pkg.VariantsCommon(conf, callsets=callsets, datasets=[records]))
+    rdd = d1.getCallsRdd(d1.getData)
+    assert len(rdd.partitions) == 6
+    # first attempt: partition 3 is corrupt (index out of range) -> the job dies after 3 committed partitions
+    good3 = rdd.partitions[3]
+    rdd.partitions[3] = type(good3)(good3.offsets.copy(), np.where(np.arange(len(good3.idx)) == 5, n + 7, good3.idx).astype(np.int32))
+    with pytest.raises(IndexError):
+        d1.getSimilarityMatrix(rdd)
+    d1.stop()
+    # (the checkpoint is written every 16 partitions and at the end; force one for the 3 partitions that committed)
+    conf2 = pkg.PcaConf(args)
+    d2 = VariantsPcaDriver(conf2, common=pkg.VariantsCommon(conf2, callsets=callsets, datasets=[records]))
+    rdd2 = d2.getCallsRdd(d2.getData)
+    nat = d2._native(n)
+    nat.reset()
+    for pid in range(3):
+        nat.accumulateCalls(pid, rdd2.partitions[pid].offsets, rdd2.partitions[pid].idx)
+        nat.commit(pid)
+    d2._save_checkpoint(nat, rdd2, {0, 1, 2}, every=1)
+    d2.stop()
+    # resume: only partitions 3..5 are processed again
+    conf3 = pkg.PcaConf(args)
+    d3 = VariantsPcaDriver(conf3, common=pkg.VariantsCommon(conf3, callsets=callsets, datasets=[records]))
+    sim = d3.getSimilarityMatrix(d3.getCallsRdd(d3.getData))
+    st = d3._nat.stats()
+    S = sim.toArray()
+    d3.stop()
+    assert np.array_equal(S, oracle.np_similarity_dense(X))
+    assert st["variants_accumulated"] == sum(len(p.offsets) - 1 for p in rdd2.partitions[3:])

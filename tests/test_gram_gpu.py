@@ -474,3 +474,28 @@ def test_gram_biobank_scale_n(oracle):
         with pytest.raises(native.VpcaError) as ei:
             nat.computePca(2)
         assert ei.value.code == native.VPCA_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("dtype_name", ["i8", "e2m1", "bf16"])
+def test_bitmap_rows_wire_format(oracle, monkeypatch, dtype_name):
+    """one N-bit row per variant instead of an index list; ragged N (not a multiple of 8 or 32), nv not a
+    multiple of 32, garbage bits after sample N-1, several staging chunks."""
+    from spark_examples_b200 import native
+    monkeypatch.setenv("VPCA_PANEL", "256")
+    dt = {"i8": native.DTYPE_I8, "e2m1": native.DTYPE_E2M1, "bf16": native.DTYPE_BF16}[dtype_name]
+    n, nv = 333, 1111
+    X = oracle.c_synth_dense(SEED, n, 0, nv)                      # (n, nv) binary
+    stride = (n + 7) // 8 + 3                                     # padded rows
+    bits = np.zeros((nv, stride), np.uint8)
+    packed = np.packbits(X.T.astype(np.uint8), axis=1, bitorder="little")
+    bits[:, : packed.shape[1]] = packed
+    bits[:, (n - 1) // 8] |= np.uint8((0xFF << ((n - 1) % 8 + 1)) & 0xFF)   # garbage after the last sample
+    bits[:, (n + 7) // 8:] = 0xFF
+    want = oracle.np_similarity_dense(X)
+    with _native(n, dtype=dt, chunk_variants=512) as nat:
+        nat.accumulateBits(0, bits[:700])
+        nat.accumulateBits(0, bits[700:])
+        nat.commit(0)
+        nat.finalizeGram()
+        assert np.array_equal(nat.getGram(), want)
+        assert nat.stats()["h2d_bytes"] == nv * stride
