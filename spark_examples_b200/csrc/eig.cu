@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(128) tridiag_big_kernel(double* __restrict__ A
 //   p2 : two length-n buffers, step j reads p_{j-1} from p2[(j+1)&1] and writes p_j to p2[j&1]
 //   v2 : two length-n buffers, block 0 publishes v_j in v2[j&1]; v_{j-1} is read from v2[(j+1)&1]
 // Reflector j-1 is copied into row j-1 of A by block 0 of step j (row j-1 has no readers any more by then).
-__global__ void __launch_bounds__(1024) tridiag_fused_kernel(double* __restrict__ A, int n, int* __restrict__ step,
+__global__ void __launch_bounds__(512) tridiag_fused_kernel(double* __restrict__ A, int n, int* __restrict__ step,
                                                             double* __restrict__ v2, double* __restrict__ p2,
                                                             double* __restrict__ diag, double* __restrict__ off,
                                                             double* __restrict__ tau) {
@@ -314,63 +314,39 @@ __global__ void __launch_bounds__(1024) tridiag_fused_kernel(double* __restrict_
             for (int t = j + tid; t < n; t += nt) store[t] = vp[t];
         }
     }
-    // ---- this block's share of the trailing rows: pending update fused with the mat-vec of step j.
-    // A row is streamed by SPL = 1, 2 or 4 consecutive warps (as many as the shrinking trailing matrix leaves idle), each
-    // taking every SPL-th 128-column block; the partial dot products are combined in a fixed order through shared memory.
+    // ---- this block's share of the trailing rows: pending update fused with the mat-vec of step j
     if (j < n - 1) {
-        __shared__ double part[32];
-        const int warps = nt >> 5, wid = tid >> 5;
-        const int m = n - 1 - j;
-        const int total_warps = (int)gridDim.x * warps;
-        const int spl = (4 * m <= total_warps) ? 4 : ((2 * m <= total_warps) ? 2 : 1);
-        const int groups = warps / spl;                       // row slots per block
-        const int g = wid / spl, q = wid - g * spl;
-        const int iters = (m + (int)gridDim.x * groups - 1) / ((int)gridDim.x * groups);
-        for (int it = 0; it < iters; ++it) {
-            const int i = j + 1 + (it * (int)gridDim.x + (int)blockIdx.x) * groups + g;
+        const int warps = nt >> 5;
+        for (int i = j + 1 + blockIdx.x * warps + (tid >> 5); i < n; i += gridDim.x * warps) {
+            double* row = A + (size_t)i * n;
+            const double vi = vp[i], wi = w[i];
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            if (i < n) {
-                double* row = A + (size_t)i * n;
-                const double vi = vp[i], wi = w[i];
-                int t = j + 1 + q * 128 + lane;
-                const int stride = 128 * spl;
-                if (j > 0) {
-                    for (; t + 96 < n; t += stride) {
-                        const double r0 = row[t], r1 = row[t + 32], r2 = row[t + 64], r3 = row[t + 96];
-                        const double u0 = r0 - (vi * w[t] + wi * vp[t]);
-                        const double u1 = r1 - (vi * w[t + 32] + wi * vp[t + 32]);
-                        const double u2 = r2 - (vi * w[t + 64] + wi * vp[t + 64]);
-                        const double u3 = r3 - (vi * w[t + 96] + wi * vp[t + 96]);
-                        row[t] = u0; row[t + 32] = u1; row[t + 64] = u2; row[t + 96] = u3;
-                        a0 += u0 * v[t]; a1 += u1 * v[t + 32]; a2 += u2 * v[t + 64]; a3 += u3 * v[t + 96];
-                    }
-                    // the last, partial 128-column block belongs to the warp whose turn it is
-                    for (; t < n; t += 32) {
-                        const double u = row[t] - (vi * w[t] + wi * vp[t]);
-                        row[t] = u;
-                        a0 += u * v[t];
-                    }
-                } else {
-                    for (; t + 96 < n; t += stride) {
-                        a0 += row[t] * v[t]; a1 += row[t + 32] * v[t + 32];
-                        a2 += row[t + 64] * v[t + 64]; a3 += row[t + 96] * v[t + 96];
-                    }
-                    for (; t < n; t += 32) a0 += row[t] * v[t];
+            int t = j + 1 + lane;
+            if (j > 0) {
+                // 4 independent 8-byte loads per lane in flight (8 was measured slower: 53 vs 42.5 ms at N = 2504)
+                for (; t + 96 < n; t += 128) {
+                    const double r0 = row[t], r1 = row[t + 32], r2 = row[t + 64], r3 = row[t + 96];
+                    const double u0 = r0 - (vi * w[t] + wi * vp[t]);
+                    const double u1 = r1 - (vi * w[t + 32] + wi * vp[t + 32]);
+                    const double u2 = r2 - (vi * w[t + 64] + wi * vp[t + 64]);
+                    const double u3 = r3 - (vi * w[t + 96] + wi * vp[t + 96]);
+                    row[t] = u0; row[t + 32] = u1; row[t + 64] = u2; row[t + 96] = u3;
+                    a0 += u0 * v[t]; a1 += u1 * v[t + 32]; a2 += u2 * v[t + 64]; a3 += u3 * v[t + 96];
                 }
+                for (; t < n; t += 32) {
+                    const double u = row[t] - (vi * w[t] + wi * vp[t]);
+                    row[t] = u;
+                    a0 += u * v[t];
+                }
+            } else {
+                for (; t + 96 < n; t += 128) {
+                    a0 += row[t] * v[t]; a1 += row[t + 32] * v[t + 32];
+                    a2 += row[t + 64] * v[t + 64]; a3 += row[t + 96] * v[t + 96];
+                }
+                for (; t < n; t += 32) a0 += row[t] * v[t];
             }
             const double sum = warp_sum((a0 + a1) + (a2 + a3));
-            if (spl == 1) {
-                if (lane == 0 && i < n) p_out[i] = tj * sum;
-            } else {
-                if (lane == 0) part[wid] = sum;
-                __syncthreads();
-                if (q == 0 && lane == 0 && i < n) {
-                    double tot = part[wid];
-                    for (int e = 1; e < spl; ++e) tot += part[wid + e];
-                    p_out[i] = tj * tot;
-                }
-                __syncthreads();
-            }
+            if (lane == 0) p_out[i] = tj * sum;
         }
     }
     // ---- the last block to finish advances the step (every block has read it by then)
@@ -719,13 +695,13 @@ cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) 
             e = cudaFuncSetAttribute(tridiag_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) return e;
         }
-        const int fused_blocks = std::max(1, std::min(sms, (n + 31) / 32));
+        const int fused_blocks = std::max(1, std::min(sms, (n + 15) / 16));
         cudaGraph_t graph = nullptr;
         e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
         if (e != cudaSuccess) return e;
         for (int g = 0; g < kGraphSteps; ++g) {
             if (fused) {
-                tridiag_fused_kernel<<<fused_blocks, 1024, fused_smem, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_p, w.d_diag,
+                tridiag_fused_kernel<<<fused_blocks, 512, fused_smem, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_p, w.d_diag,
                                                                                 w.d_off, w.d_tau);
             } else {
                 tridiag_small_kernel<<<1, kSmallThreads, 0, stream>>>(w.d_C, n, w.d_step, w.d_v, w.d_p, w.d_w, w.d_diag,
