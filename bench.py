@@ -423,121 +423,124 @@ def run_b200(args):
     e2e = None
     e2e_steps = args.e2e_steps if args.e2e_steps >= 0 else min(args.steps, 5)
     if e2e_steps > 0:
-        off_h, idx_h, nnz = build_host_calls(torch, cells, n, vpg, dev)
-        S2 = torch.zeros((n, n), dtype=torch.int32, device=dev)
-        nat2 = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=S2.data_ptr(),
-                                max_multiplicity=1)
-
-        def e2e_step():
-            nat2.reset()
-            nat2.accumulateCallsRaw(-1, off_h.data_ptr(), idx_h.data_ptr(), vpg)     # H2D + encode + Gram
-            if world > 1:
-                dist.all_reduce(S2)
-            nat2.finalizeGram()
-            return nat2.computePca(2)                                                # center + eig + D2H of the PCs
-
-        e2e_step()
-        barrier()
-        s20 = nat2.stats()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        a.record()
-        for _ in range(e2e_steps):
-            pcs = e2e_step()
-        b.record()
-        barrier()
-        wall = time.perf_counter() - t0
-        s21 = nat2.stats()
-        ems = max(a.elapsed_time(b), 0.0)
-        if world > 1:
-            t = torch.tensor([ems], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
-        # same pipeline with the 16-bit index wire format (vpca_accumulate_calls_u16): half the PCIe bytes
-        u16 = None
-        if n <= 65536:
-            idx16 = torch.empty(max(nnz, 1), dtype=torch.uint16, pin_memory=True)
-            idx16.copy_(idx_h.to(torch.uint16))
-            s30 = nat2.stats()
-
-            def e2e_step16():
-                nat2.reset()
-                nat2.accumulateCallsRaw(-1, off_h.data_ptr(), idx16.data_ptr(), vpg, idx_bytes=2)
-                if world > 1:
-                    dist.all_reduce(S2)
-                nat2.finalizeGram()
-                return nat2.computePca(2)
-
-            e2e_step16()
-            barrier()
-            s30 = nat2.stats()
-            a16, b16 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a16.record()
-            for _ in range(e2e_steps):
-                pcs16 = e2e_step16()
-            b16.record()
-            barrier()
-            s31 = nat2.stats()
-            ems16 = a16.elapsed_time(b16)
-            if world > 1:
-                t = torch.tensor([ems16], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ems16 = float(t.item())
-            u16 = {"value": n * vpg * world * e2e_steps / (ems16 * 1e-3), "ms_per_step": ems16 / e2e_steps,
-                   "h2d_bytes_per_step": (s31["h2d_bytes"] - s30["h2d_bytes"]) // e2e_steps,
-                   "pcs_match": bool(np.allclose(pcs16[0], vecs, atol=1e-9))}
-            del idx16
-        # same pipeline fed with one bitmap row per variant (vpca_accumulate_bits): N / 8 bytes per variant on the wire
-        bitleg = None
         try:
-            stride = (n + 7) // 8
-            bits_h = torch.empty((vpg, stride), dtype=torch.uint8, pin_memory=True)
-            wts = (2 ** torch.arange(8, device=dev, dtype=torch.int32))
-            for c0 in range(0, vpg, 50_000):
-                c1 = min(vpg, c0 + 50_000)
-                blk = cells(c0, c1).t().contiguous()                      # (w, n)
-                pad = torch.zeros((blk.shape[0], stride * 8), dtype=torch.int32, device=dev)
-                pad[:, :n] = blk
-                bits_h[c0:c1].copy_((pad.view(-1, stride, 8) * wts).sum(dim=2).to(torch.uint8))
-            torch.cuda.synchronize()
+            off_h, idx_h, nnz = build_host_calls(torch, cells, n, vpg, dev)
+            S2 = torch.zeros((n, n), dtype=torch.int32, device=dev)
+            nat2 = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=S2.data_ptr(),
+                                    max_multiplicity=1)
 
-            def e2e_step_bits():
+            def e2e_step():
                 nat2.reset()
-                nat2.accumulateBitsRaw(-1, bits_h.data_ptr(), vpg, stride)
+                nat2.accumulateCallsRaw(-1, off_h.data_ptr(), idx_h.data_ptr(), vpg)     # H2D + encode + Gram
                 if world > 1:
                     dist.all_reduce(S2)
                 nat2.finalizeGram()
-                return nat2.computePca(2)
+                return nat2.computePca(2)                                                # center + eig + D2H of the PCs
 
-            e2e_step_bits()
+            e2e_step()
             barrier()
-            sb0 = nat2.stats()
-            ab, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ab.record()
+            s20 = nat2.stats()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
             for _ in range(e2e_steps):
-                pcsb = e2e_step_bits()
-            bb.record()
+                pcs = e2e_step()
+            b.record()
             barrier()
-            sb1 = nat2.stats()
-            emsb = ab.elapsed_time(bb)
+            wall = time.perf_counter() - t0
+            s21 = nat2.stats()
+            ems = max(a.elapsed_time(b), 0.0)
             if world > 1:
-                t = torch.tensor([emsb], dtype=torch.float64, device=dev)
+                t = torch.tensor([ems], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                emsb = float(t.item())
-            bitleg = {"value": n * vpg * world * e2e_steps / (emsb * 1e-3), "ms_per_step": emsb / e2e_steps,
-                      "h2d_bytes_per_step": (sb1["h2d_bytes"] - sb0["h2d_bytes"]) // e2e_steps,
-                      "pcs_match": bool(np.allclose(pcsb[0], vecs, atol=1e-9))}
-            del bits_h
-        except Exception as exc:          # never lose the headline line to an auxiliary leg
-            bitleg = {"error": repr(exc)[:200]}
-        e2e = {"value": n * vpg * world * e2e_steps / (ems * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": (s21["h2d_bytes"] - s20["h2d_bytes"]) // e2e_steps,
-               "d2h_bytes_per_step": (s21["d2h_bytes"] - s20["d2h_bytes"]) // e2e_steps,
-               "steps": e2e_steps, "ms_per_step": ems / e2e_steps, "wall_ms_per_step": 1e3 * wall / e2e_steps,
-               "includes": "pinned host CSR rows -> H2D -> encode -> Gram -> centering -> eigensolve -> PCs on host",
-               "nnz": nnz, "pcs_match_resident_path": bool(np.allclose(pcs[0], vecs, atol=1e-9)),
-               "with_uint16_indices": u16, "with_bitmap_rows": bitleg}
-        nat2.close()
+                ems = float(t.item())
+            # same pipeline with the 16-bit index wire format (vpca_accumulate_calls_u16): half the PCIe bytes
+            u16 = None
+            if n <= 65536:
+                idx16 = torch.empty(max(nnz, 1), dtype=torch.uint16, pin_memory=True)
+                idx16.copy_(idx_h.to(torch.uint16))
+                s30 = nat2.stats()
+
+                def e2e_step16():
+                    nat2.reset()
+                    nat2.accumulateCallsRaw(-1, off_h.data_ptr(), idx16.data_ptr(), vpg, idx_bytes=2)
+                    if world > 1:
+                        dist.all_reduce(S2)
+                    nat2.finalizeGram()
+                    return nat2.computePca(2)
+
+                e2e_step16()
+                barrier()
+                s30 = nat2.stats()
+                a16, b16 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a16.record()
+                for _ in range(e2e_steps):
+                    pcs16 = e2e_step16()
+                b16.record()
+                barrier()
+                s31 = nat2.stats()
+                ems16 = a16.elapsed_time(b16)
+                if world > 1:
+                    t = torch.tensor([ems16], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ems16 = float(t.item())
+                u16 = {"value": n * vpg * world * e2e_steps / (ems16 * 1e-3), "ms_per_step": ems16 / e2e_steps,
+                       "h2d_bytes_per_step": (s31["h2d_bytes"] - s30["h2d_bytes"]) // e2e_steps,
+                       "pcs_match": bool(np.allclose(pcs16[0], vecs, atol=1e-9))}
+                del idx16
+            # same pipeline fed with one bitmap row per variant (vpca_accumulate_bits): N / 8 bytes per variant on the wire
+            bitleg = None
+            try:
+                stride = (n + 7) // 8
+                bits_h = torch.empty((vpg, stride), dtype=torch.uint8, pin_memory=True)
+                wts = (2 ** torch.arange(8, device=dev, dtype=torch.int32))
+                for c0 in range(0, vpg, 50_000):
+                    c1 = min(vpg, c0 + 50_000)
+                    blk = cells(c0, c1).t().contiguous()                      # (w, n)
+                    pad = torch.zeros((blk.shape[0], stride * 8), dtype=torch.int32, device=dev)
+                    pad[:, :n] = blk
+                    bits_h[c0:c1].copy_((pad.view(-1, stride, 8) * wts).sum(dim=2).to(torch.uint8))
+                torch.cuda.synchronize()
+
+                def e2e_step_bits():
+                    nat2.reset()
+                    nat2.accumulateBitsRaw(-1, bits_h.data_ptr(), vpg, stride)
+                    if world > 1:
+                        dist.all_reduce(S2)
+                    nat2.finalizeGram()
+                    return nat2.computePca(2)
+
+                e2e_step_bits()
+                barrier()
+                sb0 = nat2.stats()
+                ab, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ab.record()
+                for _ in range(e2e_steps):
+                    pcsb = e2e_step_bits()
+                bb.record()
+                barrier()
+                sb1 = nat2.stats()
+                emsb = ab.elapsed_time(bb)
+                if world > 1:
+                    t = torch.tensor([emsb], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    emsb = float(t.item())
+                bitleg = {"value": n * vpg * world * e2e_steps / (emsb * 1e-3), "ms_per_step": emsb / e2e_steps,
+                          "h2d_bytes_per_step": (sb1["h2d_bytes"] - sb0["h2d_bytes"]) // e2e_steps,
+                          "pcs_match": bool(np.allclose(pcsb[0], vecs, atol=1e-9))}
+                del bits_h
+            except Exception as exc:          # never lose the headline line to an auxiliary leg
+                bitleg = {"error": repr(exc)[:200]}
+            e2e = {"value": n * vpg * world * e2e_steps / (ems * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": (s21["h2d_bytes"] - s20["h2d_bytes"]) // e2e_steps,
+                   "d2h_bytes_per_step": (s21["d2h_bytes"] - s20["d2h_bytes"]) // e2e_steps,
+                   "steps": e2e_steps, "ms_per_step": ems / e2e_steps, "wall_ms_per_step": 1e3 * wall / e2e_steps,
+                   "includes": "pinned host CSR rows -> H2D -> encode -> Gram -> centering -> eigensolve -> PCs on host",
+                   "nnz": nnz, "pcs_match_resident_path": bool(np.allclose(pcs[0], vecs, atol=1e-9)),
+                   "with_uint16_indices": u16, "with_bitmap_rows": bitleg}
+            nat2.close()
+        except Exception as exc:      # an auxiliary leg must never cost the headline line
+            e2e = {"error": repr(exc)[:300]}
 
     # ---- comparison leg: the same cohort stored as packed 4-bit e2m1 cells (exact; half the bytes per cell) ----
     alt = None
