@@ -398,13 +398,16 @@ def run_b200(args):
             c1 = min(vpg, c0 + 100_000)
             s1 += cells(c0, c1).to(torch.float64) @ colsum[c0:c1]
         checks["S_times_ones_equals_X_Xt1"] = bool(torch.equal(S.sum(dim=1).to(torch.float64), s1))
-    nat.computePca(2)                      # first call builds the CUDA graph of the tridiagonalisation loop (one-off)
+    nat.computePca(2)                      # first call builds the CUDA graphs of the eigensolver's step loops (one-off)
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record()
     vecs, evals, nz = nat.computePca(2)
     ee1.record()
     ee1.synchronize()
     eig_ms = ee0.elapsed_time(ee1)
+    _st = nat.stats()
+    eig_info = {"method": {1: "direct", 2: "lanczos", 3: "lanczos->direct"}.get(_st["eig_method"], "?"),
+                "lanczos_steps": _st["eig_iterations"]}
     if not args.no_eig_check and rank == 0:
         Sd = S.to(torch.float64)
         rs = Sd.sum(dim=1)
@@ -600,7 +603,7 @@ def run_b200(args):
                                   else ("nccl all-reduce" if world > 1 else "none (1 GPU)")),
                        "l2_policy": f"input ({n * vpg * eb / 1e9:.2f} GB per rank) larger than L2; no flush between iterations"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
-            "eig_ms": eig_ms, "checks": checks,
+            "eig_ms": eig_ms, "eig": eig_info, "checks": checks,
         }
         if alt is not None:
             line["packed_e2m1"] = alt

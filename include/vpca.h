@@ -201,6 +201,8 @@ typedef struct vpca_stats {
     float last_eig_ms;            /* device time of the most recent centering + eigensolve                */
     int32_t gram_cta_group;       /* 1 or 2: tcgen05 cta_group used                                       */
     int32_t gram_resident;        /* 1 when the last launch kept accumulators in TMEM for the whole K loop */
+    int32_t eig_method;           /* last vpca_compute_pca: 1 direct reduction, 2 Lanczos, 3 Lanczos abandoned -> direct */
+    int32_t eig_iterations;       /* Lanczos steps taken by the last vpca_compute_pca (0 for a direct solve)  */
 } vpca_stats;
 int vpca_get_stats(vpca_ctx* ctx, vpca_stats* out);
 /* Diagnostic (set VPCA_GRAM_PROF=1 before the first Gram launch): per-CTA timestamps of the last Gram launch,

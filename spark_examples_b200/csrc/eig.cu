@@ -561,25 +561,13 @@ __global__ void __launch_bounds__(256) invit_kernel(const double* __restrict__ d
     }
 }
 
-// ----------------------------------------------------------------------------- back-transformation
-// z = H_0 H_1 ... H_{n-2} y, H_j = I - tau_j v_j v_j^T with v_j in row j of A at [j+1, n).  One block per eigenvector.
-__global__ void __launch_bounds__(512) backtransform_kernel(const double* __restrict__ A, int n,
-                                                            const double* __restrict__ tau, double* __restrict__ Y) {
+// Unit 2-norm, then the sign rule: the largest-|.| entry (lowest index on ties) is positive.  Whole block, y of length n.
+__device__ void normalise_and_orient(double* __restrict__ y, int n) {
     __shared__ double red[33];
     __shared__ int arg;
-    double* y = Y + (size_t)blockIdx.x * n;
+    __shared__ double bv[32];
+    __shared__ int bi[32];
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int j = n - 2; j >= 0; --j) {
-        const double tj = tau[j];
-        if (tj == 0.0) continue;
-        const double* v = A + (size_t)j * n;
-        double acc = 0.0;
-        for (int t = j + 1 + tid; t < n; t += nt) acc += v[t] * y[t];
-        const double s = tj * block_sum(acc, red);
-        for (int t = j + 1 + tid; t < n; t += nt) y[t] -= s * v[t];
-        __syncthreads();
-    }
-    // unit 2-norm, then the sign rule: the largest-|.| entry (lowest index on ties) is positive
     double acc = 0.0;
     for (int t = tid; t < n; t += nt) acc += y[t] * y[t];
     const double inv = 1.0 / sqrt(block_sum(acc, red));
@@ -593,8 +581,6 @@ __global__ void __launch_bounds__(512) backtransform_kernel(const double* __rest
         }
     }
     // block arg-max (value, then lowest index)
-    __shared__ double bv[16];
-    __shared__ int bi[16];
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
@@ -622,6 +608,226 @@ __global__ void __launch_bounds__(512) backtransform_kernel(const double* __rest
     const double sgn = (y[arg] < 0.0) ? -inv : inv;
     __syncthreads();
     for (int t = tid; t < n; t += nt) y[t] *= sgn;
+}
+
+// ----------------------------------------------------------------------------- back-transformation
+// z = H_0 H_1 ... H_{n-2} y, H_j = I - tau_j v_j v_j^T with v_j in row j of A at [j+1, n).  One block per eigenvector.
+__global__ void __launch_bounds__(512) backtransform_kernel(const double* __restrict__ A, int n,
+                                                            const double* __restrict__ tau, double* __restrict__ Y) {
+    __shared__ double red[33];
+    double* y = Y + (size_t)blockIdx.x * n;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = n - 2; j >= 0; --j) {
+        const double tj = tau[j];
+        if (tj == 0.0) continue;
+        const double* v = A + (size_t)j * n;
+        double acc = 0.0;
+        for (int t = j + 1 + tid; t < n; t += nt) acc += v[t] * y[t];
+        const double s = tj * block_sum(acc, red);
+        for (int t = j + 1 + tid; t < n; t += nt) y[t] -= s * v[t];
+        __syncthreads();
+    }
+    normalise_and_orient(y, n);
+}
+
+// ------------------------------------------------- Lanczos: the top-k eigenpairs without tridiagonalising C
+// For N >= kLzMinN the k largest eigenpairs come from a Krylov space instead of the full reduction: m steps of
+// symmetric Lanczos with full (twice-applied classical Gram-Schmidt) reorthogonalisation build an orthonormal
+// V (N x m) and a small tridiagonal T_m = V^T C V; its top-k eigenpairs (same bisection + inverse iteration as
+// above, on m instead of N) give Ritz values theta and vectors z = V y whose residual is |beta_m y_m|.  One step
+// costs one pass over C (50 MB from L2 at N = 2504) instead of the N steps the reduction needs, and population
+// structure separates the top of the spectrum, so a few dozen steps reach |beta_m y_m| <= 1e-12 ||T||.
+// Five launches per step (matvec | V^T w | w -= V h | V^T w | w -= V h), step index and stop flag in device
+// memory so that kLzChunk steps replay from one CUDA graph; the host looks at the residual once per chunk.
+// Anything unusual -- breakdown, slow convergence, a larger eigenvalue found by the deflated re-run that guards
+// against a missed copy of a multiple eigenvalue -- falls back to the direct reduction, which remains the
+// reference-grade path.  Every reduction has a fixed order: the result is run-to-run deterministic.
+constexpr int kLzMinN = 512;         // below this the direct reduction is as fast
+constexpr int kLzForcedMinN = 96;    // VPCA_EIG=lanczos: smallest n the chunked loop supports (tests)
+constexpr int kLzChunk = 32;      // steps per graph replay / convergence check
+constexpr int kLzMaxIter = 320;   // give up (-> direct solver) beyond this
+constexpr int kLzCap = kLzMaxIter + 64;   // columns of V: main run, or k locked vectors + one verification chunk
+// st[0] = step j, st[1] = flag (0 run, 1 converged, 2 breakdown, 3 missed eigenvalue), st[2] = ticket, st[3] = step cap
+
+__device__ __forceinline__ double lz_uniform(unsigned long long i, unsigned long long salt) {
+    unsigned long long z = (i + 1) * 0x9E3779B97F4A7C15ull + salt;   // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+// <<<ceil(n/32), 32>>>: start vector (not yet normalised) and the per-block partial sums of its squared norm
+__global__ void lz_init_kernel(double* __restrict__ w, int n, unsigned long long salt, double* __restrict__ part) {
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    double v = 0.0;
+    if (i < n) {
+        v = lz_uniform((unsigned long long)i, salt);
+        w[i] = v;
+    }
+    const double s = warp_sum(v * v);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+// Step j, phase 1: beta_j = ||w_in|| (from the partial sums), v_j = w_in / beta_j -> V[:, j], w_out = C v_j.
+// 4 rows per 256-thread block, two warps per row, 8 independent loads in flight per lane.
+__global__ void __launch_bounds__(256) lz_matvec_kernel(const double* __restrict__ C, int n, double* __restrict__ V,
+                                                        double* __restrict__ wbuf, const double* __restrict__ part,
+                                                        int npart, double* __restrict__ beta, int* __restrict__ st) {
+    __shared__ double half[8];
+    const int j = st[0];
+    if (st[1] != 0 || j >= st[3]) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double s = 0.0;
+    for (int p = lane; p < npart; p += 32) s += part[p];
+    s = warp_sum(s);
+    const double nrm = sqrt(s);
+    if (!(nrm > 0.0) || !(nrm <= DBL_MAX)) {   // exact breakdown or non-finite: every block sees the same value
+        if (blockIdx.x == 0 && threadIdx.x == 0) st[1] = 2;
+        return;
+    }
+    const double inv = 1.0 / nrm;
+    const double* __restrict__ win = wbuf + (size_t)(j & 1) * n;
+    double* __restrict__ wout = wbuf + (size_t)((j + 1) & 1) * n;
+    const int row = blockIdx.x * 4 + (wid >> 1);
+    double acc = 0.0;
+    if (row < n) {
+        const double* __restrict__ c = C + (size_t)row * n;
+        double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int t0 = (wid & 1) * 32 + lane; t0 < n; t0 += 8 * 64) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {   // predicated, so the 8 loads of the ragged last round still issue together
+                const int t = t0 + u * 64;
+                if (t < n) a[u] += c[t] * win[t];
+            }
+        }
+        acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) half[wid] = acc;
+    __syncthreads();
+    if (row < n && (wid & 1) == 0 && lane == 0) {
+        wout[row] = (half[wid] + half[wid + 1]) * inv;
+        V[(size_t)j * n + row] = win[row] * inv;
+        if (row == 0) beta[j] = nrm;
+    }
+}
+
+// Phases 2 and 4: h[q] = V[:, q] . w for q <= j.  One block per column (blocks beyond j return).
+__global__ void __launch_bounds__(128) lz_dots_kernel(const double* __restrict__ V, int n,
+                                                      const double* __restrict__ wbuf, double* __restrict__ h,
+                                                      const int* __restrict__ st) {
+    __shared__ double red[33];
+    const int j = st[0];
+    if (st[1] != 0 || j >= st[3]) return;
+    const int q = blockIdx.x;
+    if (q > j) return;
+    const double* __restrict__ w = wbuf + (size_t)((j + 1) & 1) * n;
+    const double* __restrict__ v = V + (size_t)q * n;
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t0 = threadIdx.x; t0 < n; t0 += 4 * 128) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * 128;
+            if (t < n) a[u] += v[t] * w[t];
+        }
+    }
+    const double sum = block_sum((a[0] + a[1]) + (a[2] + a[3]), red);
+    if (threadIdx.x == 0) h[q] = sum;
+}
+
+// Phases 3 and 5: w -= V[:, 0..j] h.  32 rows per block, the columns split over the 8 warps.  The second pass also
+// leaves the partial sums of ||w||^2 for the next step and, through a ticket, advances the step counter once every
+// block has read it.  alpha_j = h_j (first pass) + its correction (second pass).
+__global__ void __launch_bounds__(256) lz_update_kernel(const double* __restrict__ V, int n, double* __restrict__ wbuf,
+                                                        const double* __restrict__ h, double* __restrict__ alpha,
+                                                        double* __restrict__ part, int* __restrict__ st, int pass) {
+    __shared__ double sm[8][33];
+    const int j = st[0];
+    if (st[1] != 0 || j >= st[3]) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int row = blockIdx.x * 32 + lane;
+    double* __restrict__ w = wbuf + (size_t)((j + 1) & 1) * n;
+    double acc = 0.0;
+    if (row < n) {
+#pragma unroll 4
+        for (int q = wid; q <= j; q += 8) acc += V[(size_t)q * n + row] * h[q];
+    }
+    sm[wid][lane] = acc;
+    __syncthreads();
+    if (wid == 0) {
+        const double tot = ((sm[0][lane] + sm[1][lane]) + (sm[2][lane] + sm[3][lane])) +
+                           ((sm[4][lane] + sm[5][lane]) + (sm[6][lane] + sm[7][lane]));
+        double nw = 0.0;
+        if (row < n) {
+            nw = w[row] - tot;
+            w[row] = nw;
+        }
+        if (pass == 2) {
+            const double s2 = warp_sum(nw * nw);
+            if (lane == 0) part[blockIdx.x] = s2;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) alpha[j] = (pass == 1) ? h[j] : alpha[j] + h[j];
+    if (pass == 2 && threadIdx.x == 0) {
+        if (atomicAdd(st + 2, 1) == (int)gridDim.x - 1) {
+            st[2] = 0;
+            st[0] = j + 1;
+        }
+    }
+}
+
+// One warp.  res[0] = max_c |beta_m Y[m-1, c]| / ||T||, res[1] = beta_m; flags convergence (or NaN -> breakdown).
+__global__ void lz_check_kernel(const double* __restrict__ part, int npart, const double* __restrict__ Y, int m, int k,
+                                const double* __restrict__ scal, int* __restrict__ st, double* __restrict__ res,
+                                double tol) {
+    const int lane = threadIdx.x;
+    double s = 0.0;
+    for (int p = lane; p < npart; p += 32) s += part[p];
+    s = warp_sum(s);
+    if (lane != 0) return;
+    const double nrm = sqrt(s);
+    const double tnorm = fmax(scal[2], DBL_MIN);
+    double r = 0.0;
+    for (int c = 0; c < k; ++c) r = fmax(r, fabs(Y[(size_t)c * m + (m - 1)]));
+    const double rho = nrm * r / tnorm;
+    res[0] = rho;
+    res[1] = nrm;
+    if (st[1] == 0) {
+        if (!(rho == rho) || !(rho <= DBL_MAX)) st[1] = 2;
+        else if (rho <= tol) st[1] = 1;
+    }
+}
+
+// Z[:, c] = V[:, 0..m) Y[:, c]; grid (ceil(n/32), k), 32 rows per block, the columns split over the 8 warps.
+__global__ void __launch_bounds__(256) lz_ritz_kernel(const double* __restrict__ V, int n, const double* __restrict__ Y,
+                                                      int m, double* __restrict__ Z) {
+    __shared__ double sm[8][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int row = blockIdx.x * 32 + lane;
+    const double* __restrict__ y = Y + (size_t)blockIdx.y * m;
+    double acc = 0.0;
+    if (row < n) {
+#pragma unroll 4
+        for (int q = wid; q < m; q += 8) acc += V[(size_t)q * n + row] * y[q];
+    }
+    sm[wid][lane] = acc;
+    __syncthreads();
+    if (wid == 0 && row < n)
+        Z[(size_t)blockIdx.y * n + row] = ((sm[0][lane] + sm[1][lane]) + (sm[2][lane] + sm[3][lane])) +
+                                          ((sm[4][lane] + sm[5][lane]) + (sm[6][lane] + sm[7][lane]));
+}
+
+__global__ void __launch_bounds__(512) lz_finish_kernel(double* __restrict__ Z, int n) {
+    normalise_and_orient(Z + (size_t)blockIdx.x * n, n);
+}
+
+// One thread: the deflated re-run found a Ritz value above theta_k -> an eigenvalue was missed.
+__global__ void lz_verify_kernel(const double* __restrict__ theta, int k, const double* __restrict__ theta2,
+                                 const double* __restrict__ scal, int* __restrict__ st) {
+    const double tnorm = fmax(scal[2], DBL_MIN);
+    if (st[1] == 2) return;
+    st[1] = (theta2[0] > theta[k - 1] + 1e-9 * tnorm) ? 3 : 1;
 }
 
 }  // namespace
@@ -653,7 +859,9 @@ void eig_free(EigWork& w) {
     cudaFree(w.d_C); cudaFree(w.d_rowsum); cudaFree(w.d_v); cudaFree(w.d_w); cudaFree(w.d_p);
     cudaFree(w.d_diag); cudaFree(w.d_off); cudaFree(w.d_tau); cudaFree(w.d_scal); cudaFree(w.d_evals);
     cudaFree(w.d_evecs); cudaFree(w.d_lu); cudaFree(w.d_nz); cudaFree(w.d_step);
+    cudaFree(w.d_V); cudaFree(w.d_lzw); cudaFree(w.d_lzs); cudaFree(w.d_lzst);
     if (w.graph_exec != nullptr) cudaGraphExecDestroy(w.graph_exec);
+    if (w.lz_graph != nullptr) cudaGraphExecDestroy(w.lz_graph);
     w = EigWork{};
 }
 
@@ -666,9 +874,140 @@ cudaError_t center_gram(EigWork& w, const int32_t* d_S, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// Top-k by Lanczos.  *used = true: d_evals / d_evecs hold the answer.  *used = false: the caller runs the direct
+// solver (C is untouched).  Synchronises the stream once per kLzChunk steps to read the residual.
+static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches, bool* used) {
+    *used = false;
+    const int n = w.n;
+    const int npart = (n + 31) / 32;
+    const int kmax = w.kmax;
+    cudaError_t e;
+#define VPCA_TRY(x) if ((e = (x)) != cudaSuccess) return e
+    const size_t small_doubles = 5 * (size_t)kLzCap + (size_t)kLzCap * kmax + 16 + 4 + 16 + (size_t)npart;
+    if (w.d_V == nullptr) {
+        VPCA_TRY(cudaMalloc(&w.d_V, (size_t)n * kLzCap * sizeof(double)));
+        VPCA_TRY(cudaMalloc(&w.d_lzw, 2 * (size_t)n * sizeof(double)));
+        VPCA_TRY(cudaMalloc(&w.d_lzs, small_doubles * sizeof(double)));
+        VPCA_TRY(cudaMalloc(&w.d_lzst, 4 * sizeof(int)));
+    }
+    double* alpha = w.d_lzs;
+    double* beta = alpha + kLzCap;
+    double* h1 = beta + kLzCap;
+    double* h2 = h1 + kLzCap;
+    double* e2 = h2 + kLzCap;
+    double* Y = e2 + kLzCap;
+    double* theta2 = Y + (size_t)kLzCap * kmax;
+    double* res = theta2 + 16;
+    double* scal2 = res + 4;
+    double* part = scal2 + 16;
+    int64_t nl = 0;
+    const int upd_blocks = npart, mv_blocks = (n + 3) / 4;
+
+    if (w.lz_graph == nullptr) {
+        cudaGraph_t graph = nullptr;
+        VPCA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        for (int g = 0; g < kLzChunk; ++g) {
+            lz_matvec_kernel<<<mv_blocks, 256, 0, stream>>>(w.d_C, n, w.d_V, w.d_lzw, part, npart, beta, w.d_lzst);
+            lz_dots_kernel<<<kLzCap, 128, 0, stream>>>(w.d_V, n, w.d_lzw, h1, w.d_lzst);
+            lz_update_kernel<<<upd_blocks, 256, 0, stream>>>(w.d_V, n, w.d_lzw, h1, alpha, part, w.d_lzst, 1);
+            lz_dots_kernel<<<kLzCap, 128, 0, stream>>>(w.d_V, n, w.d_lzw, h2, w.d_lzst);
+            lz_update_kernel<<<upd_blocks, 256, 0, stream>>>(w.d_V, n, w.d_lzw, h2, alpha, part, w.d_lzst, 2);
+        }
+        VPCA_TRY(cudaStreamEndCapture(stream, &graph));
+        e = cudaGraphInstantiate(&w.lz_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return e;
+    }
+    VPCA_TRY(cudaFuncSetAttribute(invit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+
+    const double tol = 1e-12;
+    int max_iter = kLzMaxIter;
+    if (const char* mi = getenv("VPCA_EIG_MAXIT")) max_iter = std::max(kLzChunk, std::min(kLzMaxIter, atoi(mi)));
+    int hst[4] = {0, 0, 0, max_iter};
+    double hres[2] = {0.0, 0.0};
+    VPCA_TRY(cudaMemcpyAsync(w.d_lzst, hst, sizeof(hst), cudaMemcpyHostToDevice, stream));
+    lz_init_kernel<<<npart, 32, 0, stream>>>(w.d_lzw, n, 0x5eedULL, part);
+    nl += 1;
+    int m = 0;
+    bool converged = false;
+    double rho_prev = 0.0;
+    for (int chunk = 1; chunk * kLzChunk <= std::min(max_iter, n - 1); ++chunk) {
+        VPCA_TRY(cudaGraphLaunch(w.lz_graph, stream));
+        m = chunk * kLzChunk;
+        bisect_kernel<<<k, 256, 0, stream>>>(alpha, beta + 1, m, e2, w.d_evals, w.d_scal);
+        invit_kernel<true><<<1, 256, 8 * (size_t)m * sizeof(double), stream>>>(alpha, beta + 1, m, k, w.d_evals, w.d_scal,
+                                                                                w.d_lu, Y);
+        lz_check_kernel<<<1, 32, 0, stream>>>(part, npart, Y, m, k, w.d_scal, w.d_lzst, res, tol);
+        nl += 5 * kLzChunk + 3;
+        VPCA_TRY(cudaMemcpyAsync(hst, w.d_lzst, sizeof(hst), cudaMemcpyDeviceToHost, stream));
+        VPCA_TRY(cudaMemcpyAsync(hres, res, sizeof(hres), cudaMemcpyDeviceToHost, stream));
+        VPCA_TRY(cudaStreamSynchronize(stream));
+        if (hst[1] == 1) {
+            converged = true;
+            break;
+        }
+        if (hst[1] != 0) break;   // breakdown
+        const double rho = hres[0];
+        if (chunk >= 3 && rho > 1e-3) break;   // no separated top of the spectrum: hopeless within kLzMaxIter
+        if (chunk >= 2 && rho < rho_prev) {
+            const double rate = std::log(rho_prev / rho) / kLzChunk;
+            if (m + 1.5 * std::log(rho / tol) / rate > max_iter + kLzChunk) break;
+        }
+        rho_prev = rho;
+    }
+    w.last_iters = m;
+    if (launches) *launches += nl;
+    if (!converged) return cudaGetLastError();
+    nl = 0;
+
+    // Ritz vectors, unit norm, sign rule
+    lz_ritz_kernel<<<dim3(npart, k), 256, 0, stream>>>(w.d_V, n, Y, m, w.d_evecs);
+    lz_finish_kernel<<<k, 512, 0, stream>>>(w.d_evecs, n);
+    nl += 2;
+
+    // Guard against a missed copy of a multiple eigenvalue (a single Krylov sequence sees one vector per eigenspace):
+    // lock the k Ritz vectors as the first k basis columns and run one more chunk from a fresh start vector that is
+    // orthogonal to them.  Its top Ritz value is a lower bound of the largest eigenvalue of the deflated operator.
+    if (k + kLzChunk < n) {
+        VPCA_TRY(cudaMemcpyAsync(w.d_V, w.d_evecs, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        int vst[4] = {k - 1, 0, 0, k + kLzChunk};
+        VPCA_TRY(cudaMemcpyAsync(w.d_lzst, vst, sizeof(vst), cudaMemcpyHostToDevice, stream));
+        lz_init_kernel<<<npart, 32, 0, stream>>>(w.d_lzw + (size_t)(k & 1) * n, n, 0xfaceULL, part);
+        lz_dots_kernel<<<kLzCap, 128, 0, stream>>>(w.d_V, n, w.d_lzw, h1, w.d_lzst);
+        lz_update_kernel<<<upd_blocks, 256, 0, stream>>>(w.d_V, n, w.d_lzw, h1, alpha, part, w.d_lzst, 1);
+        lz_dots_kernel<<<kLzCap, 128, 0, stream>>>(w.d_V, n, w.d_lzw, h2, w.d_lzst);
+        lz_update_kernel<<<upd_blocks, 256, 0, stream>>>(w.d_V, n, w.d_lzw, h2, alpha, part, w.d_lzst, 2);
+        VPCA_TRY(cudaGraphLaunch(w.lz_graph, stream));
+        bisect_kernel<<<1, 256, 0, stream>>>(alpha + k, beta + k + 1, kLzChunk, e2, theta2, scal2);
+        lz_verify_kernel<<<1, 1, 0, stream>>>(w.d_evals, k, theta2, w.d_scal, w.d_lzst);
+        nl += 5 + 5 * kLzChunk + 2;
+        VPCA_TRY(cudaMemcpyAsync(hst, w.d_lzst, sizeof(hst), cudaMemcpyDeviceToHost, stream));
+        VPCA_TRY(cudaStreamSynchronize(stream));
+        if (launches) *launches += nl;
+        if (hst[1] != 1) return cudaGetLastError();
+    } else if (launches) {
+        *launches += nl;
+    }
+#undef VPCA_TRY
+    *used = true;
+    return cudaGetLastError();
+}
+
 cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) {
     const int n = w.n;
     if (k < 1 || k > w.kmax || k > n) return cudaErrorInvalidValue;
+    w.last_method = 1;
+    w.last_iters = 0;
+    if (w.mode != 1 && n >= (w.mode == 2 ? kLzForcedMinN : kLzMinN)) {
+        bool used = false;
+        cudaError_t le = lanczos_topk(w, k, stream, launches, &used);
+        if (le != cudaSuccess) return le;
+        if (used) {
+            w.last_method = 2;
+            return cudaSuccess;
+        }
+        w.last_method = 3;
+    }
     cudaError_t e = cudaMemsetAsync(w.d_v, 0, 2 * (size_t)n * sizeof(double), stream);
     if (e != cudaSuccess) return e;
     cudaMemsetAsync(w.d_w, 0, (size_t)n * sizeof(double), stream);

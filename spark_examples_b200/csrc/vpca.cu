@@ -702,8 +702,14 @@ int vpca_compute_pca(vpca_ctx* ctx, int32_t k, double* vecs, double* evals, int3
     CUDA_OK(ctx, cudaEventRecord(ctx->ev_e0, ctx->stream));
     int rc = run_center(ctx);
     if (rc != VPCA_OK) return rc;
+    {   // VPCA_EIG=direct|lanczos|auto (default auto: Lanczos from 512 samples up, direct reduction as its fallback)
+        const char* em = getenv("VPCA_EIG");
+        ctx->eig.mode = (em != nullptr && strcmp(em, "direct") == 0) ? 1 : (em != nullptr && strcmp(em, "lanczos") == 0) ? 2 : 0;
+    }
     CUDA_OK(ctx, eig_topk(ctx->eig, k, ctx->stream, &ctx->st.kernel_launches));
     CUDA_OK(ctx, cudaEventRecord(ctx->ev_e1, ctx->stream));
+    ctx->st.eig_method = ctx->eig.last_method;
+    ctx->st.eig_iterations = ctx->eig.last_iters;
     ctx->eig_timed = true;
     const size_t nb = (size_t)ctx->n * k * sizeof(double);
     CUDA_OK(ctx, cudaMemcpyAsync(vecs, ctx->eig.d_evecs, nb, cudaMemcpyDeviceToHost, ctx->stream));
@@ -736,6 +742,8 @@ int vpca_get_tridiagonal(vpca_ctx* ctx, double* diag, double* offdiag) {
     if (ctx == nullptr || diag == nullptr || offdiag == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->pca_done) return fail(ctx, VPCA_ERR_STATE, "call vpca_compute_pca first");
+    if (ctx->eig.last_method == 2)
+        return fail(ctx, VPCA_ERR_STATE, "the last solve used Lanczos and did not tridiagonalise C (set VPCA_EIG=direct)");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     CUDA_OK(ctx, cudaMemcpyAsync(diag, ctx->eig.d_diag, (size_t)ctx->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(ctx, cudaMemcpyAsync(offdiag, ctx->eig.d_off, (size_t)(ctx->n - 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -89,6 +89,15 @@ struct EigWork {
     int graph_n = 0;
     bool graph_fused = false;
     int kmax = 0;
+    // Lanczos workspace (allocated on the first Lanczos solve)
+    double* d_V = nullptr;      // n x kLzCap orthonormal basis, column-major
+    double* d_lzw = nullptr;    // 2 n: w ping-pong
+    double* d_lzs = nullptr;    // alpha | beta | h | h2 | e2 | Y | theta2 | res | scal2 | part
+    int* d_lzst = nullptr;      // {step, flag, ticket, step cap}
+    cudaGraphExec_t lz_graph = nullptr;   // kLzChunk Lanczos steps
+    int last_method = 0;        // 1 direct, 2 Lanczos, 3 Lanczos abandoned -> direct
+    int last_iters = 0;         // Lanczos steps of the last solve
+    int mode = 0;               // 0 auto, 1 direct, 2 Lanczos whenever n allows
 };
 cudaError_t eig_alloc(EigWork& w, int n, int kmax);
 void eig_free(EigWork& w);

@@ -85,6 +85,8 @@ class VpcaStats(ctypes.Structure):
         ("last_eig_ms", ctypes.c_float),
         ("gram_cta_group", ctypes.c_int32),
         ("gram_resident", ctypes.c_int32),
+        ("eig_method", ctypes.c_int32),
+        ("eig_iterations", ctypes.c_int32),
     ]
 
 

@@ -44,7 +44,7 @@ def test_struct_layout_matches_header(lib):
     from spark_examples_b200 import native
     assert ctypes.sizeof(native.VpcaConfig) == 64
     assert native.VpcaConfig.stream.offset == 48 and native.VpcaConfig.d_gram.offset == 56
-    assert ctypes.sizeof(native.VpcaStats) == 56
+    assert ctypes.sizeof(native.VpcaStats) == 64
     assert lib.vpca_version() == 1
 
 
