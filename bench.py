@@ -398,6 +398,9 @@ def run_b200(args):
             c1 = min(vpg, c0 + 100_000)
             s1 += cells(c0, c1).to(torch.float64) @ colsum[c0:c1]
         checks["S_times_ones_equals_X_Xt1"] = bool(torch.equal(S.sum(dim=1).to(torch.float64), s1))
+    if n > 65535:
+        raise SystemExit("bench.py times Gram + eigensolve; vpca_compute_pca (like MLlib's RowMatrix) stops at 65535 "
+                         "samples -- use tools/large_n_shard.py for the Gram alone at biobank-scale N")
     nat.computePca(2)                      # first call builds the CUDA graphs of the eigensolver's step loops (one-off)
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record()
