@@ -51,9 +51,10 @@ def parse_args():
     ap.add_argument("--no-alt", action="store_true", help="skip the packed-e2m1 comparison leg")
     ap.add_argument("--panel-variants", type=int, default=int(os.environ.get("VPCA_BENCH_PANEL", "8192")),
                     help="resident cohort layout: panels of this many variants (vpca_accumulate_panels); 0 = row-major")
-    ap.add_argument("--reduce", choices=["nccl", "fused"], default=os.environ.get("VPCA_BENCH_REDUCE", "nccl"),
+    ap.add_argument("--reduce", choices=["nccl", "fused", "scatter"], default=os.environ.get("VPCA_BENCH_REDUCE", "nccl"),
                     help="N > 1: 'nccl' = one all-reduce after the Gram kernel; 'fused' = the Gram epilogue adds into every "
-                         "rank's Gram over NVLink peer memory (vpca_gram_set_peers)")
+                         "rank's Gram over NVLink peer memory (vpca_gram_set_peers); 'scatter' = the epilogue adds into the "
+                         "Gram of the rank that owns the row band, then every rank pulls the other bands (vpca_gram_gather)")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 5); 0 disables the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eig-check", action="store_true")
@@ -253,14 +254,15 @@ def run_b200(args):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    fused = world > 1 and args.reduce == "fused"
+    fused = world > 1 and args.reduce in ("fused", "scatter")
+    scatter = world > 1 and args.reduce == "scatter"
     S = torch.zeros((n, n), dtype=torch.int32, device=dev)
     nat = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=0 if fused else S.data_ptr(),
                            max_multiplicity=1)
     if fused:
         handles = [None] * world
         dist.all_gather_object(handles, nat.exportIpcHandle())
-        nat.setPeers(handles, rank)
+        nat.setPeers(handles, rank, mode="owner_rows" if scatter else "replicate")
     P = args.panel_variants
     if P > 0:
         npan = (vpg + P - 1) // P
@@ -282,8 +284,8 @@ def run_b200(args):
         nat.reset()
         if fused:
             nat.peerBarrier()                  # every rank's Gram is zeroed before anyone adds into it
-            gram_launch(nat, X)                # epilogue reds go to all ranks' Grams over NVLink
-            nat.peerBarrier()                  # all contributions have landed
+            gram_launch(nat, X)                # epilogue reds go to all ranks' Grams (or the row's owner) over NVLink
+            nat.gatherGram()                   # all contributions have landed (+ pull the other ranks' row bands)
         else:
             gram_launch(nat, X)
             if world > 1:
@@ -318,16 +320,23 @@ def run_b200(args):
     launches = st1["kernel_launches"] - st0["kernel_launches"]
 
     # ---- Gram kernel alone (roofline numerator / denominator) ----
-    kt = []
+    kt, gt = [], []
     for _ in range(max(5, min(args.steps, 20))):
         nat.reset()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if fused:
+            nat.peerBarrier()                  # same protocol as step(): nobody adds into a Gram that is being zeroed
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record()
         gram_launch(nat, X)
         b.record()
-        b.synchronize()
+        if fused:
+            nat.gatherGram()
+        c.record()
+        c.synchronize()
         kt.append(a.elapsed_time(b))
+        gt.append(b.elapsed_time(c))
     kernel_ms = sum(kt) / len(kt)
+    fused_close_ms = sum(gt) / len(gt) if fused else None      # closing barrier(s) + gather, incl. waiting for the slowest peer
     ops = float(n) * (n + 1) * vpg                       # SYRK-minimal ops per launch
     achieved_tops = ops / (kernel_ms * 1e-3) / 1e12
     mxf4 = args.dtype == "e2m1" and os.environ.get("VPCA_E2M1_MXF4", "1") != "0"
@@ -602,11 +611,13 @@ def run_b200(args):
                        "samples": n, "variants_per_gpu": vpg, "parallelism": f"variant-sharded x{world}",
                        "hbm_layout": (f"panels of {P} variants x {n} samples (vpca_accumulate_panels)" if P > 0
                                       else "row-major samples x variants"),
-                       "reduce": ("fused: Gram epilogue red.add into every rank's Gram over NVLink peer memory" if fused
+                       "reduce": ("fused reduce-scatter: Gram epilogue red.add into the owner of each Gram row band over NVLink peer "
+                                  "memory, then a peer-load all-gather" if scatter else
+                                  "fused: Gram epilogue red.add into every rank's Gram over NVLink peer memory" if fused
                                   else ("nccl all-reduce" if world > 1 else "none (1 GPU)")),
                        "l2_policy": f"input ({n * vpg * eb / 1e9:.2f} GB per rank) larger than L2; no flush between iterations"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
-            "eig_ms": eig_ms, "eig": eig_info, "checks": checks,
+            "eig_ms": eig_ms, "eig": eig_info, "checks": checks, "fused_close_ms": fused_close_ms,
         }
         if alt is not None:
             line["packed_e2m1"] = alt

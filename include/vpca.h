@@ -151,6 +151,17 @@ int vpca_gram_device_ptr(vpca_ctx* ctx, void** d_gram);
 int vpca_gram_export_ipc(vpca_ctx* ctx, void* handle64);
 int vpca_gram_set_peers(vpca_ctx* ctx, const void* handles, int32_t world, int32_t rank);
 int vpca_peer_barrier(vpca_ctx* ctx);
+/* How the fused epilogue reduces across the peers set above:
+ *   VPCA_PEER_REPLICATE (default): every flush goes into the Gram of every rank -- world x the remote traffic, no
+ *     second phase.  Best at 2 GPUs.
+ *   VPCA_PEER_OWNER_ROWS: reduce-scatter + all-gather.  Rank q owns a band of Gram rows (equal shares of the lower
+ *     triangle, boundaries on multiples of 32); a flush goes only to the owner of its row, and vpca_gram_gather()
+ *     (barrier, pull the rows owned by the other ranks over NVLink, barrier) completes every rank's copy.
+ *     Protocol per pass:  vpca_reset -> vpca_peer_barrier -> accumulate ... (commit) -> vpca_gram_gather ->
+ *     vpca_finalize_gram.  vpca_gram_gather() is valid in both modes (REPLICATE: just the closing barrier). */
+enum { VPCA_PEER_REPLICATE = 0, VPCA_PEER_OWNER_ROWS = 1 };
+int vpca_gram_set_peer_mode(vpca_ctx* ctx, int32_t mode);
+int vpca_gram_gather(vpca_ctx* ctx);
 
 /* Mirror the lower triangle into the upper one: after this the buffer equals the reference's
  * similarity matrix with all N^2 entries present (:189-190). */

@@ -24,6 +24,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -63,8 +65,10 @@ constexpr int kMaxPeers = 16;
 
 struct GramArgs {
     int32_t* S;
-    int32_t* peer[kMaxPeers];   // num_peers > 0: every flush is added into ALL of these Grams (own included) over NVLink
-    int num_peers;
+    int32_t* peer[kMaxPeers];   // num_peers > 0: the flush goes to peer-mapped Grams (own included) over NVLink:
+    int num_peers;              //   peer_mode 0: into ALL of them (replicated reduce);
+    int peer_mode;              //   peer_mode 1: only into the Gram of the rank that owns the row (reduce-scatter)
+    int own_end[kMaxPeers];     // rank q owns Gram rows [own_end[q-1], own_end[q]); multiples of 32, >= 32 apart
     const int2* tiles;
     int* err;          // mapped host memory: watchdog diagnostics
     int n;
@@ -397,6 +401,17 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                 uint32_t r[32];
                 ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
                 ptx::tmem_ld_wait();
+                // owner-rows mode: the (at most two) ranks that own rows of this 32-row chunk
+                int32_t* own_lo = nullptr;
+                int32_t* own_hi = nullptr;
+                int own_split = 0;
+                if (a.num_peers != 0 && a.peer_mode == 1) {
+                    int q = 0;
+                    while (q + 1 < a.num_peers && rbase >= a.own_end[q]) ++q;
+                    own_split = a.own_end[q];
+                    own_lo = a.peer[q];
+                    own_hi = a.peer[min(q + 1, a.num_peers - 1)];
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int row = rbase + j;
@@ -408,6 +423,10 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                             const size_t o = (size_t)row * (size_t)a.n;
                             if (a.num_peers == 0) {
                                 asm volatile("red.global.add.s32 [%0], %1;" ::"l"(out + o), "r"(v) : "memory");
+                            } else if (a.peer_mode == 1) {
+                                // fused reduce-scatter: one red, into the Gram of the rank that owns this row
+                                int32_t* dst = (row >= own_split ? own_hi : own_lo) + col + o;
+                                asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(dst), "r"(v) : "memory");
                             } else {
                                 // fused reduceByKey: the same red, once per rank, on peer-mapped Gram buffers
                                 for (int d = 0; d < a.num_peers; ++d)
@@ -534,6 +553,73 @@ __global__ void add_i32_peers_kernel(PeerPtrs dst, int npeers, const int32_t* __
         if (v != 0)
             for (int d = 0; d < npeers; ++d)
                 asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(dst.p[d] + i), "r"(v) : "memory");
+    }
+}
+
+struct OwnEnds {
+    int e[kMaxPeers];
+};
+
+__device__ __forceinline__ int owner_of_row(const OwnEnds& own, int npeers, int row) {
+    int q = 0;
+    while (q + 1 < npeers && row >= own.e[q]) ++q;
+    return q;
+}
+
+// Staged partition -> owners: element (row, col) of the lower triangle is added into the Gram of the row's owner.
+__global__ void add_i32_owner_kernel(PeerPtrs dst, OwnEnds own, int npeers, const int32_t* __restrict__ src, int n) {
+    for (int row = blockIdx.x; row < n; row += gridDim.x) {
+        int32_t* d = dst.p[owner_of_row(own, npeers, row)] + (size_t)row * n;
+        const int32_t* s = src + (size_t)row * n;
+        for (int c = threadIdx.x; c <= row; c += blockDim.x) {
+            const int v = s[c];
+            if (v != 0) asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(d + c), "r"(v) : "memory");
+        }
+    }
+}
+
+// All-gather after the reduce-scatter: every rank pulls the lower-triangle part of the rows it does not own from the
+// owner's Gram (peer loads over NVLink, 16-byte when the row pitch allows).
+__global__ void __launch_bounds__(256) gather_rows_kernel(PeerPtrs src, int32_t* __restrict__ dst, OwnEnds own, int npeers,
+                                                          int rank, int n) {
+    const bool vec = (n & 3) == 0;
+    for (int row = blockIdx.x; row < n; row += gridDim.x) {
+        const int q = owner_of_row(own, npeers, row);
+        if (q == rank) continue;
+        const int32_t* s = src.p[q] + (size_t)row * n;
+        int32_t* d = dst + (size_t)row * n;
+        if (vec) {
+            const int4* s4 = reinterpret_cast<const int4*>(s);
+            int4* d4 = reinterpret_cast<int4*>(d);
+            for (int c = threadIdx.x; c < (row + 4) / 4; c += blockDim.x) d4[c] = s4[c];   // up to 3 cells past the diagonal: zeros
+        } else {
+            for (int c = threadIdx.x; c <= row; c += blockDim.x) d[c] = s[c];
+        }
+    }
+}
+
+// The same all-gather as posted writes: every rank pushes the lower-triangle part of the rows it owns into the Gram of
+// every other rank (remote stores are fire-and-forget; remote loads pay a NVLink round trip each).
+__global__ void __launch_bounds__(256) push_rows_kernel(PeerPtrs dst, const int32_t* __restrict__ src, OwnEnds own,
+                                                        int npeers, int rank, int n) {
+    const bool vec = (n & 3) == 0;
+    const int row_lo = rank == 0 ? 0 : own.e[rank - 1], row_hi = own.e[rank];
+    for (int row = row_lo + blockIdx.x; row < row_hi; row += gridDim.x) {
+        const int32_t* s = src + (size_t)row * n;
+        if (vec) {
+            const int4* s4 = reinterpret_cast<const int4*>(s);
+            for (int c = threadIdx.x; c < (row + 4) / 4; c += blockDim.x) {
+                const int4 v = s4[c];
+                for (int d = 0; d < npeers; ++d)
+                    if (d != rank) reinterpret_cast<int4*>(dst.p[d] + (size_t)row * n)[c] = v;
+            }
+        } else {
+            for (int c = threadIdx.x; c <= row; c += blockDim.x) {
+                const int v = s[c];
+                for (int d = 0; d < npeers; ++d)
+                    if (d != rank) dst.p[d][(size_t)row * n + c] = v;
+            }
+        }
     }
 }
 
@@ -749,6 +835,8 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     args.S = d_S;
     args.num_peers = (plan.num_peers > 1 && d_S == plan.peer_S[plan.peer_rank]) ? plan.num_peers : 0;
     for (int d = 0; d < kMaxPeers; ++d) args.peer[d] = d < plan.num_peers ? plan.peer_S[d] : nullptr;
+    args.peer_mode = plan.peer_mode;
+    for (int d = 0; d < kMaxPeers; ++d) args.own_end[d] = plan.own_end[d];
     args.tiles = plan.d_tiles;
     cudaHostGetDevicePointer(reinterpret_cast<void**>(&args.err), plan.d_err, 0);
     args.n = n;
@@ -822,6 +910,39 @@ cudaError_t gram_add_peers(GramPlan& plan, const int32_t* d_src, int64_t count, 
     PeerPtrs pp{};
     for (int d = 0; d < plan.num_peers; ++d) pp.p[d] = plan.peer_S[d];
     add_i32_peers_kernel<<<592, 256, 0, stream>>>(pp, plan.num_peers, d_src, count);
+    return cudaGetLastError();
+}
+
+cudaError_t gram_add_owners(GramPlan& plan, const int32_t* d_src, int n, cudaStream_t stream) {
+    PeerPtrs pp{};
+    OwnEnds own{};
+    for (int d = 0; d < plan.num_peers; ++d) pp.p[d] = plan.peer_S[d];
+    for (int d = 0; d < kMaxPeers; ++d) own.e[d] = plan.own_end[d];
+    add_i32_owner_kernel<<<592, 256, 0, stream>>>(pp, own, plan.num_peers, d_src, n);
+    return cudaGetLastError();
+}
+
+cudaError_t gram_gather_rows(GramPlan& plan, int32_t* d_S, int n, cudaStream_t stream) {
+    PeerPtrs pp{};
+    OwnEnds own{};
+    for (int d = 0; d < plan.num_peers; ++d) pp.p[d] = plan.peer_S[d];
+    for (int d = 0; d < kMaxPeers; ++d) own.e[d] = plan.own_end[d];
+    // VPCA_GATHER=push (default) | pull | copy: posted peer stores, peer loads, or copy-engine 2-D copies per band
+    const char* how = getenv("VPCA_GATHER");
+    if (how != nullptr && strcmp(how, "pull") == 0) {
+        gather_rows_kernel<<<1184, 256, 0, stream>>>(pp, d_S, own, plan.num_peers, plan.peer_rank, n);
+    } else if (how != nullptr && strcmp(how, "copy") == 0) {
+        for (int q = 0; q < plan.num_peers; ++q) {
+            if (q == plan.peer_rank) continue;
+            const int r0 = q == 0 ? 0 : plan.own_end[q - 1], r1 = plan.own_end[q];
+            cudaError_t e = cudaMemcpy2DAsync(d_S + (size_t)r0 * n, (size_t)n * 4, plan.peer_S[q] + (size_t)r0 * n,
+                                              (size_t)n * 4, (size_t)std::min(n, r1) * 4, (size_t)(r1 - r0),
+                                              cudaMemcpyDeviceToDevice, stream);
+            if (e != cudaSuccess) return e;
+        }
+    } else {
+        push_rows_kernel<<<1184, 256, 0, stream>>>(pp, d_S, own, plan.num_peers, plan.peer_rank, n);
+    }
     return cudaGetLastError();
 }
 

@@ -495,7 +495,9 @@ int vpca_commit(vpca_ctx* ctx, int64_t partition_id) {
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     rc = check_overflow(ctx, 0);
     if (rc != VPCA_OK) return rc;
-    if (ctx->plan.num_peers > 1)
+    if (ctx->plan.num_peers > 1 && ctx->plan.peer_mode == 1)
+        CUDA_OK(ctx, gram_add_owners(ctx->plan, s->d_S, ctx->n, ctx->stream));
+    else if (ctx->plan.num_peers > 1)
         CUDA_OK(ctx, gram_add_peers(ctx->plan, s->d_S, (int64_t)ctx->n * ctx->n, ctx->stream));
     else
         CUDA_OK(ctx, gram_add(ctx->d_S, s->d_S, (int64_t)ctx->n * ctx->n, ctx->stream));
@@ -820,6 +822,47 @@ int vpca_gram_set_peers(vpca_ctx* ctx, const void* handles, int32_t world, int32
     }
     ctx->plan.peer_rank = rank;
     ctx->plan.num_peers = world;
+    return VPCA_OK;
+}
+
+int vpca_gram_set_peer_mode(vpca_ctx* ctx, int32_t mode) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (mode != VPCA_PEER_REPLICATE && mode != VPCA_PEER_OWNER_ROWS)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_gram_set_peer_mode: unknown mode %d", mode);
+    if (ctx->plan.num_peers < 1) return fail(ctx, VPCA_ERR_STATE, "call vpca_gram_set_peers first");
+    const int world = ctx->plan.num_peers, n = ctx->n;
+    if (mode == VPCA_PEER_OWNER_ROWS) {
+        if (n < 64 * world)
+            return fail(ctx, VPCA_ERR_UNSUPPORTED, "owner-rows mode needs n_samples >= 64 x world (%d < %d)", n, 64 * world);
+        // equal shares of the lower triangle: rows [0, R) hold R^2 / 2 cells -> R_q = n sqrt(q / world), on multiples of 32
+        int prev = 0;
+        for (int q = 0; q < world; ++q) {
+            int end = (q + 1 == world) ? n : (int)(std::sqrt((double)(q + 1) / world) * n / 32.0 + 0.5) * 32;
+            end = std::max(end, prev + 32);
+            if (q + 1 < world) end = std::min(end, n - 32 * (world - 1 - q));
+            ctx->plan.own_end[q] = end;
+            prev = end;
+        }
+        for (int q = world; q < 16; ++q) ctx->plan.own_end[q] = n;
+    }
+    ctx->plan.peer_mode = mode;
+    return VPCA_OK;
+}
+
+int vpca_gram_gather(vpca_ctx* ctx) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized");
+    if (ctx->plan.num_peers < 2) return VPCA_OK;
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    CUDA_OK(ctx, gram_peer_barrier(ctx->plan, ctx->stream));          // every rank's contributions have landed
+    ctx->st.kernel_launches += 1;
+    if (ctx->plan.peer_mode == 1) {
+        CUDA_OK(ctx, gram_gather_rows(ctx->plan, ctx->d_S, ctx->n, ctx->stream));
+        CUDA_OK(ctx, gram_peer_barrier(ctx->plan, ctx->stream));      // nobody resets a Gram a peer is still reading
+        ctx->st.kernel_launches += 2;
+    }
     return VPCA_OK;
 }
 

@@ -33,6 +33,8 @@ struct GramPlan {
     int num_peers = 0, peer_rank = 0, peer_epoch = 0;
     int32_t* peer_S[16] = {};
     int32_t* peer_flags[16] = {};
+    int peer_mode = 0;        // 0: every flush goes to all ranks' Grams; 1: to the owner of the row only (+ gather)
+    int own_end[16] = {};     // peer_mode 1: rank q owns Gram rows [own_end[q-1], own_end[q])
     bool profile = false;     // VPCA_GRAM_PROF=1: per-CTA timestamps in d_prof
     long long* d_prof = nullptr;
 };
@@ -53,6 +55,8 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
 cudaError_t gram_symmetrize(int32_t* d_S, int n, cudaStream_t stream);
 cudaError_t gram_add(int32_t* d_dst, const int32_t* d_src, int64_t count, cudaStream_t stream);
 cudaError_t gram_add_peers(GramPlan& plan, const int32_t* d_src, int64_t count, cudaStream_t stream);
+cudaError_t gram_add_owners(GramPlan& plan, const int32_t* d_src, int n, cudaStream_t stream);
+cudaError_t gram_gather_rows(GramPlan& plan, int32_t* d_S, int n, cudaStream_t stream);
 cudaError_t gram_peer_barrier(GramPlan& plan, cudaStream_t stream);
 void gram_plan_free(GramPlan& plan);
 

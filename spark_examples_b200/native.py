@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = (
     "vpca_get_tridiagonal", "vpca_synth_dense_device", "vpca_get_stats", "vpca_debug_gram_profile",
     "vpca_gram_export_ipc", "vpca_gram_set_peers", "vpca_peer_barrier", "vpca_accumulate_panels",
     "vpca_synth_panels_device", "vpca_accumulate_calls_u16", "vpca_get_partial_gram", "vpca_load_partial_gram",
-    "vpca_accumulate_bits",
+    "vpca_accumulate_bits", "vpca_gram_set_peer_mode", "vpca_gram_gather",
 )
 
 
@@ -166,6 +166,10 @@ def load_library() -> ctypes.CDLL:
     L.vpca_gram_set_peers.argtypes = [vp, vp, i32, i32]
     L.vpca_peer_barrier.restype = ctypes.c_int
     L.vpca_peer_barrier.argtypes = [vp]
+    L.vpca_gram_set_peer_mode.restype = ctypes.c_int
+    L.vpca_gram_set_peer_mode.argtypes = [vp, ctypes.c_int32]
+    L.vpca_gram_gather.restype = ctypes.c_int
+    L.vpca_gram_gather.argtypes = [vp]
     L.vpca_debug_gram_profile.restype = ctypes.c_int
     L.vpca_debug_gram_profile.argtypes = [vp, vp, i32]
     _lib = L
@@ -326,10 +330,16 @@ class NativePca:
         self._check(self._lib.vpca_gram_export_ipc(self._h, buf))
         return buf.raw
 
-    def setPeers(self, handles, rank: int):
-        """handles: list of 64-byte handles of all ranks, in rank order."""
+    def setPeers(self, handles, rank: int, mode: str = "replicate"):
+        """handles: list of 64-byte handles of all ranks, in rank order.  mode: "replicate" (every flush into every
+        rank's Gram) or "owner_rows" (reduce-scatter by Gram row bands; finish a pass with gatherGram())."""
         blob = ctypes.create_string_buffer(b"".join(handles), 64 * len(handles))
         self._check(self._lib.vpca_gram_set_peers(self._h, blob, len(handles), int(rank)))
+        self._check(self._lib.vpca_gram_set_peer_mode(self._h, {"replicate": 0, "owner_rows": 1}[mode]))
+
+    def gatherGram(self):
+        """Closing step of a fused pass: all-rank barrier (+ pull of the other ranks' row bands in owner_rows mode)."""
+        self._check(self._lib.vpca_gram_gather(self._h))
 
     def peerBarrier(self):
         self._check(self._lib.vpca_peer_barrier(self._h))

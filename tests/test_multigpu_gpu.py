@@ -1,5 +1,6 @@
 """Two-GPU tests (skipped on boxes with fewer than 2 devices): variant-sharded Gram reduced (a) by the host-driven
-NCCL all-reduce and (b) by the fused peer-memory epilogue, both equal to the oracle's Gram of the whole cohort."""
+NCCL all-reduce, (b) by the fused peer-memory epilogue into every rank's Gram and (c) by the fused reduce-scatter into
+row-band owners + all-gather, all equal to the oracle's Gram of the whole cohort."""
 import os
 import socket
 
@@ -37,6 +38,8 @@ def _worker(rank, world, port, n, nv, out_dir):
         torch.cuda.set_stream(stream)
         per = nv // world
         X = torch.empty((n, per), dtype=torch.int8, device="cuda")
+        from oracle import oracle as _o
+        calls = _o.c_synth_calls(20240901, n, rank * per, per)     # the same shard as index rows (test input only)
         # (a) NCCL
         S = torch.zeros((n, n), dtype=torch.int32, device="cuda")
         with native.NativePca(n, device=rank, stream=stream.cuda_stream, d_gram=S.data_ptr()) as nat:
@@ -59,6 +62,25 @@ def _worker(rank, world, port, n, nv, out_dir):
                 G = nat.getGram()
             np.save(os.path.join(out_dir, f"fused_{rank}.npy"), G)
             dist.barrier()          # nobody unmaps a peer buffer while another rank may still touch it
+        # (c) fused reduce-scatter by Gram row bands + all-gather over peer memory; the second pass goes through a
+        #     staged partition (commit adds into the owners) to cover that route too
+        with native.NativePca(n, device=rank, stream=stream.cuda_stream) as nat:
+            handles = [None] * world
+            dist.all_gather_object(handles, nat.exportIpcHandle())
+            nat.setPeers(handles, rank, mode="owner_rows")
+            for p in range(2):
+                nat.reset()
+                nat.peerBarrier()
+                if p == 0:
+                    nat.accumulateDenseDevice(X.data_ptr(), per, per)
+                else:
+                    off, idx = calls
+                    nat.accumulateCalls(7 + rank, off, idx)
+                    nat.commit(7 + rank)
+                nat.gatherGram()
+                nat.finalizeGram()
+                np.save(os.path.join(out_dir, f"owner{p}_{rank}.npy"), nat.getGram())
+            dist.barrier()
     finally:
         dist.destroy_process_group()
 
@@ -72,3 +94,5 @@ def test_two_gpu_nccl_and_fused_reduce(tmp_path, oracle):
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"nccl_{r}.npy"), want)
         assert np.array_equal(np.load(tmp_path / f"fused_{r}.npy"), want)
+        assert np.array_equal(np.load(tmp_path / f"owner0_{r}.npy"), want)
+        assert np.array_equal(np.load(tmp_path / f"owner1_{r}.npy"), want)
