@@ -159,6 +159,31 @@ def cpu_similarity_sample(n, seconds, threads=None):
     return n * nv / dt, {"variants": nv, "seconds": dt, "threads": threads, "checksum": int(S.trace())}
 
 
+def cpu_blas_sample(n, nv=65_536, threads=None):
+    """Context number so that the CPU comparison is not against a strawman (SURVEY.md 8d "strong CPU"): the same Gram
+    as one float32 BLAS product X X^T over `nv` variants (exact: every sum stays below 2^24), all host threads."""
+    import numpy as np
+    from oracle import oracle
+    oracle.build()
+    threads = threads or host_threads()
+    oracle.c_set_threads(threads)
+    X = oracle.c_synth_dense(SEED, n, 0, nv, 0).astype(np.float32)
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=threads)
+    except Exception:
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        _ = X[:, :1024] @ X[:, :1024].T            # thread-pool warm-up
+        t0 = time.perf_counter()
+        G = X @ X.T
+        dt = time.perf_counter() - t0
+    return {"value": n * nv / dt, "unit": UNIT, "cores": threads,
+            "sample": f"{nv} variants x {n} samples, numpy float32 X @ X.T ({dt:.2f} s), exact below 2^24",
+            "checksum": int(np.trace(G.astype(np.float64)))}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -187,7 +212,8 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{nvs[-1]} variants x {n} samples per step, oracle/vpca_oracle.c vo_similarity "
                                    f"(VariantsPca.scala:182-191 restated; Spark/JVM not runnable here), OpenMP "
-                                   f"{threads} threads; Gram only"},
+                                   f"{threads} threads; Gram only",
+                         "strong_cpu_blas": cpu_blas_sample(n, threads=threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -598,6 +624,10 @@ def run_b200(args):
         cpu = {"value": v, "unit": UNIT, "cores": info["threads"], "kind": "port",
                "sample": f"{info['variants']} variants x {n} samples ({info['seconds']:.1f} s), oracle/vpca_oracle.c "
                          f"vo_similarity = VariantsPca.scala:182-191 restated, OpenMP; Gram only"}
+        try:
+            cpu["strong_cpu_blas"] = cpu_blas_sample(n)
+        except Exception as exc:
+            cpu["strong_cpu_blas"] = {"error": repr(exc)[:200]}
 
     if rank == 0:
         line = {

@@ -631,8 +631,11 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, int npeers, int rank, int ep
         __threadfence_system();
         asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flags.p[d] + rank), "r"(epoch) : "memory");
         int v;
+        const long long t0 = globaltimer_ns();
         do {
             asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags.p[rank] + d) : "memory");
+            // a peer that died or never reached the barrier must surface as an error, not hang the box
+            if (v < epoch && globaltimer_ns() - t0 > 30000000000LL) __trap();
         } while (v < epoch);
     }
     __syncthreads();
