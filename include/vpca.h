@@ -119,6 +119,13 @@ int vpca_accumulate_calls_u16(vpca_ctx* ctx, int64_t partition_id, const int64_t
  * ~4.3 KB of int32 indices for the synthetic cohort); expanded to cells on the device by a bit-matrix transpose.
  * Binary carriers only (a sample cannot be listed twice).  Same staging / commit semantics as vpca_accumulate_calls. */
 int vpca_accumulate_bits(vpca_ctx* ctx, int64_t partition_id, const uint8_t* bits, int64_t nv, int64_t stride_bytes);
+/* PLINK 1 .bed rows as they are on disk (variant-major; 2 bits per sample, low bits first: 00 homozygous A1,
+ * 01 missing, 10 heterozygous, 11 homozygous A2), rows stride_bytes apart (>= ceil(n_samples / 4)).  `hasVariation`
+ * (:58) = "carries the counted allele": counted_allele 1 -> codes {00, 10} (A1, PLINK's minor / alternate allele),
+ * 2 -> codes {10, 11}; a missing call carries nothing, like a no-call.  Stands in for the retired ingestion
+ * (rdd/VariantsRDD.scala:187-236) at N/4 bytes per variant.  Same staging / commit semantics as vpca_accumulate_calls. */
+int vpca_accumulate_bed(vpca_ctx* ctx, int64_t partition_id, const uint8_t* rows, int64_t nv, int64_t stride_bytes,
+                        int32_t counted_allele);
 int vpca_commit(vpca_ctx* ctx, int64_t partition_id);
 int vpca_abort(vpca_ctx* ctx, int64_t partition_id);
 

@@ -108,4 +108,6 @@ class PcaConf(GenomicsConf):
             ("synthetic", str, None, False),              # "N,V[,seed]": synthetic cohort instead of the retired API
             ("variantsPerPartition", int, 65536, False),  # rows per partition for offline/synthetic sources
             ("checkpointPath", str, None, False),         # save / resume the similarity matrix + partition watermark
+            ("bedPath", str, None, False),                # PLINK 1 fileset prefix (.bed/.bim/.fam) as the variants source
+            ("bedCountedAllele", str, "A1", False),       # which .bim allele is "variation": A1 (PLINK's minor) or A2
         ]

@@ -109,9 +109,22 @@ __global__ void encode_e2m1_kernel(const int64_t* __restrict__ off, int64_t base
 // 32-bit word (32 samples of its variant), 32 ballots transpose the 32 x 32 bit tile so that lane = sample holds the
 // 32 variant bits of its sample, which it expands to 32 cells and stores as one contiguous 32-byte (int8) /
 // 16-byte (e2m1) / 64-byte (bf16) run of its sample row.  A bit-matrix transpose at HBM speed; no atomics.
+// CODE 0: rows are bitmaps (1 bit per sample).  CODE 1 / 2: rows are PLINK .bed rows (2 bits per sample, low bits
+// first; 00 hom A1, 01 missing, 10 het, 11 hom A2) and the carrier bit is "has an A1" (codes 00, 10 = low bit clear) /
+// "has an A2" (codes 10, 11 = high bit set); a missing call carries nothing, like a no-call under VariantsPca.scala:58.
+__device__ __forceinline__ uint32_t compress_even_bits(uint64_t x) {   // bit 2j of x -> bit j
+    x &= 0x5555555555555555ull;
+    x = (x | (x >> 1)) & 0x3333333333333333ull;
+    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x >> 16)) & 0x00000000FFFFFFFFull;
+    return (uint32_t)x;
+}
+
 template <int BITS>
 __global__ void bits_to_cells_kernel(const uint8_t* __restrict__ bits, int64_t stride, int64_t nv, int n,
-                                     uint8_t* __restrict__ x, int64_t ld, int64_t panel) {
+                                     uint8_t* __restrict__ x, int64_t ld, int64_t panel, int code) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int words = (n + 31) / 32;                          // 32-sample words per variant
@@ -121,12 +134,21 @@ __global__ void bits_to_cells_kernel(const uint8_t* __restrict__ bits, int64_t s
     const int k = (int)(warp - vg * words);
     const int64_t v = vg * 32 + lane;                         // my variant while loading
     uint32_t word = 0;
-    if (v < nv) {
+    if (v < nv && code == 0) {
         const uint8_t* row = bits + v * stride + (size_t)k * 4;
         const int64_t avail = stride - (int64_t)k * 4;        // bytes of this row from here on
 #pragma unroll
         for (int b = 0; b < 4; ++b)
             if (b < avail) word |= (uint32_t)row[b] << (8 * b);
+    } else if (v < nv) {
+        const uint8_t* row = bits + v * stride + (size_t)k * 8;   // 32 samples = 8 bytes of 2-bit codes
+        const int64_t avail = stride - (int64_t)k * 8;
+        uint64_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+            if (b < avail) w |= (uint64_t)row[b] << (8 * b);
+        // padding samples (code 00 = "hom A1") beyond n are masked below (smp >= n)
+        word = code == 1 ? ~compress_even_bits(w) : compress_even_bits(w >> 1);
     }
     uint32_t mine = 0;                                        // after the loop: bit j = variant vg*32+j at MY sample
 #pragma unroll
@@ -181,7 +203,7 @@ __global__ void bits_to_cells_kernel(const uint8_t* __restrict__ bits, int64_t s
 }  // namespace
 
 cudaError_t encode_bits(const uint8_t* d_bits, int64_t stride, int64_t nv, int n, int elem_bits, void* d_x, int64_t ld,
-                        int64_t panel, cudaStream_t stream) {
+                        int64_t panel, int code, cudaStream_t stream) {
     if (nv <= 0) return cudaSuccess;
     // every cell of the touched 32-variant groups is written, so only a partial last panel / k-block needs zeroing
     cudaError_t e = cudaSuccess;
@@ -201,11 +223,11 @@ cudaError_t encode_bits(const uint8_t* d_bits, int64_t stride, int64_t nv, int n
     const int threads = 256;
     const int64_t blocks = (warps * 32 + threads - 1) / threads;
     if (elem_bits == 8)
-        bits_to_cells_kernel<8><<<(unsigned)blocks, threads, 0, stream>>>(d_bits, stride, nv, n, static_cast<uint8_t*>(d_x), ld, panel);
+        bits_to_cells_kernel<8><<<(unsigned)blocks, threads, 0, stream>>>(d_bits, stride, nv, n, static_cast<uint8_t*>(d_x), ld, panel, code);
     else if (elem_bits == 4)
-        bits_to_cells_kernel<4><<<(unsigned)blocks, threads, 0, stream>>>(d_bits, stride, nv, n, static_cast<uint8_t*>(d_x), ld, panel);
+        bits_to_cells_kernel<4><<<(unsigned)blocks, threads, 0, stream>>>(d_bits, stride, nv, n, static_cast<uint8_t*>(d_x), ld, panel, code);
     else
-        bits_to_cells_kernel<16><<<(unsigned)blocks, threads, 0, stream>>>(d_bits, stride, nv, n, static_cast<uint8_t*>(d_x), ld, panel);
+        bits_to_cells_kernel<16><<<(unsigned)blocks, threads, 0, stream>>>(d_bits, stride, nv, n, static_cast<uint8_t*>(d_x), ld, panel, code);
     return cudaGetLastError();
 }
 

@@ -429,11 +429,14 @@ static int accumulate_calls_impl(vpca_ctx* ctx, int64_t partition_id, const int6
     return VPCA_OK;
 }
 
-int vpca_accumulate_bits(vpca_ctx* ctx, int64_t partition_id, const uint8_t* bits, int64_t nv, int64_t stride_bytes) {
+// code 0: bitmap rows; 1 / 2: PLINK .bed rows counting A1 / A2 (see encode.cu)
+static int accumulate_packed(vpca_ctx* ctx, int64_t partition_id, const uint8_t* bits, int64_t nv, int64_t stride_bytes,
+                             int code) {
     if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    if (nv < 0 || (nv > 0 && bits == nullptr) || stride_bytes < (ctx->n + 7) / 8)
-        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_accumulate_bits: stride_bytes must be >= ceil(n_samples / 8)");
+    const int64_t min_stride = code == 0 ? (ctx->n + 7) / 8 : (ctx->n + 3) / 4;
+    if (nv < 0 || (nv > 0 && bits == nullptr) || stride_bytes < min_stride)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "packed rows: stride_bytes must be >= ceil(n_samples / %d)", code == 0 ? 8 : 4);
     if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     if (nv == 0) return VPCA_OK;
@@ -469,7 +472,7 @@ int vpca_accumulate_bits(vpca_ctx* ctx, int64_t partition_id, const uint8_t* bit
         ctx->st.h2d_bytes += nvc * stride_bytes;
         CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
         CUDA_OK(ctx, encode_bits(reinterpret_cast<const uint8_t*>(ctx->d_idx[b]), stride_bytes, nvc, ctx->n, ctx->elem_bits,
-                                 ctx->d_x[b], P, P, ctx->stream));
+                                 ctx->d_x[b], P, P, code, ctx->stream));
         ctx->st.kernel_launches += 1;
         rc = launch_gram(ctx, ctx->d_x[b], nvc, P, P, target);
         if (rc != VPCA_OK) {
@@ -483,6 +486,17 @@ int vpca_accumulate_bits(vpca_ctx* ctx, int64_t partition_id, const uint8_t* bit
     else ctx->total_variants += nv;
     ctx->st.variants_accumulated += nv;
     return VPCA_OK;
+}
+
+int vpca_accumulate_bits(vpca_ctx* ctx, int64_t partition_id, const uint8_t* bits, int64_t nv, int64_t stride_bytes) {
+    return accumulate_packed(ctx, partition_id, bits, nv, stride_bytes, 0);
+}
+
+int vpca_accumulate_bed(vpca_ctx* ctx, int64_t partition_id, const uint8_t* rows, int64_t nv, int64_t stride_bytes,
+                        int32_t counted_allele) {
+    if (counted_allele != 1 && counted_allele != 2)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_accumulate_bed: counted_allele must be 1 (A1) or 2 (A2)");
+    return accumulate_packed(ctx, partition_id, rows, nv, stride_bytes, counted_allele);
 }
 
 int vpca_commit(vpca_ctx* ctx, int64_t partition_id) {

@@ -68,9 +68,10 @@ cudaError_t encode_calls(const int64_t* d_off, int64_t base, const void* d_idx, 
                          int elem_bits, int max_mult, void* d_x, int64_t ld, int64_t panel, int* d_flags,
                          cudaStream_t stream);   // idx_bytes: 4 (int32) or 2 (uint16)
 
-// Bitmap rows (one N-bit row per variant, LSB first, `stride` bytes apart) -> dense cells (binary carriers).
+// Packed rows (`stride` bytes apart) -> dense cells (binary carriers).  code 0: one N-bit bitmap per variant, LSB
+// first; code 1 / 2: PLINK .bed rows (2 bits per sample), carriers of A1 / of A2.
 cudaError_t encode_bits(const uint8_t* d_bits, int64_t stride, int64_t nv, int n, int elem_bits, void* d_x, int64_t ld,
-                        int64_t panel, cudaStream_t stream);
+                        int64_t panel, int code, cudaStream_t stream);
 
 // ---- centering + eigensolve (eig.cu) ---------------------------------------------------------------
 struct EigWork {

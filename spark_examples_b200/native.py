@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = (
     "vpca_get_tridiagonal", "vpca_synth_dense_device", "vpca_get_stats", "vpca_debug_gram_profile",
     "vpca_gram_export_ipc", "vpca_gram_set_peers", "vpca_peer_barrier", "vpca_accumulate_panels",
     "vpca_synth_panels_device", "vpca_accumulate_calls_u16", "vpca_get_partial_gram", "vpca_load_partial_gram",
-    "vpca_accumulate_bits", "vpca_gram_set_peer_mode", "vpca_gram_gather",
+    "vpca_accumulate_bits", "vpca_gram_set_peer_mode", "vpca_gram_gather", "vpca_accumulate_bed",
 )
 
 
@@ -128,6 +128,8 @@ def load_library() -> ctypes.CDLL:
     L.vpca_accumulate_calls_u16.argtypes = [vp, i64, vp, vp, i64]
     L.vpca_accumulate_bits.restype = ctypes.c_int
     L.vpca_accumulate_bits.argtypes = [vp, i64, vp, i64, i64]
+    L.vpca_accumulate_bed.restype = ctypes.c_int
+    L.vpca_accumulate_bed.argtypes = [vp, i64, vp, i64, i64, ctypes.c_int32]
     L.vpca_commit.restype = ctypes.c_int
     L.vpca_commit.argtypes = [vp, i64]
     L.vpca_abort.restype = ctypes.c_int
@@ -271,6 +273,15 @@ class NativePca:
         if b.ndim != 2:
             raise VpcaError(VPCA_ERR_BAD_ARG, "bits must be (nv, stride_bytes)")
         self._check(self._lib.vpca_accumulate_bits(self._h, int(partition_id), _host_ptr(b), b.shape[0], b.shape[1]))
+
+    def accumulateBed(self, partition_id: int, rows: np.ndarray, counted_allele: int = 1):
+        """rows: (nv, stride) uint8 PLINK .bed rows (2 bits per sample: 00 hom A1, 01 missing, 10 het, 11 hom A2);
+        counted_allele 1: carriers of A1, 2: carriers of A2 (plink.py)."""
+        b = np.ascontiguousarray(rows, dtype=np.uint8)
+        if b.ndim != 2:
+            raise VpcaError(VPCA_ERR_BAD_ARG, "rows must be (nv, stride_bytes)")
+        self._check(self._lib.vpca_accumulate_bed(self._h, int(partition_id), _host_ptr(b), b.shape[0], b.shape[1],
+                                                  int(counted_allele)))
 
     def accumulateBitsRaw(self, partition_id: int, ptr: int, nv: int, stride_bytes: int):
         self._check(self._lib.vpca_accumulate_bits(self._h, int(partition_id), ptr, int(nv), int(stride_bytes)))

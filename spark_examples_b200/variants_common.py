@@ -35,9 +35,21 @@ class SyntheticSlice:
     nv: int
 
 
+@dataclass
+class BedSlice:
+    """Variants [v0, v0 + nv) of a PLINK .bed file (plink.py); the packed rows go to the device as they are on disk."""
+    bed: object           # plink.BedFile
+    v0: int
+    nv: int
+    counted: int          # 1: carriers of A1, 2: carriers of A2
+
+    def rows(self) -> np.ndarray:
+        return self.bed.rows(self.v0, self.v0 + self.nv)
+
+
 class VariantsDataset:
     """Stand-in for one `RDD[Variant]`: an ordered list of partitions.  A partition is a list of `Variant`
-    records, a `CallsBatch` or a `SyntheticSlice`."""
+    records, a `CallsBatch`, a `SyntheticSlice` or a `BedSlice`."""
 
     def __init__(self, partitions: Sequence[object], variantSetId: str = ""):
         self.partitions = list(partitions)
@@ -70,6 +82,14 @@ class VariantsCommon:
             self._set_callsets([(f"synth-{i:06d}", f"S{i:06d}") for i in range(n)])
             slices = [SyntheticSlice(self.synthetic_seed, v0, min(per_part, v - v0)) for v0 in range(0, v, per_part)]
             self.data = [VariantsDataset(slices, "synth")]
+        elif conf.bedPath.isDefined:                               # additive: PLINK fileset on disk
+            from . import plink
+            counted = {"A1": plink.COUNT_A1, "A2": plink.COUNT_A2}[conf.bedCountedAllele().upper()]
+            self._set_callsets(plink.read_fam(conf.bedPath()))
+            bed = plink.BedFile(conf.bedPath(), n_samples=len(self.indexes))
+            slices = [BedSlice(bed, v0, min(per_part, bed.n_variants - v0), counted)
+                      for v0 in range(0, bed.n_variants, per_part)]
+            self.data = [VariantsDataset(slices, "bed")]
         elif conf.inputPath.isDefined:                             # VariantsCommon.scala:53-55
             callsets, variants = read_variants_file(conf.inputPath())
             self._set_callsets(callsets)
@@ -77,7 +97,7 @@ class VariantsCommon:
         else:
             raise RuntimeError(
                 "The Google Genomics API the reference streams from (VariantsCommon.scala:38-66) is retired; "
-                "give --input-path FILE.jsonl or --synthetic N,V[,seed]")
+                "give --input-path FILE.jsonl, --bed-path PLINK_PREFIX or --synthetic N,V[,seed]")
         print(f"Matrix size: {len(self.indexes)}.")                 # :48
 
     def _set_callsets(self, callsets: Sequence[Tuple[str, str]]):

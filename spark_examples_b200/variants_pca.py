@@ -29,7 +29,7 @@ from . import native
 from .conf import PcaConf
 from .jformat import jdouble
 from .records import Call, CallData, Variant
-from .variants_common import CallsBatch, SyntheticSlice, VariantsCommon, VariantsDataset
+from .variants_common import BedSlice, CallsBatch, SyntheticSlice, VariantsCommon, VariantsDataset
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -107,7 +107,7 @@ class CallsRdd:
     """`RDD[Seq[Int]]` (VariantsPca.scala:153): partitions of rows; a row lists the sample indices with variation."""
 
     def __init__(self, partitions: Sequence[object], n_samples: int):
-        self.partitions = list(partitions)       # CallsBatch | SyntheticSlice
+        self.partitions = list(partitions)       # CallsBatch | SyntheticSlice | BedSlice
         self.n_samples = n_samples
 
     def collect(self) -> List[List[int]]:
@@ -115,12 +115,15 @@ class CallsRdd:
         for p in self.partitions:
             if isinstance(p, SyntheticSlice):
                 raise RuntimeError("synthetic partitions are generated on the device; use getSimilarityMatrix")
+            if isinstance(p, BedSlice):
+                from . import plink
+                p = CallsBatch(*plink.rows_to_calls(p.rows(), self.n_samples, p.counted))
             for v in range(len(p.offsets) - 1):
                 rows.append(p.idx[p.offsets[v]:p.offsets[v + 1]].tolist())
         return rows
 
     def count(self) -> int:
-        return sum(p.nv if isinstance(p, SyntheticSlice) else len(p.offsets) - 1 for p in self.partitions)
+        return sum(p.nv if isinstance(p, (SyntheticSlice, BedSlice)) else len(p.offsets) - 1 for p in self.partitions)
 
 
 class SimilarityMatrix:
@@ -172,7 +175,7 @@ class VariantsPcaDriver:
             return np.float32(float(af[0])) >= np.float32(min_af)   # .get(0).toFloat >= minAlleleFrequency
 
         def fn(part):
-            if isinstance(part, (CallsBatch, SyntheticSlice)):
+            if isinstance(part, (CallsBatch, SyntheticSlice, BedSlice)):
                 raise ValueError("--min-allele-frequency needs Variant records (INFO field AF)")
             return [v for v in part if keep(v)]
         return data.map_partitions(fn)
@@ -214,8 +217,8 @@ class VariantsPcaDriver:
         if variantSetCount == 1:
             parts = []
             for part in data[0].partitions:
-                if isinstance(part, (CallsBatch, SyntheticSlice)):
-                    parts.append(part)                          # already RDD[Seq[Int]] rows
+                if isinstance(part, (CallsBatch, SyntheticSlice, BedSlice)):
+                    parts.append(part)                          # already RDD[Seq[Int]] rows (or their packed form)
                 else:
                     parts.append(_rows_to_batch([extractCallInfo(v, mapping) for v in part]))
             return CallsRdd(parts, n)
@@ -237,7 +240,10 @@ class VariantsPcaDriver:
                 self._accumulate_synthetic(nat, part)
                 continue
             try:
-                nat.accumulateCalls(pid, part.offsets, part.idx)
+                if isinstance(part, BedSlice):
+                    nat.accumulateBed(pid, part.rows(), part.counted)
+                else:
+                    nat.accumulateCalls(pid, part.offsets, part.idx)
                 nat.commit(pid)
             except Exception:
                 nat.abort(pid)
