@@ -12,6 +12,7 @@ object NativePca {
 
   val DTYPE_I8 = 0
   val DTYPE_BF16 = 1
+  val DTYPE_E2M1 = 2 // packed 4-bit cells (tcgen05 kind::mxf4 with unit scales; exact for 0/1/2)
 
   // every native method throws RuntimeException(vpca_last_error) on a negative vpca_status
   @native def create(nSamples: Int, device: Int, dtype: Int, numPc: Int, maxMultiplicity: Int,
@@ -20,12 +21,21 @@ object NativePca {
   @native def reset(handle: Long): Unit
   /** offsets: nv + 1 entries; sampleIdx: the concatenated rows of one batch of RDD[Seq[Int]] (VariantsPca.scala:153-168). */
   @native def accumulateCalls(handle: Long, partitionId: Long, offsets: Array[Long], sampleIdx: Array[Int], nv: Long): Unit
+  /** Same rows with 16-bit sample indices (N <= 65536): half the PCIe bytes. */
+  @native def accumulateCallsU16(handle: Long, partitionId: Long, offsets: Array[Long], sampleIdx: Array[Short], nv: Long): Unit
+  /** One N-bit bitmap per variant, bit s (LSB first) = hasVariation of sample s; rows strideBytes apart. */
+  @native def accumulateBits(handle: Long, partitionId: Long, bits: Array[Byte], nv: Long, strideBytes: Long): Unit
+  /** PLINK .bed rows as on disk (2 bits per sample); countedAllele 1 = A1, 2 = A2. */
+  @native def accumulateBed(handle: Long, partitionId: Long, rows: Array[Byte], nv: Long, strideBytes: Long,
+                            countedAllele: Int): Unit
   @native def commit(handle: Long, partitionId: Long): Unit
   @native def abort(handle: Long, partitionId: Long): Unit
   @native def finalizeGram(handle: Long): Unit
   /** Row-major N x N (the collected RDD[((Int, Int), Int)] of VariantsPca.scala:182-191 in key order). */
   @native def getGram(handle: Long, out: Array[Int]): Unit
   @native def setGram(handle: Long, gram: Array[Int]): Unit
+  /** Device address of the int32 Gram, for the NCCL all-reduce of NativePcaPool (INTEGRATION.md section 3). */
+  @native def gramDevicePtr(handle: Long): Long
   /** vecs: N x k column-major -- the layout of `pca.toArray` (VariantsPca.scala:227); returns nonZeroRows (:207). */
   @native def computePca(handle: Long, k: Int, vecs: Array[Double], evals: Array[Double]): Int
 }

@@ -8,6 +8,8 @@
 #include <jni.h>
 #include <stdint.h>
 
+#include <stddef.h>
+
 #include "vpca.h"
 
 #define CLS(name) Java_com_google_cloud_genomics_spark_examples_NativePca_00024_##name
@@ -52,6 +54,48 @@ JNIEXPORT void JNICALL CLS(accumulateCalls)(JNIEnv* env, jobject self, jlong h, 
     if (ix != NULL) (*env)->ReleasePrimitiveArrayCritical(env, idx, ix, JNI_ABORT);
     if (off != NULL) (*env)->ReleasePrimitiveArrayCritical(env, offsets, off, JNI_ABORT);
     if (rc != VPCA_OK) throw_last(env, ctx);
+}
+
+JNIEXPORT void JNICALL CLS(accumulateCallsU16)(JNIEnv* env, jobject self, jlong h, jlong pid, jlongArray offsets,
+                                               jshortArray idx, jlong nv) {
+    vpca_ctx* ctx = (vpca_ctx*)(intptr_t)h;
+    jlong* off = (*env)->GetPrimitiveArrayCritical(env, offsets, NULL);
+    jshort* ix = (*env)->GetPrimitiveArrayCritical(env, idx, NULL);
+    int rc = VPCA_ERR_NOMEM;
+    if (off != NULL && ix != NULL) rc = vpca_accumulate_calls_u16(ctx, pid, (const int64_t*)off, (const uint16_t*)ix, nv);
+    if (ix != NULL) (*env)->ReleasePrimitiveArrayCritical(env, idx, ix, JNI_ABORT);
+    if (off != NULL) (*env)->ReleasePrimitiveArrayCritical(env, offsets, off, JNI_ABORT);
+    if (rc != VPCA_OK) throw_last(env, ctx);
+}
+
+/* packed rows: mode 0 = bitmaps (vpca_accumulate_bits), 1 / 2 = PLINK .bed rows counting A1 / A2 */
+static void accumulate_packed(JNIEnv* env, jlong h, jlong pid, jbyteArray rows, jlong nv, jlong stride, int mode) {
+    vpca_ctx* ctx = (vpca_ctx*)(intptr_t)h;
+    jbyte* p = (*env)->GetPrimitiveArrayCritical(env, rows, NULL);
+    int rc = VPCA_ERR_NOMEM;
+    if (p != NULL)
+        rc = mode == 0 ? vpca_accumulate_bits(ctx, pid, (const uint8_t*)p, nv, stride)
+                       : vpca_accumulate_bed(ctx, pid, (const uint8_t*)p, nv, stride, mode);
+    if (p != NULL) (*env)->ReleasePrimitiveArrayCritical(env, rows, p, JNI_ABORT);
+    if (rc != VPCA_OK) throw_last(env, ctx);
+}
+
+JNIEXPORT void JNICALL CLS(accumulateBits)(JNIEnv* env, jobject self, jlong h, jlong pid, jbyteArray bits, jlong nv,
+                                           jlong stride) {
+    accumulate_packed(env, h, pid, bits, nv, stride, 0);
+}
+
+JNIEXPORT void JNICALL CLS(accumulateBed)(JNIEnv* env, jobject self, jlong h, jlong pid, jbyteArray rows, jlong nv,
+                                          jlong stride, jint counted) {
+    if (counted != 1 && counted != 2) counted = 1;
+    accumulate_packed(env, h, pid, rows, nv, stride, counted);
+}
+
+JNIEXPORT jlong JNICALL CLS(gramDevicePtr)(JNIEnv* env, jobject self, jlong h) {
+    vpca_ctx* ctx = (vpca_ctx*)(intptr_t)h;
+    void* p = NULL;
+    if (vpca_gram_device_ptr(ctx, &p) != VPCA_OK) throw_last(env, ctx);
+    return (jlong)(intptr_t)p;
 }
 
 JNIEXPORT void JNICALL CLS(commit)(JNIEnv* env, jobject self, jlong h, jlong pid) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for mode in nccl scatter nccl scatter; do
-  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+for mode in nccl scatter; do
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus 8 --steps 30 --warmup 3 --reduce $mode --e2e-steps 0 --no-cpu-baseline --no-alt --no-eig-check \
     > gpurun_out/bench_8gpu_$mode.json 2> gpurun_out/bench_8gpu_$mode.err
   python - <<PY
@@ -12,6 +12,5 @@ try:
 except Exception as e:
     print('$mode failed', e)
 PY
-  cp gpurun_out/bench_8gpu_$mode.json gpurun_out/bench_8gpu_${mode}_$RANDOM.json
 done
 tail -3 gpurun_out/bench_8gpu_scatter.err
