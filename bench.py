@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--no-alt", action="store_true", help="skip the packed-e2m1 comparison leg")
     ap.add_argument("--panel-variants", type=int, default=int(os.environ.get("VPCA_BENCH_PANEL", "8192")),
                     help="resident cohort layout: panels of this many variants (vpca_accumulate_panels); 0 = row-major")
-    ap.add_argument("--reduce", choices=["nccl", "fused", "scatter"], default=os.environ.get("VPCA_BENCH_REDUCE", "nccl"),
+    ap.add_argument("--reduce", choices=["nccl", "fused", "scatter"], default=os.environ.get("VPCA_BENCH_REDUCE", "scatter"),
                     help="N > 1: 'nccl' = one all-reduce after the Gram kernel; 'fused' = the Gram epilogue adds into every "
                          "rank's Gram over NVLink peer memory (vpca_gram_set_peers); 'scatter' = the epilogue adds into the "
                          "Gram of the rank that owns the row band, then every rank pulls the other bands (vpca_gram_gather)")
@@ -286,9 +286,20 @@ def run_b200(args):
     nat = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=0 if fused else S.data_ptr(),
                            max_multiplicity=1)
     if fused:
-        handles = [None] * world
-        dist.all_gather_object(handles, nat.exportIpcHandle())
-        nat.setPeers(handles, rank, mode="owner_rows" if scatter else "replicate")
+        ok = 1
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, nat.exportIpcHandle())
+            nat.setPeers(handles, rank, mode="owner_rows" if scatter else "replicate")
+        except Exception as exc:               # no peer access between these GPUs: every rank falls back together
+            print(f"[bench] rank {rank}: peer-memory reduce unavailable ({exc!r}); using the NCCL all-reduce", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            nat.close()
+            fused = scatter = False
+            nat = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=S.data_ptr(), max_multiplicity=1)
     P = args.panel_variants
     if P > 0:
         npan = (vpg + P - 1) // P
@@ -642,7 +653,7 @@ def run_b200(args):
                        "hbm_layout": (f"panels of {P} variants x {n} samples (vpca_accumulate_panels)" if P > 0
                                       else "row-major samples x variants"),
                        "reduce": ("fused reduce-scatter: Gram epilogue red.add into the owner of each Gram row band over NVLink peer "
-                                  "memory, then a peer-load all-gather" if scatter else
+                                  "memory, then every rank pushes its finished band to the others" if scatter else
                                   "fused: Gram epilogue red.add into every rank's Gram over NVLink peer memory" if fused
                                   else ("nccl all-reduce" if world > 1 else "none (1 GPU)")),
                        "l2_policy": f"input ({n * vpg * eb / 1e9:.2f} GB per rank) larger than L2; no flush between iterations"},

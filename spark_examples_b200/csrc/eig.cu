@@ -638,13 +638,13 @@ __global__ void __launch_bounds__(512) backtransform_kernel(const double* __rest
 // costs one pass over C (50 MB from L2 at N = 2504) instead of the N steps the reduction needs, and population
 // structure separates the top of the spectrum, so a few dozen steps reach |beta_m y_m| <= 1e-12 ||T||.
 // Five launches per step (matvec | V^T w | w -= V h | V^T w | w -= V h), step index and stop flag in device
-// memory so that kLzChunk steps replay from one CUDA graph; the host looks at the residual once per chunk.
+// memory so that kLzChunk steps replay from one CUDA graph; the host looks at the residual after a replay.
 // Anything unusual -- breakdown, slow convergence, a larger eigenvalue found by the deflated re-run that guards
 // against a missed copy of a multiple eigenvalue -- falls back to the direct reduction, which remains the
 // reference-grade path.  Every reduction has a fixed order: the result is run-to-run deterministic.
 constexpr int kLzMinN = 512;         // below this the direct reduction is as fast
 constexpr int kLzForcedMinN = 96;    // VPCA_EIG=lanczos: smallest n the chunked loop supports (tests)
-constexpr int kLzChunk = 32;      // steps per graph replay / convergence check
+constexpr int kLzChunk = 16;      // steps per graph replay (population structure converges the top pairs in <= 16)
 constexpr int kLzMaxIter = 320;   // give up (-> direct solver) beyond this
 constexpr int kLzCap = kLzMaxIter + 64;   // columns of V: main run, or k locked vectors + one verification chunk
 // st[0] = step j, st[1] = flag (0 run, 1 converged, 2 breakdown, 3 missed eigenvalue), st[2] = ticket, st[3] = step cap
@@ -928,17 +928,21 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     VPCA_TRY(cudaMemcpyAsync(w.d_lzst, hst, sizeof(hst), cudaMemcpyHostToDevice, stream));
     lz_init_kernel<<<npart, 32, 0, stream>>>(w.d_lzw, n, 0x5eedULL, part);
     nl += 1;
-    int m = 0;
+    int m = 0, m_prev = 0;
     bool converged = false;
     double rho_prev = 0.0;
-    for (int chunk = 1; chunk * kLzChunk <= std::min(max_iter, n - 1); ++chunk) {
+    const int max_chunks = std::min(max_iter, n - 1) / kLzChunk;
+    for (int chunk = 1; chunk <= max_chunks; ++chunk) {
         VPCA_TRY(cudaGraphLaunch(w.lz_graph, stream));
         m = chunk * kLzChunk;
+        nl += 5 * kLzChunk;
+        // look at the residual after every replay up to 64 steps, then after every other one
+        if (chunk > 4 && (chunk & 1) && chunk != max_chunks) continue;
         bisect_kernel<<<k, 256, 0, stream>>>(alpha, beta + 1, m, e2, w.d_evals, w.d_scal);
         invit_kernel<true><<<1, 256, 8 * (size_t)m * sizeof(double), stream>>>(alpha, beta + 1, m, k, w.d_evals, w.d_scal,
                                                                                 w.d_lu, Y);
         lz_check_kernel<<<1, 32, 0, stream>>>(part, npart, Y, m, k, w.d_scal, w.d_lzst, res, tol);
-        nl += 5 * kLzChunk + 3;
+        nl += 3;
         VPCA_TRY(cudaMemcpyAsync(hst, w.d_lzst, sizeof(hst), cudaMemcpyDeviceToHost, stream));
         VPCA_TRY(cudaMemcpyAsync(hres, res, sizeof(hres), cudaMemcpyDeviceToHost, stream));
         VPCA_TRY(cudaStreamSynchronize(stream));
@@ -948,12 +952,13 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
         }
         if (hst[1] != 0) break;   // breakdown
         const double rho = hres[0];
-        if (chunk >= 3 && rho > 1e-3) break;   // no separated top of the spectrum: hopeless within kLzMaxIter
-        if (chunk >= 2 && rho < rho_prev) {
-            const double rate = std::log(rho_prev / rho) / kLzChunk;
-            if (m + 1.5 * std::log(rho / tol) / rate > max_iter + kLzChunk) break;
+        if (m >= 96 && rho > 1e-3) break;   // no separated top of the spectrum: hopeless within kLzMaxIter
+        if (m_prev >= 32 && rho < rho_prev) {
+            const double rate = std::log(rho_prev / rho) / (m - m_prev);
+            if (m + 1.5 * std::log(rho / tol) / rate > max_iter + 2 * kLzChunk) break;
         }
         rho_prev = rho;
+        m_prev = m;
     }
     w.last_iters = m;
     if (launches) *launches += nl;

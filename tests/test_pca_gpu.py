@@ -49,7 +49,7 @@ def test_top2_eigenvectors_match_mllib_recipe(oracle, monkeypatch, n, nv, method
             assert st["eig_method"] == 1 and st["eig_iterations"] == 0
             d, e = nat.getTridiagonal()
         else:
-            assert st["eig_method"] == 2 and 32 <= st["eig_iterations"] <= 320, st
+            assert st["eig_method"] == 2 and 16 <= st["eig_iterations"] <= 320, st
             with pytest.raises(Exception):
                 nat.getTridiagonal()
     C, rs, nz_want = oracle.np_center(S)
