@@ -286,17 +286,26 @@ def run_b200(args):
     nat = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=0 if fused else S.data_ptr(),
                            max_multiplicity=1)
     if fused:
-        ok = 1
+        # every rank takes part in every collective below, whatever fails locally, so that all ranks fall back together
+        handle = None
         try:
-            handles = [None] * world
-            dist.all_gather_object(handles, nat.exportIpcHandle())
-            nat.setPeers(handles, rank, mode="owner_rows" if scatter else "replicate")
-        except Exception as exc:               # no peer access between these GPUs: every rank falls back together
-            print(f"[bench] rank {rank}: peer-memory reduce unavailable ({exc!r}); using the NCCL all-reduce", file=sys.stderr)
-            ok = 0
+            handle = nat.exportIpcHandle()
+        except Exception as exc:
+            print(f"[bench] rank {rank}: cannot export the Gram for peer access ({exc!r})", file=sys.stderr)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        ok = 0
+        if all(h is not None for h in handles):
+            try:
+                nat.setPeers(handles, rank, mode="owner_rows" if scatter else "replicate")
+                ok = 1
+            except Exception as exc:
+                print(f"[bench] rank {rank}: peer-memory reduce unavailable ({exc!r})", file=sys.stderr)
         flag = torch.tensor([ok], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
+            if rank == 0:
+                print("[bench] falling back to the NCCL all-reduce", file=sys.stderr)
             nat.close()
             fused = scatter = False
             nat = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=S.data_ptr(), max_multiplicity=1)
