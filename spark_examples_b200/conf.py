@@ -108,6 +108,7 @@ class PcaConf(GenomicsConf):
             ("synthetic", str, None, False),              # "N,V[,seed]": synthetic cohort instead of the retired API
             ("variantsPerPartition", int, 65536, False),  # rows per partition for offline/synthetic sources
             ("checkpointPath", str, None, False),         # save / resume the similarity matrix + partition watermark
+            ("vcfPath", str, None, False),                # VCF file(s), comma-separated: one variant set per file
             ("bedPath", str, None, False),                # PLINK 1 fileset prefix (.bed/.bim/.fam) as the variants source
             ("bedCountedAllele", str, "A1", False),       # which .bim allele is "variation": A1 (PLINK's minor) or A2
         ]

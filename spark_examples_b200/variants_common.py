@@ -82,6 +82,19 @@ class VariantsCommon:
             self._set_callsets([(f"synth-{i:06d}", f"S{i:06d}") for i in range(n)])
             slices = [SyntheticSlice(self.synthetic_seed, v0, min(per_part, v - v0)) for v0 in range(0, v, per_part)]
             self.data = [VariantsDataset(slices, "synth")]
+        elif conf.vcfPath.isDefined:                               # additive: VCF file(s), one variant set each
+            from . import vcf
+            paths = [p for p in conf.vcfPath().split(",") if p]
+            regions = None
+            if conf.references.isSupplied and not conf.allReferences():   # explicit --references only (the BRCA1
+                regions = vcf.parse_regions(conf.references())             # default would silently empty other files)
+            callsets: List[Tuple[str, str]] = []
+            self.data = []
+            for path in paths:
+                callsets += vcf.read_header(path)[0]
+                self.data.append(VariantsDataset(_chunk(list(vcf.read_variants(path, regions)), per_part),
+                                                 vcf.dataset_stem(path)))
+            self._set_callsets(callsets)
         elif conf.bedPath.isDefined:                               # additive: PLINK fileset on disk
             from . import plink
             counted = {"A1": plink.COUNT_A1, "A2": plink.COUNT_A2}[conf.bedCountedAllele().upper()]
@@ -97,7 +110,7 @@ class VariantsCommon:
         else:
             raise RuntimeError(
                 "The Google Genomics API the reference streams from (VariantsCommon.scala:38-66) is retired; "
-                "give --input-path FILE.jsonl, --bed-path PLINK_PREFIX or --synthetic N,V[,seed]")
+                "give --vcf-path FILE.vcf[.gz][,...], --bed-path PLINK_PREFIX, --input-path FILE.jsonl or --synthetic N,V[,seed]")
         print(f"Matrix size: {len(self.indexes)}.")                 # :48
 
     def _set_callsets(self, callsets: Sequence[Tuple[str, str]]):
