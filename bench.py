@@ -483,13 +483,31 @@ def run_b200(args):
     # ---- end to end through the public API with host inputs ----
     e2e = None
     e2e_steps = args.e2e_steps if args.e2e_steps >= 0 else min(args.steps, 5)
+    def agree(ok):
+        """True when `ok` holds on EVERY rank.  The legs below contain collectives, so a rank that could not stage its
+        host inputs (e.g. pinned memory exhausted with 8 ranks on one host) must take all ranks out of the leg with it."""
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item()) == 1
+
+    staged = False
     if e2e_steps > 0:
         try:
             off_h, idx_h, nnz = build_host_calls(torch, cells, n, vpg, dev)
             S2 = torch.zeros((n, n), dtype=torch.int32, device=dev)
             nat2 = native.NativePca(n, device=local_rank, dtype=dtype, stream=stream, d_gram=S2.data_ptr(),
                                     max_multiplicity=1)
-
+            staged = True
+        except Exception as exc:
+            e2e = {"error": "staging the host inputs failed: " + repr(exc)[:250]}
+        if not agree(staged):
+            staged = False
+            if e2e is None:
+                e2e = {"error": "skipped: another rank could not stage its host inputs"}
+    if staged:
+        try:
             def e2e_step():
                 nat2.reset()
                 nat2.accumulateCallsRaw(-1, off_h.data_ptr(), idx_h.data_ptr(), vpg)     # H2D + encode + Gram
@@ -517,9 +535,15 @@ def run_b200(args):
                 ems = float(t.item())
             # same pipeline with the 16-bit index wire format (vpca_accumulate_calls_u16): half the PCIe bytes
             u16 = None
+            idx16 = None
             if n <= 65536:
-                idx16 = torch.empty(max(nnz, 1), dtype=torch.uint16, pin_memory=True)
-                idx16.copy_(idx_h.to(torch.uint16))
+                try:
+                    idx16 = torch.empty(max(nnz, 1), dtype=torch.uint16, pin_memory=True)
+                    idx16.copy_(idx_h.to(torch.uint16))
+                except Exception as exc:
+                    idx16 = None
+                    u16 = {"error": repr(exc)[:200]}
+            if n <= 65536 and agree(idx16 is not None):
                 s30 = nat2.stats()
 
                 def e2e_step16():
@@ -551,8 +575,9 @@ def run_b200(args):
                 del idx16
             # same pipeline fed with one bitmap row per variant (vpca_accumulate_bits): N / 8 bytes per variant on the wire
             bitleg = None
+            bits_h = None
+            stride = (n + 7) // 8
             try:
-                stride = (n + 7) // 8
                 bits_h = torch.empty((vpg, stride), dtype=torch.uint8, pin_memory=True)
                 wts = (2 ** torch.arange(8, device=dev, dtype=torch.int32))
                 for c0 in range(0, vpg, 50_000):
@@ -562,6 +587,13 @@ def run_b200(args):
                     pad[:, :n] = blk
                     bits_h[c0:c1].copy_((pad.view(-1, stride, 8) * wts).sum(dim=2).to(torch.uint8))
                 torch.cuda.synchronize()
+            except Exception as exc:
+                bits_h = None
+                bitleg = {"error": repr(exc)[:200]}
+            bits_ok = agree(bits_h is not None)
+            try:
+                if not bits_ok:
+                    raise RuntimeError("skipped: a rank could not stage the bitmap rows")
 
                 def e2e_step_bits():
                     nat2.reset()
@@ -591,7 +623,8 @@ def run_b200(args):
                           "pcs_match": bool(np.allclose(pcsb[0], vecs, atol=1e-9))}
                 del bits_h
             except Exception as exc:          # never lose the headline line to an auxiliary leg
-                bitleg = {"error": repr(exc)[:200]}
+                if bitleg is None:
+                    bitleg = {"error": repr(exc)[:200]}
             e2e = {"value": n * vpg * world * e2e_steps / (ems * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": (s21["h2d_bytes"] - s20["h2d_bytes"]) // e2e_steps,
                    "d2h_bytes_per_step": (s21["d2h_bytes"] - s20["d2h_bytes"]) // e2e_steps,
