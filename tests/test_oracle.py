@@ -121,6 +121,26 @@ def test_mllib_recipe_equals_eigh_of_centered(oracle):
         oracle.mllib_principal_components(np.empty((65536, 0)), 1)
 
 
+def test_mllib_recipe_known_answer_of_upstream_pca_test(oracle):
+    """The 4 x 3 matrix and the expected components of the "pca" test in upstream Spark's RowMatrixSuite
+    (mllib/src/test/scala/org/apache/spark/mllib/linalg/distributed/RowMatrixSuite.scala -- spark-mllib is the
+    un-vendored dependency behind VariantsPca.scala:225-226; the suite is not fetchable here, so the numbers are restated
+    and re-derived: Cov = [[15, 0, 0], [0, 10, 10], [0, 10, 10]] exactly, eigenvalues 20, 15, 0).  Upstream compares
+    columns up to sign (`assertColumnEqualUpToSign`)."""
+    rows = np.array([[0.0, 1.0, 2.0], [3.0, 4.0, 5.0], [6.0, 7.0, 8.0], [9.0, 0.0, 1.0]])
+    want = np.array([[0.0, 1.0, 0.0],
+                     [np.sqrt(2.0) / 2.0, 0.0, np.sqrt(2.0) / 2.0],
+                     [np.sqrt(2.0) / 2.0, 0.0, -np.sqrt(2.0) / 2.0]])
+    m, mu = 4.0, rows.mean(axis=0)
+    cov = rows.T @ rows / (m - 1.0) - m / (m - 1.0) * np.outer(mu, mu)       # computeCovariance, as oracle.py restates it
+    assert np.allclose(cov, [[15, 0, 0], [0, 10, 10], [0, 10, 10]], atol=1e-12)
+    U, sv = oracle.mllib_principal_components(rows, 3)
+    assert np.allclose(sv, [20.0, 15.0, 0.0], atol=1e-12)
+    assert np.allclose(sv[:2] / sv.sum(), [4.0 / 7.0, 3.0 / 7.0])          # explainedVariance of the later suite versions
+    for c in range(3):
+        assert np.allclose(U[:, c], want[:, c], atol=1e-12) or np.allclose(U[:, c], -want[:, c], atol=1e-12)
+
+
 @pytest.mark.parametrize("name", ["cohort_n48_v200", "cohort_n200_v1500"])
 def test_golden_cohorts(oracle, name):
     g = np.load(GOLD / f"{name}.npz")
