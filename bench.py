@@ -184,6 +184,26 @@ def cpu_blas_sample(n, nv=65_536, threads=None):
             "checksum": int(np.trace(G.astype(np.float64)))}
 
 
+def cpu_eigensolve_sample(S_host, threads=None):
+    """Centering + the MLlib recipe (Cov, LAPACK dgesdd through numpy.linalg.svd, first 2 columns of U) on the host:
+    oracle.compute_pca = VariantsPca.scala:198-227 restated.  Timed once on the full N x N matrix."""
+    from oracle import oracle
+    threads = threads or host_threads()
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=threads)
+    except Exception:
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        t0 = time.perf_counter()
+        U, sv = oracle.compute_pca(S_host, 2)
+        dt = time.perf_counter() - t0
+    return {"seconds": dt, "cores": threads, "n": int(S_host.shape[0]),
+            "what": "oracle.compute_pca: FP64 centering + Cov = C^T C/(m-1) - ... + numpy.linalg.svd (LAPACK dgesdd), "
+                    "first 2 columns of U"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -681,6 +701,10 @@ def run_b200(args):
             cpu["strong_cpu_blas"] = cpu_blas_sample(n)
         except Exception as exc:
             cpu["strong_cpu_blas"] = {"error": repr(exc)[:200]}
+        try:                                   # a-4 + a-5 on the host: what vpca_compute_pca (eig_ms above) replaces
+            cpu["eigensolve"] = cpu_eigensolve_sample(S.cpu().numpy())
+        except Exception as exc:
+            cpu["eigensolve"] = {"error": repr(exc)[:200]}
 
     if rank == 0:
         line = {
