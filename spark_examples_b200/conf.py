@@ -109,6 +109,7 @@ class PcaConf(GenomicsConf):
             ("variantsPerPartition", int, 65536, False),  # rows per partition for offline/synthetic sources
             ("checkpointPath", str, None, False),         # save / resume the similarity matrix + partition watermark
             ("vcfPath", str, None, False),                # VCF file(s), comma-separated: one variant set per file
+            ("callsParquetPath", str, None, False),       # Parquet file of calls rows (parquet_calls.py): RDD[Seq[Int]] at rest
             ("bedPath", str, None, False),                # PLINK 1 fileset prefix (.bed/.bim/.fam) as the variants source
             ("bedCountedAllele", str, "A1", False),       # which .bim allele is "variation": A1 (PLINK's minor) or A2
         ]

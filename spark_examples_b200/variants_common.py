@@ -49,7 +49,7 @@ class BedSlice:
 
 class VariantsDataset:
     """Stand-in for one `RDD[Variant]`: an ordered list of partitions.  A partition is a list of `Variant`
-    records, a `CallsBatch`, a `SyntheticSlice` or a `BedSlice`."""
+    records, a `CallsBatch`, a `SyntheticSlice`, a `BedSlice` or a `parquet_calls.ParquetSlice`."""
 
     def __init__(self, partitions: Sequence[object], variantSetId: str = ""):
         self.partitions = list(partitions)
@@ -95,6 +95,11 @@ class VariantsCommon:
                 self.data.append(VariantsDataset(_chunk(list(vcf.read_variants(path, regions)), per_part),
                                                  vcf.dataset_stem(path)))
             self._set_callsets(callsets)
+        elif conf.callsParquetPath.isDefined:                      # additive: calls rows at rest, one row group = one partition
+            from . import parquet_calls
+            pf = parquet_calls.CallsParquet(conf.callsParquetPath())
+            self._set_callsets(pf.callsets)
+            self.data = [VariantsDataset(pf.slices, "parquet")]
         elif conf.bedPath.isDefined:                               # additive: PLINK fileset on disk
             from . import plink
             counted = {"A1": plink.COUNT_A1, "A2": plink.COUNT_A2}[conf.bedCountedAllele().upper()]
@@ -110,7 +115,8 @@ class VariantsCommon:
         else:
             raise RuntimeError(
                 "The Google Genomics API the reference streams from (VariantsCommon.scala:38-66) is retired; "
-                "give --vcf-path FILE.vcf[.gz][,...], --bed-path PLINK_PREFIX, --input-path FILE.jsonl or --synthetic N,V[,seed]")
+                "give --vcf-path FILE.vcf[.gz][,...], --bed-path PLINK_PREFIX, --calls-parquet-path FILE, --input-path FILE.jsonl "
+                "or --synthetic N,V[,seed]")
         print(f"Matrix size: {len(self.indexes)}.")                 # :48
 
     def _set_callsets(self, callsets: Sequence[Tuple[str, str]]):

@@ -29,6 +29,7 @@ from . import native
 from .conf import PcaConf
 from .jformat import jdouble
 from .records import Call, CallData, Variant
+from .parquet_calls import ParquetSlice
 from .variants_common import BedSlice, CallsBatch, SyntheticSlice, VariantsCommon, VariantsDataset
 
 
@@ -118,12 +119,15 @@ class CallsRdd:
             if isinstance(p, BedSlice):
                 from . import plink
                 p = CallsBatch(*plink.rows_to_calls(p.rows(), self.n_samples, p.counted))
+            if isinstance(p, ParquetSlice):
+                p = p.load()
             for v in range(len(p.offsets) - 1):
                 rows.append(p.idx[p.offsets[v]:p.offsets[v + 1]].tolist())
         return rows
 
     def count(self) -> int:
-        return sum(p.nv if isinstance(p, (SyntheticSlice, BedSlice)) else len(p.offsets) - 1 for p in self.partitions)
+        return sum(p.nv if isinstance(p, (SyntheticSlice, BedSlice, ParquetSlice)) else len(p.offsets) - 1
+                   for p in self.partitions)
 
 
 class SimilarityMatrix:
@@ -175,7 +179,7 @@ class VariantsPcaDriver:
             return np.float32(float(af[0])) >= np.float32(min_af)   # .get(0).toFloat >= minAlleleFrequency
 
         def fn(part):
-            if isinstance(part, (CallsBatch, SyntheticSlice, BedSlice)):
+            if isinstance(part, (CallsBatch, SyntheticSlice, BedSlice, ParquetSlice)):
                 raise ValueError("--min-allele-frequency needs Variant records (INFO field AF)")
             return [v for v in part if keep(v)]
         return data.map_partitions(fn)
@@ -217,7 +221,7 @@ class VariantsPcaDriver:
         if variantSetCount == 1:
             parts = []
             for part in data[0].partitions:
-                if isinstance(part, (CallsBatch, SyntheticSlice, BedSlice)):
+                if isinstance(part, (CallsBatch, SyntheticSlice, BedSlice, ParquetSlice)):
                     parts.append(part)                          # already RDD[Seq[Int]] rows (or their packed form)
                 else:
                     parts.append(_rows_to_batch([extractCallInfo(v, mapping) for v in part]))
@@ -239,6 +243,8 @@ class VariantsPcaDriver:
             if isinstance(part, SyntheticSlice):
                 self._accumulate_synthetic(nat, part)
                 continue
+            if isinstance(part, ParquetSlice):
+                part = part.load()                              # row group -> CSR rows, no per-record work
             try:
                 if isinstance(part, BedSlice):
                     nat.accumulateBed(pid, part.rows(), part.counted)
