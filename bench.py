@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--reduce", choices=["nccl", "fused", "scatter"], default=os.environ.get("VPCA_BENCH_REDUCE", "scatter"),
                     help="N > 1: 'nccl' = one all-reduce after the Gram kernel; 'fused' = the Gram epilogue adds into every "
                          "rank's Gram over NVLink peer memory (vpca_gram_set_peers); 'scatter' = the epilogue adds into the "
-                         "Gram of the rank that owns the row band, then every rank pulls the other bands (vpca_gram_gather)")
+                         "Gram of the rank that owns the row band, then every rank pushes its band to the others (vpca_gram_gather)")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 5); 0 disables the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eig-check", action="store_true")
