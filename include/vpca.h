@@ -13,15 +13,22 @@
  *     CUDA device pointer where the parameter name starts with `d_`.
  *   - every function returns VPCA_OK (0) or a negative vpca_status; vpca_last_error() gives the text.
  *     No C++ exception crosses the ABI.
- *   - a vpca_ctx owns one GPU's worth of state (device buffers, streams, staging).  Calls on one ctx
- *     are serialised internally, so Spark task threads may call accumulate/commit concurrently.
- *   - all device work is ordered on the stream given in vpca_config.stream (or a private stream);
- *     functions that return host data synchronise that stream before returning.
+ *   - a vpca_ctx owns one GPU's worth of state (device buffers, streams, staging); a vpca_pool owns one ctx per GPU
+ *     of the box and is what one driver JVM holds (the reference's process model, VariantsPca.scala:38-50).
+ *   - threading: accumulate_* / commit / abort may be called concurrently from many threads (the task threads of
+ *     `mapPartitions`, VariantsPca.scala:184-189).  Host-input calls run on one of `staging_lanes` private lanes
+ *     (streams + staging buffers): the context mutex is held for bookkeeping only, never across a copy, a kernel or
+ *     a synchronisation, so the H2D copy and encode of one task overlap the Gram kernel of another.  One partition
+ *     id belongs to one thread at a time (spark.speculation off).  reset / finalize / get_* / compute_pca are
+ *     driver-side calls made when no accumulate call is in flight.
+ *   - device-resident input (on_device tiles, panels) and everything driver-side is ordered on the stream given in
+ *     vpca_config.stream (or a private stream); functions that return host data synchronise before returning.
  *   - there is no CPU fallback: vpca_create fails with VPCA_ERR_CUDA when no sm_100 device is usable.
  */
 #ifndef VPCA_H_
 #define VPCA_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -29,7 +36,7 @@ extern "C" {
 #endif
 
 #define VPCA_VERSION_MAJOR 0
-#define VPCA_VERSION_MINOR 1
+#define VPCA_VERSION_MINOR 2
 
 typedef enum vpca_status {
     VPCA_OK = 0,
@@ -37,7 +44,8 @@ typedef enum vpca_status {
     VPCA_ERR_INDEX_OUT_OF_RANGE = -2, /* sample index outside [0, n_samples): the reference would throw
                                          (VariantsPca.scala:59 NoSuchElementException / :188 Breeze bounds) */
     VPCA_ERR_CUDA = -3,
-    VPCA_ERR_NCCL = -4,     /* reserved: collectives are driven by the host */
+    VPCA_ERR_NCCL = -4,     /* the cross-GPU reduction (`reduceByKey`, VariantsPca.scala:190) cannot run: no peer path
+                               between two devices, or a peer mapping failed */
     VPCA_ERR_OVERFLOW = -5, /* an int32 similarity count (VariantsPca.scala:185) could exceed 2^31-1,
                                or a multiplicity does not fit the encoding */
     VPCA_ERR_STATE = -6,
@@ -70,12 +78,18 @@ typedef struct vpca_config {
                                   reference rule VariantsPca.scala:58; 2 = dosage / a sample listed
                                   twice).  0 -> 2.  Used for the overflow guards.                     */
     int32_t partitions_in_flight; /* staging Grams for uncommitted partitions; 0 -> 4                 */
-    int32_t reserved0;
+    int32_t staging_lanes;     /* host-input calls that may run concurrently on this GPU (each lane: two
+                                  streams + double-buffered staging, ~1 GB); 0 -> 2, at most 16            */
     int64_t chunk_variants;    /* variants per device staging chunk for CSR input; 0 -> automatic     */
     int64_t chunk_nnz;         /* sample-index entries per device staging chunk; 0 -> automatic       */
     void* stream;              /* cudaStream_t to order all work on; NULL -> private stream           */
     void* d_gram;              /* optional caller-owned device buffer of n_samples^2 int32 (e.g. the
                                   tensor the host all-reduces with NCCL); NULL -> library-owned       */
+    int32_t gram_band_row0;    /* gram_band_rows > 0: this context stores ONLY rows [row0, row0 + rows) of the   */
+    int32_t gram_band_rows;    /* Gram -- the band it owns in VPCA_PEER_OWNER_ROWS mode (vpca_owner_row_bands);
+                                  for cohorts whose full Gram should not be replicated per GPU (100 k
+                                  samples: 40 GB; the reference's sizing note at VariantsPca.scala:176-177).
+                                  0 -> the whole matrix                                                 */
 } vpca_config;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -88,6 +102,13 @@ int vpca_destroy(vpca_ctx* ctx);
 const char* vpca_last_error(const vpca_ctx* ctx);
 /* Zero the Gram and forget all partitions: start a new analysis on the same ctx. */
 int vpca_reset(vpca_ctx* ctx);
+/* Wait for everything enqueued on the context's stream (kernels of device-resident input, commits, gathers). */
+int vpca_synchronize(vpca_ctx* ctx);
+/* Pinned (page-locked, portable) host memory for callers that stage rows themselves -- the JNI binding wraps it in
+ * direct ByteBuffers so that Spark tasks pack RDD[Seq[Int]] rows (VariantsPca.scala:153-168) straight into memory the
+ * copy engines read at full PCIe rate, with no JVM array pinning. */
+int vpca_host_alloc(size_t bytes, void** out);
+int vpca_host_free(void* p);
 
 /* ---- encode (VariantsPca.scala:56-60 extractCallInfo, :153-168 getCallsRdd) ---------------------
  * Host-side records arrive already projected to `RDD[Seq[Int]]` rows (CSR: row v = the sample indices
@@ -157,6 +178,11 @@ int vpca_gram_device_ptr(vpca_ctx* ctx, void** d_gram);
  * vpca_peer_barrier enqueues an all-rank barrier over peer-mapped flags on the context's stream. */
 int vpca_gram_export_ipc(vpca_ctx* ctx, void* handle64);
 int vpca_gram_set_peers(vpca_ctx* ctx, const void* handles, int32_t world, int32_t rank);
+/* The same wiring when ONE process owns all `world` contexts (the reference's process model: one driver JVM whose task
+ * threads share the executors' state, VariantsPca.scala:38-50, :184-190): peer access is enabled between the devices and
+ * ctxs[r] becomes rank r.  Contexts may share a device (a 1-GPU box exercises the same kernels).  VPCA_ERR_NCCL when two
+ * of the devices have no peer path.  vpca_pool_create does this for the contexts it creates. */
+int vpca_gram_set_peers_local(vpca_ctx* const* ctxs, int32_t world);
 int vpca_peer_barrier(vpca_ctx* ctx);
 /* How the fused epilogue reduces across the peers set above:
  *   VPCA_PEER_REPLICATE (default): every flush goes into the Gram of every rank -- world x the remote traffic, no
@@ -169,6 +195,15 @@ int vpca_peer_barrier(vpca_ctx* ctx);
 enum { VPCA_PEER_REPLICATE = 0, VPCA_PEER_OWNER_ROWS = 1 };
 int vpca_gram_set_peer_mode(vpca_ctx* ctx, int32_t mode);
 int vpca_gram_gather(vpca_ctx* ctx);
+/* Row bands of VPCA_PEER_OWNER_ROWS: rank q owns Gram rows [row_end[q-1], row_end[q]) (row_end[-1] = 0).  A context
+ * created with vpca_config.gram_band_row0 / gram_band_rows set to its band stores nothing else: its kernels still
+ * compute the whole lower triangle of their variant shard, but every flush leaves for the owner of its row, the bands
+ * ARE the result (no gather), and vpca_get_gram_band reads them.  This is the biobank-scale form (100 k samples: a
+ * 40 GB matrix, 2.6 - 14 GB per GPU at 8 GPUs) of `reduceByKey` (VariantsPca.scala:190). */
+int vpca_owner_row_bands(int32_t n_samples, int32_t world, int32_t* row_end /* world entries */);
+/* Rows [row0, row0 + rows) of the Gram as this context holds them (lower triangle meaningful before finalize;
+ * n_samples int32 per row). */
+int vpca_get_gram_band(vpca_ctx* ctx, int32_t row0, int32_t rows, int32_t* out);
 
 /* Mirror the lower triangle into the upper one: after this the buffer equals the reference's
  * similarity matrix with all N^2 entries present (:189-190). */
@@ -179,8 +214,12 @@ int vpca_get_gram(vpca_ctx* ctx, int32_t* out);
 /* Checkpoint / resume of a long accumulation: copy out / restore the Gram as accumulated so far
  * (committed partitions only, NOT finalized: lower triangle meaningful).  After vpca_load_partial_gram accumulation
  * continues on top of the restored counts; the caller keeps the watermark (which partitions are in it). */
-int vpca_get_partial_gram(vpca_ctx* ctx, int32_t* out);
-int vpca_load_partial_gram(vpca_ctx* ctx, const int32_t* gram);
+int vpca_get_partial_gram(vpca_ctx* ctx, int32_t* out, int64_t* variants_in_gram /* may be NULL */);
+/* variants_in_gram: how many variants the restored counts stand for (what vpca_get_partial_gram reported); they keep
+ * counting against the int32 bound of a similarity count (VariantsPca.scala:185). */
+int vpca_load_partial_gram(vpca_ctx* ctx, const int32_t* gram, int64_t variants_in_gram);
+/* Variants folded into the Gram so far (committed partitions + direct input); negative vpca_status on error. */
+int64_t vpca_variant_count(vpca_ctx* ctx);
 /* Load a Gram (checkpoint restore / tests); marks it finalized. */
 int vpca_set_gram(vpca_ctx* ctx, const int32_t* gram);
 
@@ -197,6 +236,42 @@ int vpca_compute_pca(vpca_ctx* ctx, int32_t k, double* vecs, double* evals, int3
 int vpca_get_centered(vpca_ctx* ctx, double* out);
 /* Tridiagonal form of the centered matrix after the last vpca_compute_pca (diag: n, offdiag: n-1). */
 int vpca_get_tridiagonal(vpca_ctx* ctx, double* diag, double* offdiag);
+
+/* ---- one process, all GPUs of the box (SURVEY 8b "process model") --------------------------------------------------
+ * A vpca_pool is what `class VariantsPcaDriver` holds on a multi-GPU host: one vpca_ctx per GPU, wired with
+ * vpca_gram_set_peers_local in VPCA_PEER_OWNER_ROWS mode (VPCA_PEER_REPLICATE when n_samples < 64 x n_gpus).  Spark
+ * partition p is served by GPU p % n_gpus (`mapPartitionsWithIndex`, VariantsPca.scala:184); all entry points below
+ * except create / destroy / reset / reduce / get / compute may be called concurrently from the task threads.
+ *   vpca_pool_create(cfg, n_gpus, devices, &pool)      cfg.device / stream / d_gram / gram_band_* are ignored
+ *   task p:  vpca_pool_accumulate_* (pool, p, ...) ...  vpca_pool_commit(pool, p)   |  vpca_pool_abort(pool, p)
+ *   driver:  vpca_pool_reduce_and_finalize(pool)        `reduceByKey(_ + _)` (:190): every commit has already been
+ *                                                       added into the owners of its Gram rows over NVLink; this is the
+ *                                                       closing barrier + all-gather of the bands + symmetrize
+ *            vpca_pool_get_gram / vpca_pool_compute_pca  (:189-190, :198-227), served by GPU 0 of the pool */
+typedef struct vpca_pool vpca_pool;
+int vpca_pool_create(const vpca_config* cfg, int32_t n_gpus, const int32_t* devices /* NULL: 0 .. n_gpus-1 */,
+                     vpca_pool** out);
+int vpca_pool_destroy(vpca_pool* pool);
+int32_t vpca_pool_size(const vpca_pool* pool);
+/* The context that serves partition_id (partition_id < 0: GPU 0). */
+vpca_ctx* vpca_pool_ctx(vpca_pool* pool, int64_t partition_id);
+const char* vpca_pool_last_error(const vpca_pool* pool);
+int vpca_pool_reset(vpca_pool* pool);
+int vpca_pool_accumulate_calls(vpca_pool* pool, int64_t partition_id, const int64_t* offsets, const int32_t* sample_idx,
+                               int64_t nv);
+int vpca_pool_accumulate_calls_u16(vpca_pool* pool, int64_t partition_id, const int64_t* offsets,
+                                   const uint16_t* sample_idx, int64_t nv);
+int vpca_pool_accumulate_bits(vpca_pool* pool, int64_t partition_id, const uint8_t* bits, int64_t nv, int64_t stride_bytes);
+int vpca_pool_accumulate_bed(vpca_pool* pool, int64_t partition_id, const uint8_t* rows, int64_t nv, int64_t stride_bytes,
+                             int32_t counted_allele);
+int vpca_pool_commit(vpca_pool* pool, int64_t partition_id);
+int vpca_pool_abort(vpca_pool* pool, int64_t partition_id);
+int vpca_pool_reduce_and_finalize(vpca_pool* pool);
+int vpca_pool_get_gram(vpca_pool* pool, int32_t* out);
+int vpca_pool_compute_pca(vpca_pool* pool, int32_t k, double* vecs, double* evals, int32_t* non_zero_rows);
+/* Sum of the per-GPU statistics (times: the maximum). */
+struct vpca_stats;
+int vpca_pool_get_stats(vpca_pool* pool, struct vpca_stats* out);
 
 /* ---- synthetic cohort (stands in for the retired Genomics API ingestion, rdd/VariantsRDD.scala:187-236;
  *      specification in DESIGN.md "Synthetic generator") --------------------------------------------------

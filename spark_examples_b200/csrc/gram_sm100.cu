@@ -836,7 +836,7 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
 
     GramArgs args{};
     args.S = d_S;
-    args.num_peers = (plan.num_peers > 1 && d_S == plan.peer_S[plan.peer_rank]) ? plan.num_peers : 0;
+    args.num_peers = (plan.num_peers > 1 && d_S == plan.peer_base[plan.peer_rank]) ? plan.num_peers : 0;
     for (int d = 0; d < kMaxPeers; ++d) args.peer[d] = d < plan.num_peers ? plan.peer_S[d] : nullptr;
     args.peer_mode = plan.peer_mode;
     for (int d = 0; d < kMaxPeers; ++d) args.own_end[d] = plan.own_end[d];

@@ -1,10 +1,20 @@
 // libvpca C ABI (include/vpca.h): context management, host<->device staging and the call sequence
-// encode -> Gram -> (host-driven all-reduce) -> symmetrize -> centering -> eigensolve.
+// encode -> Gram -> (cross-GPU reduce) -> symmetrize -> centering -> eigensolve.
 // Mirrors the method set of the reference's VariantsPcaDriver
 // (src/main/scala/com/google/cloud/genomics/spark/examples/VariantsPca.scala:81-286); see vpca.h for the mapping.
+//
+// Threading model (the reference runs the bodies of `mapPartitions` concurrently, one task thread per core,
+// VariantsPca.scala:184-189): host-input calls (accumulate_calls / _u16 / _bits / _bed / dense-from-host) take one
+// of `staging_lanes` LANES -- a private stream pair, double-buffered staging and a private Gram schedule -- and hold
+// the context mutex only for bookkeeping, never across a copy, a kernel or a stream synchronisation.  So the H2D copy
+// and encode of one task overlap the Gram kernel of another; a partition's staging Gram (slot) is private to the
+// task that owns the partition id, and `commit` folds it into the Gram with integer adds on the context's stream.
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -18,7 +28,9 @@ using namespace vpca;
 
 namespace {
 thread_local std::string tls_error;
-}
+thread_local const vpca_ctx* tls_error_ctx = nullptr;
+thread_local std::string tls_error_copy;
+}   // namespace
 
 struct vpca_ctx {
     vpca_config cfg{};
@@ -28,12 +40,12 @@ struct vpca_ctx {
     int num_pc = 2;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t copy_stream = nullptr;
     int32_t* d_S = nullptr;
     bool own_S = false;
+    int band_row0 = 0, band_rows = 0;   // rows of the Gram this context stores (band_rows == n: all of them)
     bool finalized = false;
     bool pca_done = false;
-    GramPlan plan;
+    GramPlan plan;        // schedule state of the launches on `stream` (device-resident input)
     EigWork eig;
     bool eig_ready = false;
 
@@ -41,26 +53,44 @@ struct vpca_ctx {
         int64_t pid = -1;
         int32_t* d_S = nullptr;
         bool used = false;
+        bool busy = false;             // a call of the owning task is in flight
+        bool fresh = false;            // still to be zeroed by its first batch
         int64_t nv = 0;
+        cudaEvent_t ev_free = nullptr; // recorded after the commit that last read the slot
     };
     std::vector<Slot> slots;
 
-    // CSR / dense staging, double buffered
+    // One lane = everything a host-input call needs to run without the other lanes: streams, double-buffered CSR /
+    // dense staging, error flags and its own Gram schedule (the speed-weighted stream-K shares must not change under
+    // a running kernel, so they are per stream).
+    struct Lane {
+        cudaStream_t stream = nullptr, copy_stream = nullptr;
+        int64_t* d_off[2] = {nullptr, nullptr};
+        int32_t* d_idx[2] = {nullptr, nullptr};
+        void* d_x[2] = {nullptr, nullptr};
+        cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+        cudaEvent_t ev_done[2] = {nullptr, nullptr};
+        cudaEvent_t ev_order = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+        int* d_flags = nullptr;
+        int* h_flags = nullptr;
+        GramPlan plan;
+        bool ready = false, busy = false;
+    };
+    std::vector<Lane> lanes;
     int64_t chunk_variants = 0, chunk_nnz = 0;
     int64_t panel = 8192;   // cells per panel row of the internal dense staging tiles (VPCA_PANEL)
-    int64_t* d_off[2] = {nullptr, nullptr};
-    int32_t* d_idx[2] = {nullptr, nullptr};
-    void* d_x[2] = {nullptr, nullptr};
-    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
-    cudaEvent_t ev_done[2] = {nullptr, nullptr};
-    int* d_flags = nullptr;
-    int* h_flags = nullptr;
+
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_e0 = nullptr, ev_e1 = nullptr;
     bool gram_timed = false, eig_timed = false;
 
-    int64_t total_variants = 0;   // committed + direct
+    int64_t total_variants = 0;      // committed + direct
+    int64_t inflight_variants = 0;   // staged in slots, not yet committed
     vpca_stats st{};
+    std::atomic<int64_t> c_launches{0}, c_gram{0}, c_h2d{0}, c_d2h{0};
+    std::atomic<float> lane_gram_ms{0.f};
     std::mutex mu;
+    std::condition_variable cv;
+    std::mutex err_mu;
     std::string err;
 };
 
@@ -72,8 +102,12 @@ int fail(vpca_ctx* ctx, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (ctx) ctx->err = buf;
     tls_error = buf;
+    tls_error_ctx = ctx;
+    if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->err_mu);
+        ctx->err = buf;
+    }
     return code;
 }
 
@@ -85,17 +119,64 @@ int fail(vpca_ctx* ctx, int code, const char* fmt, ...) {
                         __LINE__);                                                                              \
     } while (0)
 
-int check_overflow(vpca_ctx* ctx, int64_t extra_variants) {
-    // every similarity count is at most (#variants) * max_mult^2 and must stay a Java Int (VariantsPca.scala:185)
-    const long double worst = (long double)(ctx->total_variants + extra_variants) * ctx->max_mult * ctx->max_mult;
+// every similarity count is at most (#variants) * max_mult^2 and must stay a Java Int (VariantsPca.scala:185).
+// `extra` = variants about to be added on top of everything committed AND everything staged in uncommitted partitions.
+int check_overflow(vpca_ctx* ctx, int64_t extra) {
+    const long double worst =
+        (long double)(ctx->total_variants + ctx->inflight_variants + extra) * ctx->max_mult * ctx->max_mult;
     if (worst > 2147483647.0L)
         return fail(ctx, VPCA_ERR_OVERFLOW, "%lld variants x multiplicity %d^2 could overflow an int32 similarity count",
-                    (long long)(ctx->total_variants + extra_variants), ctx->max_mult);
+                    (long long)(ctx->total_variants + ctx->inflight_variants + extra), ctx->max_mult);
     return VPCA_OK;
 }
 
-int ensure_staging(vpca_ctx* ctx) {
-    if (ctx->d_x[0] != nullptr) return VPCA_OK;
+void free_lane(vpca_ctx::Lane& L) {
+    if (L.stream) cudaStreamSynchronize(L.stream);
+    if (L.copy_stream) cudaStreamSynchronize(L.copy_stream);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(L.d_off[b]);
+        cudaFree(L.d_idx[b]);
+        cudaFree(L.d_x[b]);
+        if (L.ev_copy[b]) cudaEventDestroy(L.ev_copy[b]);
+        if (L.ev_done[b]) cudaEventDestroy(L.ev_done[b]);
+        L.d_off[b] = nullptr;
+        L.d_idx[b] = nullptr;
+        L.d_x[b] = nullptr;
+        L.ev_copy[b] = L.ev_done[b] = nullptr;
+    }
+    for (cudaEvent_t* ev : {&L.ev_order, &L.ev_t0, &L.ev_t1})
+        if (*ev) {
+            cudaEventDestroy(*ev);
+            *ev = nullptr;
+        }
+    cudaFree(L.d_flags);
+    L.d_flags = nullptr;
+    if (L.h_flags) cudaFreeHost(L.h_flags);
+    L.h_flags = nullptr;
+    gram_plan_free(L.plan);
+    if (L.copy_stream) cudaStreamDestroy(L.copy_stream);
+    if (L.stream) cudaStreamDestroy(L.stream);
+    L.copy_stream = L.stream = nullptr;
+    L.ready = false;
+}
+
+void copy_peers(const GramPlan& from, GramPlan& to) {
+    to.num_peers = from.num_peers;
+    to.peer_rank = from.peer_rank;
+    to.peer_mode = from.peer_mode;
+    for (int d = 0; d < 16; ++d) {
+        to.peer_S[d] = from.peer_S[d];
+        to.peer_flags[d] = from.peer_flags[d];
+        to.own_end[d] = from.own_end[d];
+    }
+}
+
+void sync_peers_to_lanes(vpca_ctx* ctx) {
+    for (auto& L : ctx->lanes) copy_peers(ctx->plan, L.plan);
+}
+
+void staging_geometry(vpca_ctx* ctx) {
+    if (ctx->chunk_variants != 0) return;
     const int n = ctx->n, bits = ctx->elem_bits;
     int64_t cv = ctx->cfg.chunk_variants;
     if (cv <= 0) {
@@ -112,46 +193,106 @@ int ensure_staging(vpca_ctx* ctx) {
     cz = std::max<int64_t>(cz, 1024);
     ctx->chunk_variants = cv;
     ctx->chunk_nnz = cz;
-    for (int b = 0; b < 2; ++b) {
-        CUDA_OK(ctx, cudaMalloc(&ctx->d_off[b], (size_t)(cv + 1) * sizeof(int64_t)));
-        CUDA_OK(ctx, cudaMalloc(&ctx->d_idx[b], (size_t)cz * sizeof(int32_t)));
-        CUDA_OK(ctx, cudaMalloc(&ctx->d_x[b], (size_t)n * (size_t)cv * bits / 8));
-        CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[b], cudaEventDisableTiming));
-        CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_done[b], cudaEventDisableTiming));
+}
+
+// Allocates the lane's streams and staging buffers on first use; on any failure everything is released again, so a
+// later call retries from scratch instead of running on half a lane.
+int ensure_lane(vpca_ctx* ctx, vpca_ctx::Lane& L) {
+    if (L.ready) return VPCA_OK;
+    const int n = ctx->n, bits = ctx->elem_bits;
+    const int64_t cv = ctx->chunk_variants, cz = ctx->chunk_nnz;
+    cudaError_t e = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&L.copy_stream, cudaStreamNonBlocking);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaMalloc(&L.d_off[b], (size_t)(cv + 1) * sizeof(int64_t));
+        if (e == cudaSuccess) e = cudaMalloc(&L.d_idx[b], (size_t)cz * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&L.d_x[b], (size_t)n * (size_t)cv * bits / 8);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&L.ev_copy[b], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&L.ev_done[b], cudaEventDisableTiming);
     }
-    CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&L.ev_order, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&L.ev_t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&L.ev_t1);
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_flags, sizeof(int));
+    if (e == cudaSuccess) e = cudaHostAlloc(&L.h_flags, sizeof(int), cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        free_lane(L);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? VPCA_ERR_NOMEM : VPCA_ERR_CUDA, "staging lane: %s",
+                    cudaGetErrorString(e));
+    }
+    copy_peers(ctx->plan, L.plan);
+    L.ready = true;
     return VPCA_OK;
 }
 
-int launch_gram(vpca_ctx* ctx, const void* d_x, int64_t nv, int64_t ld, int64_t panel, int32_t* d_target) {
-    // fp32 TMEM accumulation (bf16 / e2m1) is exact only below 2^24: bound the variants one launch may fold
+// A free lane, blocking while all are taken.  Also orders the lane's stream after everything enqueued on the context's
+// stream so far (a preceding vpca_reset / vpca_load_partial_gram).
+struct LaneGuard {
+    vpca_ctx* ctx;
+    vpca_ctx::Lane* lane = nullptr;
+    int rc = VPCA_OK;
+    explicit LaneGuard(vpca_ctx* c) : ctx(c) {
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        staging_geometry(ctx);
+        ctx->cv.wait(lk, [&] {
+            for (auto& L : ctx->lanes)
+                if (!L.busy) return true;
+            return false;
+        });
+        for (auto& L : ctx->lanes)
+            if (!L.busy) {
+                lane = &L;
+                break;
+            }
+        lane->busy = true;
+        rc = ensure_lane(ctx, *lane);
+        if (rc == VPCA_OK) {
+            cudaError_t e = cudaEventRecord(lane->ev_order, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(lane->stream, lane->ev_order, 0);
+            if (e != cudaSuccess) rc = fail(ctx, VPCA_ERR_CUDA, "lane ordering: %s", cudaGetErrorString(e));
+        }
+    }
+    ~LaneGuard() {
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            lane->busy = false;
+        }
+        ctx->cv.notify_one();
+    }
+};
+
+int launch_gram(vpca_ctx* ctx, GramPlan& plan, cudaStream_t stream, cudaEvent_t t0, cudaEvent_t t1, const void* d_x,
+                int64_t nv, int64_t ld, int64_t panel, int32_t* d_target) {
+    // fp32 TMEM accumulation (bf16 / e2m1) is exact only below 2^24: bound the variants one launch may fold.
+    // vpca_create guarantees that the bound is at least one panel.
     int64_t limit = nv;
     if (ctx->elem_bits != 8) {
         limit = (int64_t)(16777216ll / ((int64_t)ctx->max_mult * ctx->max_mult));
         const int64_t q = panel > 0 ? panel : 128;
-        limit = std::max<int64_t>(q, (limit / q) * q);
+        limit = (limit / q) * q;
+        if (limit <= 0)
+            return fail(ctx, VPCA_ERR_UNSUPPORTED, "max_multiplicity %d leaves no exact fp32 accumulation window for panels of "
+                        "%lld variants", ctx->max_mult, (long long)q);
     }
     for (int64_t v0 = 0; v0 < nv; v0 += limit) {
         const int64_t cnt = std::min<int64_t>(limit, nv - v0);
         std::string msg;
-        cudaEventRecord(ctx->ev_t0, ctx->stream);
+        cudaEventRecord(t0, stream);
         // sub-launches start on a panel boundary (panel layout) or at column v0 (row-major)
         const size_t byte_off = panel > 0 ? (size_t)(v0 / panel) * (size_t)ctx->n * (size_t)panel * ctx->elem_bits / 8
                                           : (size_t)v0 * ctx->elem_bits / 8;
-        cudaError_t e = gram_accumulate(ctx->plan, static_cast<const char*>(d_x) + byte_off, ctx->elem_bits, ctx->n, cnt, ld,
-                                        panel, d_target, ctx->stream, &msg);
-        cudaEventRecord(ctx->ev_t1, ctx->stream);
+        cudaError_t e = gram_accumulate(plan, static_cast<const char*>(d_x) + byte_off, ctx->elem_bits, ctx->n, cnt, ld,
+                                        panel, d_target, stream, &msg);
+        cudaEventRecord(t1, stream);
         if (e != cudaSuccess)
             return fail(ctx, VPCA_ERR_CUDA, "Gram launch failed: %s %s", cudaGetErrorString(e), msg.c_str());
-        ctx->gram_timed = true;
-        ctx->st.gram_launches += 1;
-        ctx->st.kernel_launches += 1;
+        ctx->c_gram += 1;
+        ctx->c_launches += 1;
     }
-    ctx->st.gram_cta_group = ctx->plan.cta_group;
-    ctx->st.gram_resident = ctx->plan.last_resident;
     return VPCA_OK;
 }
 
+// Caller holds ctx->mu.
 vpca_ctx::Slot* find_slot(vpca_ctx* ctx, int64_t pid, bool create, int* rc) {
     *rc = VPCA_OK;
     for (auto& s : ctx->slots)
@@ -161,17 +302,17 @@ vpca_ctx::Slot* find_slot(vpca_ctx* ctx, int64_t pid, bool create, int* rc) {
         if (!s.used) {
             if (s.d_S == nullptr) {
                 cudaError_t e = cudaMalloc(&s.d_S, (size_t)ctx->n * ctx->n * sizeof(int32_t));
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.ev_free, cudaEventDisableTiming);
                 if (e != cudaSuccess) {
+                    cudaFree(s.d_S);
+                    s.d_S = nullptr;
                     *rc = fail(ctx, VPCA_ERR_NOMEM, "cudaMalloc of a partition Gram failed: %s", cudaGetErrorString(e));
                     return nullptr;
                 }
             }
-            cudaError_t e = cudaMemsetAsync(s.d_S, 0, (size_t)ctx->n * ctx->n * sizeof(int32_t), ctx->stream);
-            if (e != cudaSuccess) {
-                *rc = fail(ctx, VPCA_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
-                return nullptr;
-            }
             s.used = true;
+            s.fresh = true;
+            s.busy = false;
             s.pid = pid;
             s.nv = 0;
             return &s;
@@ -181,17 +322,93 @@ vpca_ctx::Slot* find_slot(vpca_ctx* ctx, int64_t pid, bool create, int* rc) {
     return nullptr;
 }
 
-// CSR rows -> encode -> (optionally) Gram.  out_tile != nullptr: copy the encoded tile back instead of the Gram.
-int process_calls(vpca_ctx* ctx, const int64_t* offsets, const void* sample_idx, int idx_bytes, int64_t nv,
-                  int32_t* d_target, void* out_tile, int64_t out_ld) {
-    int rc = ensure_staging(ctx);
-    if (rc != VPCA_OK) return rc;
+// Bookkeeping that brackets every host-input accumulate call.  begin(): state + overflow checks, slot lookup.
+// end(): counters, slot release; a failed batch poisons its partition (the staging Gram may be partially updated).
+struct CallScope {
+    vpca_ctx* ctx;
+    int64_t pid, nv;
+    vpca_ctx::Slot* slot = nullptr;
+    int32_t* target = nullptr;
+    bool fresh = false;
+    int begin() {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
+        int rc = check_overflow(ctx, nv);
+        if (rc != VPCA_OK) return rc;
+        target = ctx->d_S;
+        if (pid >= 0) {
+            slot = find_slot(ctx, pid, true, &rc);
+            if (slot == nullptr) return rc;
+            if (slot->busy) {
+                slot = nullptr;
+                return fail(ctx, VPCA_ERR_STATE, "partition %lld is being written by another thread (spark.speculation "
+                            "must stay off)", (long long)pid);
+            }
+            slot->busy = true;
+            fresh = slot->fresh;
+            slot->fresh = false;
+            target = slot->d_S;
+            ctx->inflight_variants += nv;   // reserved now, so that concurrent tasks cannot jointly pass the bound
+        } else if (ctx->band_rows != ctx->n) {
+            return fail(ctx, VPCA_ERR_STATE, "a band-only Gram takes device-resident input in owner-rows mode");
+        }
+        return VPCA_OK;
+    }
+    int end(int rc) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (slot != nullptr) {
+            slot->busy = false;
+            if (rc == VPCA_OK) {
+                slot->nv += nv;
+            } else {
+                ctx->inflight_variants -= nv + slot->nv;
+                ctx->st.variants_accumulated -= slot->nv;
+                slot->used = false;
+            }
+        } else if (rc == VPCA_OK) {
+            ctx->total_variants += nv;
+        } else if (rc == VPCA_ERR_INDEX_OUT_OF_RANGE || rc == VPCA_ERR_OVERFLOW) {
+            std::lock_guard<std::mutex> lk2(ctx->err_mu);
+            ctx->err += " [direct accumulation: the Gram may hold a partial batch, call vpca_reset]";
+            tls_error = ctx->err;
+        }
+        if (rc == VPCA_OK) ctx->st.variants_accumulated += nv;
+        return rc;
+    }
+};
+
+// First batch of a partition: zero its staging Gram on the lane's stream, after the commit that last read it.
+int prepare_slot(vpca_ctx* ctx, vpca_ctx::Lane& L, CallScope& sc) {
+    if (sc.slot == nullptr || !sc.fresh) return VPCA_OK;
+    CUDA_OK(ctx, cudaStreamWaitEvent(L.stream, sc.slot->ev_free, 0));
+    CUDA_OK(ctx, cudaMemsetAsync(sc.slot->d_S, 0, (size_t)ctx->n * ctx->n * sizeof(int32_t), L.stream));
+    return VPCA_OK;
+}
+
+void lane_gram_time(vpca_ctx* ctx, vpca_ctx::Lane& L) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, L.ev_t0, L.ev_t1) == cudaSuccess) {
+        ctx->lane_gram_ms.store(ms);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->gram_timed = false;
+        ctx->st.gram_cta_group = L.plan.cta_group;
+        ctx->st.gram_resident = L.plan.last_resident;
+    }
+}
+
+// CSR rows -> encode -> (optionally) Gram, on lane L.  out_tile != nullptr: copy the encoded tile back instead.
+int process_calls(vpca_ctx* ctx, vpca_ctx::Lane& L, const int64_t* offsets, const void* sample_idx, int idx_bytes,
+                  int64_t nv, int32_t* d_target, void* out_tile, int64_t out_ld) {
     const int bits = ctx->elem_bits;
+    // validate the whole offsets array before anything is sized from it
     if (offsets[0] < 0) return fail(ctx, VPCA_ERR_BAD_ARG, "offsets[0] must be >= 0");
-    *ctx->h_flags = 0;
-    CUDA_OK(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    for (int64_t q = 0; q < nv; ++q)
+        if (offsets[q + 1] < offsets[q]) return fail(ctx, VPCA_ERR_BAD_ARG, "offsets must be non-decreasing (row %lld)", (long long)q);
+    *L.h_flags = 0;
+    CUDA_OK(ctx, cudaMemsetAsync(L.d_flags, 0, sizeof(int), L.stream));
     int64_t v = 0;
     int chunk = 0;
+    bool launched = false;
     while (v < nv) {
         // largest run of rows that fits both the variant and the index budget
         int64_t vend = std::min(nv, v + ctx->chunk_variants);
@@ -203,24 +420,25 @@ int process_calls(vpca_ctx* ctx, const int64_t* offsets, const void* sample_idx,
                 return fail(ctx, VPCA_ERR_BAD_ARG, "row %lld has %lld entries, more than chunk_nnz=%lld", (long long)v,
                             (long long)(offsets[v + 1] - offsets[v]), (long long)ctx->chunk_nnz);
         }
-        for (int64_t q = v; q < vend; ++q)
-            if (offsets[q + 1] < offsets[q]) return fail(ctx, VPCA_ERR_BAD_ARG, "offsets must be non-decreasing");
         const int64_t nvc = vend - v, nnz = offsets[vend] - offsets[v];
+        if (nnz > ctx->chunk_nnz || nvc > ctx->chunk_variants)
+            return fail(ctx, VPCA_ERR_BAD_ARG, "internal: chunk of %lld rows / %lld entries exceeds the staging buffers",
+                        (long long)nvc, (long long)nnz);
         const int b = chunk & 1;
         // the copy stream may overwrite buffer b only after the kernels that read it have run
-        CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
-        CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_off[b], offsets + v, (size_t)(nvc + 1) * sizeof(int64_t),
-                                     cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_OK(ctx, cudaStreamWaitEvent(L.copy_stream, L.ev_done[b], 0));
+        CUDA_OK(ctx, cudaMemcpyAsync(L.d_off[b], offsets + v, (size_t)(nvc + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                     L.copy_stream));
         if (nnz > 0)
-            CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_idx[b], static_cast<const char*>(sample_idx) + (size_t)offsets[v] * idx_bytes,
-                                         (size_t)nnz * idx_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
-        ctx->st.h2d_bytes += (nvc + 1) * 8 + nnz * idx_bytes;
-        CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
+            CUDA_OK(ctx, cudaMemcpyAsync(L.d_idx[b], static_cast<const char*>(sample_idx) + (size_t)offsets[v] * idx_bytes,
+                                         (size_t)nnz * idx_bytes, cudaMemcpyHostToDevice, L.copy_stream));
+        CUDA_OK(ctx, cudaEventRecord(L.ev_copy[b], L.copy_stream));
+        ctx->c_h2d += (nvc + 1) * 8 + nnz * idx_bytes;
+        CUDA_OK(ctx, cudaStreamWaitEvent(L.stream, L.ev_copy[b], 0));
         const int64_t P = ctx->panel;
-        CUDA_OK(ctx, encode_calls(ctx->d_off[b], offsets[v], ctx->d_idx[b], idx_bytes, nvc, ctx->n, bits, ctx->max_mult, ctx->d_x[b], P,
-                                  P, ctx->d_flags, ctx->stream));
-        ctx->st.kernel_launches += 2;
+        CUDA_OK(ctx, encode_calls(L.d_off[b], offsets[v], L.d_idx[b], idx_bytes, nvc, ctx->n, bits, ctx->max_mult, L.d_x[b], P, P,
+                                  L.d_flags, L.stream));
+        ctx->c_launches += 2;
         if (out_tile != nullptr) {
             // panel layout -> the caller's row-major tile, one 2-D copy per panel (chunk boundaries are multiples of
             // 128 variants, so 4-bit rows split on byte boundaries)
@@ -228,26 +446,28 @@ int process_calls(vpca_ctx* ctx, const int64_t* offsets, const void* sample_idx,
                 const int64_t wv = std::min(P, nvc - pv);
                 CUDA_OK(ctx, cudaMemcpy2DAsync(static_cast<char*>(out_tile) + (size_t)(v + pv) * bits / 8,
                                                (size_t)out_ld * bits / 8,
-                                               static_cast<const char*>(ctx->d_x[b]) + (size_t)(pv / P) * ctx->n * P * bits / 8,
+                                               static_cast<const char*>(L.d_x[b]) + (size_t)(pv / P) * ctx->n * P * bits / 8,
                                                (size_t)P * bits / 8, (size_t)(wv * bits + 7) / 8, (size_t)ctx->n,
-                                               cudaMemcpyDeviceToHost, ctx->stream));
+                                               cudaMemcpyDeviceToHost, L.stream));
             }
-            ctx->st.d2h_bytes += (nvc * bits + 7) / 8 * (int64_t)ctx->n;
+            ctx->c_d2h += (nvc * bits + 7) / 8 * (int64_t)ctx->n;
         } else {
-            rc = launch_gram(ctx, ctx->d_x[b], nvc, P, P, d_target);
+            int rc = launch_gram(ctx, L.plan, L.stream, L.ev_t0, L.ev_t1, L.d_x[b], nvc, P, P, d_target);
             if (rc != VPCA_OK) return rc;
+            launched = true;
         }
-        CUDA_OK(ctx, cudaEventRecord(ctx->ev_done[b], ctx->stream));
+        CUDA_OK(ctx, cudaEventRecord(L.ev_done[b], L.stream));
         v = vend;
         ++chunk;
     }
-    CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(L.h_flags, L.d_flags, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
     // the caller's buffers are read asynchronously: do not return before every copy has completed
-    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (*ctx->h_flags & 1)
+    CUDA_OK(ctx, cudaStreamSynchronize(L.stream));
+    if (launched) lane_gram_time(ctx, L);
+    if (*L.h_flags & 1)
         return fail(ctx, VPCA_ERR_INDEX_OUT_OF_RANGE, "sample index outside [0, %d) (the reference throws at "
                     "VariantsPca.scala:59/:188)", ctx->n);
-    if (*ctx->h_flags & 2)
+    if (*L.h_flags & 2)
         return fail(ctx, VPCA_ERR_OVERFLOW, "a sample is listed more than max_multiplicity=%d times in one row",
                     ctx->max_mult);
     return VPCA_OK;
@@ -260,8 +480,12 @@ extern "C" {
 int vpca_version(void) { return VPCA_VERSION_MAJOR * 1000 + VPCA_VERSION_MINOR; }
 
 const char* vpca_last_error(const vpca_ctx* ctx) {
-    if (ctx != nullptr) return ctx->err.c_str();
-    return tls_error.c_str();
+    // a thread that just failed on `ctx` reads its own message, whatever other threads have done to the context since
+    if (ctx == nullptr || tls_error_ctx == ctx) return tls_error.c_str();
+    vpca_ctx* c = const_cast<vpca_ctx*>(ctx);
+    std::lock_guard<std::mutex> lk(c->err_mu);
+    tls_error_copy = c->err;
+    return tls_error_copy.c_str();
 }
 
 int vpca_create(const vpca_config* cfg, vpca_ctx** out) {
@@ -273,6 +497,8 @@ int vpca_create(const vpca_config* cfg, vpca_ctx** out) {
     if (cfg->n_samples < 2) return fail(nullptr, VPCA_ERR_BAD_ARG, "n_samples must be >= 2");
     if (cfg->dtype != VPCA_DTYPE_I8 && cfg->dtype != VPCA_DTYPE_BF16 && cfg->dtype != VPCA_DTYPE_E2M1)
         return fail(nullptr, VPCA_ERR_BAD_ARG, "unknown dtype %d", cfg->dtype);
+    if (cfg->staging_lanes < 0 || cfg->staging_lanes > 16)
+        return fail(nullptr, VPCA_ERR_BAD_ARG, "staging_lanes must be in [0, 16]");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -295,36 +521,51 @@ int vpca_create(const vpca_config* cfg, vpca_ctx** out) {
         delete ctx;
         return fail(nullptr, VPCA_ERR_BAD_ARG, "VPCA_DTYPE_E2M1 represents multiplicities 0, 1, 2 only (max_multiplicity <= 2)");
     }
+    if (ctx->elem_bits != 8 && 16777216ll / ((int64_t)ctx->max_mult * ctx->max_mult) < 8192) {
+        // fp32 tensor accumulation is exact below 2^24 only: a launch folds at least one panel (8192 variants), so the
+        // largest count of one panel, 8192 * max_mult^2, must stay below that (bf16: max_multiplicity <= 45)
+        const int mm = ctx->max_mult;
+        delete ctx;
+        return fail(nullptr, VPCA_ERR_BAD_ARG, "max_multiplicity %d is too large for exact fp32 accumulation of bf16 cells "
+                    "(<= 45); use VPCA_DTYPE_I8", mm);
+    }
+    const bool band = cfg->gram_band_rows > 0;
+    if (band && (cfg->d_gram != nullptr || cfg->gram_band_row0 < 0 || cfg->gram_band_row0 + cfg->gram_band_rows > ctx->n)) {
+        delete ctx;
+        return fail(nullptr, VPCA_ERR_BAD_ARG, "gram_band_row0/rows must lie in [0, n_samples] and need a library-owned Gram");
+    }
+    ctx->band_row0 = band ? cfg->gram_band_row0 : 0;
+    ctx->band_rows = band ? cfg->gram_band_rows : ctx->n;
     if (cfg->stream != nullptr) {
         ctx->stream = static_cast<cudaStream_t>(cfg->stream);
     } else {
         e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
         ctx->own_stream = true;
     }
-    const size_t gram_bytes = (size_t)ctx->n * ctx->n * sizeof(int32_t);
+    const size_t gram_cells = (size_t)ctx->band_rows * ctx->n;
     if (e == cudaSuccess) {
         if (cfg->d_gram != nullptr) {
             ctx->d_S = static_cast<int32_t*>(cfg->d_gram);
         } else {
-            e = cudaMalloc(&ctx->d_S, gram_bytes + 64 * sizeof(int32_t));   // + barrier flags of the peer-reduce mode
+            e = cudaMalloc(&ctx->d_S, (gram_cells + 64) * sizeof(int32_t));   // + barrier flags of the peer-reduce mode
             ctx->own_S = true;
-            if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_S + (size_t)ctx->n * ctx->n, 0, 64 * sizeof(int32_t), ctx->stream);
+            if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_S + gram_cells, 0, 64 * sizeof(int32_t), ctx->stream);
         }
     }
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_S, 0, gram_bytes, ctx->stream);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_flags, sizeof(int));
-    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_flags, sizeof(int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_S, 0, gram_cells * sizeof(int32_t), ctx->stream);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_t1);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_e0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_e1);
     if (e != cudaSuccess) {
-        const int rc = fail(nullptr, VPCA_ERR_CUDA, "vpca_create: %s", cudaGetErrorString(e));
+        const int rc = fail(nullptr, e == cudaErrorMemoryAllocation ? VPCA_ERR_NOMEM : VPCA_ERR_CUDA, "vpca_create: %s",
+                            cudaGetErrorString(e));
         vpca_destroy(ctx);
         return rc;
     }
     const int nslots = cfg->partitions_in_flight > 0 ? cfg->partitions_in_flight : 4;
     ctx->slots.resize(nslots);
+    ctx->lanes.resize(cfg->staging_lanes > 0 ? cfg->staging_lanes : 2);
     *out = ctx;
     return VPCA_OK;
 }
@@ -333,23 +574,15 @@ int vpca_destroy(vpca_ctx* ctx) {
     if (ctx == nullptr) return VPCA_OK;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->copy_stream) {
-        cudaStreamSynchronize(ctx->copy_stream);
-        cudaStreamDestroy(ctx->copy_stream);
+    for (auto& L : ctx->lanes) free_lane(L);
+    for (auto& s : ctx->slots) {
+        cudaFree(s.d_S);
+        if (s.ev_free) cudaEventDestroy(s.ev_free);
     }
-    for (int b = 0; b < 2; ++b) {
-        cudaFree(ctx->d_off[b]);
-        cudaFree(ctx->d_idx[b]);
-        cudaFree(ctx->d_x[b]);
-        if (ctx->ev_copy[b]) cudaEventDestroy(ctx->ev_copy[b]);
-        if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
-    }
-    for (auto& s : ctx->slots) cudaFree(s.d_S);
-    for (int d = 0; d < ctx->plan.num_peers; ++d)
-        if (d != ctx->plan.peer_rank && ctx->plan.peer_S[d] != nullptr) cudaIpcCloseMemHandle(ctx->plan.peer_S[d]);
+    if (ctx->plan.peers_ipc)
+        for (int d = 0; d < ctx->plan.num_peers; ++d)
+            if (d != ctx->plan.peer_rank && ctx->plan.peer_S[d] != nullptr) cudaIpcCloseMemHandle(ctx->plan.peer_base[d]);
     if (ctx->own_S) cudaFree(ctx->d_S);
-    cudaFree(ctx->d_flags);
-    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->eig_ready) eig_free(ctx->eig);
     gram_plan_free(ctx->plan);
     for (cudaEvent_t ev : {ctx->ev_t0, ctx->ev_t1, ctx->ev_e0, ctx->ev_e1})
@@ -359,15 +592,25 @@ int vpca_destroy(vpca_ctx* ctx) {
     return VPCA_OK;
 }
 
+int vpca_synchronize(vpca_ctx* ctx) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VPCA_OK;
+}
+
 int vpca_reset(vpca_ctx* ctx) {
     if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto& L : ctx->lanes)
+        if (L.busy) return fail(ctx, VPCA_ERR_STATE, "vpca_reset while an accumulate call is in flight");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    CUDA_OK(ctx, cudaMemsetAsync(ctx->d_S, 0, (size_t)ctx->n * ctx->n * sizeof(int32_t), ctx->stream));
+    CUDA_OK(ctx, cudaMemsetAsync(ctx->d_S, 0, (size_t)ctx->band_rows * ctx->n * sizeof(int32_t), ctx->stream));
     for (auto& s : ctx->slots) s.used = false;
     ctx->finalized = false;
     ctx->pca_done = false;
     ctx->total_variants = 0;
+    ctx->inflight_variants = 0;
     ctx->st.variants_accumulated = 0;
     return VPCA_OK;
 }
@@ -375,16 +618,37 @@ int vpca_reset(vpca_ctx* ctx) {
 int vpca_encode_calls(vpca_ctx* ctx, const int64_t* offsets, const int32_t* sample_idx, int64_t nv, void* out,
                       int64_t ld) {
     if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
-    std::lock_guard<std::mutex> lk(ctx->mu);
     if (offsets == nullptr || out == nullptr || nv < 0 || ld < nv || (nv > 0 && sample_idx == nullptr && offsets[nv] > offsets[0]))
         return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_encode_calls: bad argument");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     if (nv == 0) return VPCA_OK;
-    return process_calls(ctx, offsets, sample_idx, 4, nv, nullptr, out, ld);
+    LaneGuard lg(ctx);
+    if (lg.rc != VPCA_OK) return lg.rc;
+    return process_calls(ctx, *lg.lane, offsets, sample_idx, 4, nv, nullptr, out, ld);
 }
 
 static int accumulate_calls_impl(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const void* sample_idx,
-                                 int idx_bytes, int64_t nv);
+                                 int idx_bytes, int64_t nv) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    if (offsets == nullptr || nv < 0 || (nv > 0 && sample_idx == nullptr && offsets[nv] > offsets[0]))
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_accumulate_calls: bad argument");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    if (nv == 0) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
+        return VPCA_OK;
+    }
+    CallScope sc{ctx, partition_id, nv};
+    int rc = sc.begin();
+    if (rc != VPCA_OK) return rc;
+    {
+        LaneGuard lg(ctx);
+        rc = lg.rc;
+        if (rc == VPCA_OK) rc = prepare_slot(ctx, *lg.lane, sc);
+        if (rc == VPCA_OK) rc = process_calls(ctx, *lg.lane, offsets, sample_idx, idx_bytes, nv, sc.target, nullptr, 0);
+    }
+    return sc.end(rc);
+}
 
 int vpca_accumulate_calls(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const int32_t* sample_idx,
                           int64_t nv) {
@@ -397,95 +661,59 @@ int vpca_accumulate_calls_u16(vpca_ctx* ctx, int64_t partition_id, const int64_t
     return accumulate_calls_impl(ctx, partition_id, offsets, sample_idx, 2, nv);
 }
 
-static int accumulate_calls_impl(vpca_ctx* ctx, int64_t partition_id, const int64_t* offsets, const void* sample_idx,
-                                 int idx_bytes, int64_t nv) {
-    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (offsets == nullptr || nv < 0 || (nv > 0 && sample_idx == nullptr && offsets[nv] > offsets[0]))
-        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_accumulate_calls: bad argument");
-    if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
-    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    if (nv == 0) return VPCA_OK;
-    int rc = check_overflow(ctx, nv);
-    if (rc != VPCA_OK) return rc;
-    int32_t* target = ctx->d_S;
-    vpca_ctx::Slot* slot = nullptr;
-    if (partition_id >= 0) {
-        slot = find_slot(ctx, partition_id, true, &rc);
-        if (slot == nullptr) return rc;
-        target = slot->d_S;
-    }
-    rc = process_calls(ctx, offsets, sample_idx, idx_bytes, nv, target, nullptr, 0);
-    if (rc != VPCA_OK) {
-        // a failed batch poisons the partition (its staging Gram may be partially updated): drop it
-        if (slot) slot->used = false;
-        else if (rc == VPCA_ERR_INDEX_OUT_OF_RANGE || rc == VPCA_ERR_OVERFLOW)
-            ctx->err += " [direct accumulation: the Gram may hold a partial batch, call vpca_reset]";
-        return rc;
-    }
-    if (slot) slot->nv += nv;
-    else ctx->total_variants += nv;
-    ctx->st.variants_accumulated += nv;
-    return VPCA_OK;
-}
-
 // code 0: bitmap rows; 1 / 2: PLINK .bed rows counting A1 / A2 (see encode.cu)
 static int accumulate_packed(vpca_ctx* ctx, int64_t partition_id, const uint8_t* bits, int64_t nv, int64_t stride_bytes,
                              int code) {
     if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
-    std::lock_guard<std::mutex> lk(ctx->mu);
     const int64_t min_stride = code == 0 ? (ctx->n + 7) / 8 : (ctx->n + 3) / 4;
     if (nv < 0 || (nv > 0 && bits == nullptr) || stride_bytes < min_stride)
         return fail(ctx, VPCA_ERR_BAD_ARG, "packed rows: stride_bytes must be >= ceil(n_samples / %d)", code == 0 ? 8 : 4);
-    if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    if (nv == 0) return VPCA_OK;
-    int rc = check_overflow(ctx, nv);
-    if (rc != VPCA_OK) return rc;
-    rc = ensure_staging(ctx);
-    if (rc != VPCA_OK) return rc;
-    int32_t* target = ctx->d_S;
-    vpca_ctx::Slot* slot = nullptr;
-    if (partition_id >= 0) {
-        slot = find_slot(ctx, partition_id, true, &rc);
-        if (slot == nullptr) return rc;
-        target = slot->d_S;
+    if (nv == 0) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
+        return VPCA_OK;
     }
-    // bits beyond sample n-1 in the last byte of a row would be read as carriers of non-existent samples: the kernel
-    // masks them (smp >= n), nothing to validate on the host.
-    const int64_t P = ctx->panel;
-    const int64_t cap_rows = std::min<int64_t>(ctx->chunk_variants, (ctx->chunk_nnz * (int64_t)sizeof(int32_t)) / stride_bytes);
-    if (cap_rows < 32) {
-        if (slot) slot->used = false;
-        return fail(ctx, VPCA_ERR_BAD_ARG, "stride_bytes too large for the staging buffer");
-    }
-    const int64_t step = std::max<int64_t>(P, (cap_rows / P) * P) <= cap_rows ? std::max<int64_t>(P, (cap_rows / P) * P)
-                                                                              : (cap_rows / 32) * 32;
-    int chunk = 0;
-    for (int64_t v = 0; v < nv; v += step, ++chunk) {
-        const int64_t nvc = std::min(step, nv - v);
-        const int b = chunk & 1;
-        CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
-        CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_idx[b], bits + (size_t)v * stride_bytes, (size_t)nvc * stride_bytes,
-                                     cudaMemcpyHostToDevice, ctx->copy_stream));
-        CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
-        ctx->st.h2d_bytes += nvc * stride_bytes;
-        CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
-        CUDA_OK(ctx, encode_bits(reinterpret_cast<const uint8_t*>(ctx->d_idx[b]), stride_bytes, nvc, ctx->n, ctx->elem_bits,
-                                 ctx->d_x[b], P, P, code, ctx->stream));
-        ctx->st.kernel_launches += 1;
-        rc = launch_gram(ctx, ctx->d_x[b], nvc, P, P, target);
-        if (rc != VPCA_OK) {
-            if (slot) slot->used = false;
-            return rc;
+    CallScope sc{ctx, partition_id, nv};
+    int rc = sc.begin();
+    if (rc != VPCA_OK) return rc;
+    auto body = [&](vpca_ctx::Lane& L) -> int {
+        int r = prepare_slot(ctx, L, sc);
+        if (r != VPCA_OK) return r;
+        // bits beyond sample n-1 in the last byte of a row would be read as carriers of non-existent samples: the kernel
+        // masks them (smp >= n), nothing to validate on the host.
+        const int64_t P = ctx->panel;
+        const int64_t cap_rows = std::min<int64_t>(ctx->chunk_variants, (ctx->chunk_nnz * (int64_t)sizeof(int32_t)) / stride_bytes);
+        if (cap_rows < 32) return fail(ctx, VPCA_ERR_BAD_ARG, "stride_bytes too large for the staging buffer");
+        const int64_t whole = std::max<int64_t>(P, (cap_rows / P) * P);
+        const int64_t step = whole <= cap_rows ? whole : (cap_rows / 32) * 32;
+        int chunk = 0;
+        for (int64_t v = 0; v < nv; v += step, ++chunk) {
+            const int64_t nvc = std::min(step, nv - v);
+            const int b = chunk & 1;
+            CUDA_OK(ctx, cudaStreamWaitEvent(L.copy_stream, L.ev_done[b], 0));
+            CUDA_OK(ctx, cudaMemcpyAsync(L.d_idx[b], bits + (size_t)v * stride_bytes, (size_t)nvc * stride_bytes,
+                                         cudaMemcpyHostToDevice, L.copy_stream));
+            CUDA_OK(ctx, cudaEventRecord(L.ev_copy[b], L.copy_stream));
+            ctx->c_h2d += nvc * stride_bytes;
+            CUDA_OK(ctx, cudaStreamWaitEvent(L.stream, L.ev_copy[b], 0));
+            CUDA_OK(ctx, encode_bits(reinterpret_cast<const uint8_t*>(L.d_idx[b]), stride_bytes, nvc, ctx->n, ctx->elem_bits,
+                                     L.d_x[b], P, P, code, L.stream));
+            ctx->c_launches += 1;
+            r = launch_gram(ctx, L.plan, L.stream, L.ev_t0, L.ev_t1, L.d_x[b], nvc, P, P, sc.target);
+            if (r != VPCA_OK) return r;
+            CUDA_OK(ctx, cudaEventRecord(L.ev_done[b], L.stream));
         }
-        CUDA_OK(ctx, cudaEventRecord(ctx->ev_done[b], ctx->stream));
+        CUDA_OK(ctx, cudaStreamSynchronize(L.stream));   // the caller's buffer is free to reuse on return
+        lane_gram_time(ctx, L);
+        return VPCA_OK;
+    };
+    {
+        LaneGuard lg(ctx);
+        rc = lg.rc;
+        if (rc == VPCA_OK) rc = body(*lg.lane);
     }
-    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));   // the caller's buffer is free to reuse on return
-    if (slot) slot->nv += nv;
-    else ctx->total_variants += nv;
-    ctx->st.variants_accumulated += nv;
-    return VPCA_OK;
+    return sc.end(rc);
 }
 
 int vpca_accumulate_bits(vpca_ctx* ctx, int64_t partition_id, const uint8_t* bits, int64_t nv, int64_t stride_bytes) {
@@ -506,17 +734,22 @@ int vpca_commit(vpca_ctx* ctx, int64_t partition_id) {
     int rc;
     vpca_ctx::Slot* s = find_slot(ctx, partition_id, false, &rc);
     if (s == nullptr) return VPCA_OK;   // an empty partition never staged anything
+    if (s->busy) return fail(ctx, VPCA_ERR_STATE, "partition %lld still has an accumulate call in flight", (long long)partition_id);
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    rc = check_overflow(ctx, 0);
-    if (rc != VPCA_OK) return rc;
-    if (ctx->plan.num_peers > 1 && ctx->plan.peer_mode == 1)
-        CUDA_OK(ctx, gram_add_owners(ctx->plan, s->d_S, ctx->n, ctx->stream));
-    else if (ctx->plan.num_peers > 1)
-        CUDA_OK(ctx, gram_add_peers(ctx->plan, s->d_S, (int64_t)ctx->n * ctx->n, ctx->stream));
-    else
-        CUDA_OK(ctx, gram_add(ctx->d_S, s->d_S, (int64_t)ctx->n * ctx->n, ctx->stream));
-    ctx->st.kernel_launches += 1;
+    // the partition's variants were reserved against the int32 bound when they were staged (CallScope::begin)
+    if (s->nv > 0) {
+        // every accumulate call of the partition synchronised its lane before returning: the staging Gram is complete
+        if (ctx->plan.num_peers > 1 && ctx->plan.peer_mode == 1)
+            CUDA_OK(ctx, gram_add_owners(ctx->plan, s->d_S, ctx->n, ctx->stream));
+        else if (ctx->plan.num_peers > 1)
+            CUDA_OK(ctx, gram_add_peers(ctx->plan, s->d_S, (int64_t)ctx->n * ctx->n, ctx->stream));
+        else
+            CUDA_OK(ctx, gram_add(ctx->d_S, s->d_S, (int64_t)ctx->n * ctx->n, ctx->stream));
+        CUDA_OK(ctx, cudaEventRecord(s->ev_free, ctx->stream));
+        ctx->c_launches += 1;
+    }
     ctx->total_variants += s->nv;
+    ctx->inflight_variants -= s->nv;
     s->used = false;
     return VPCA_OK;
 }
@@ -527,7 +760,9 @@ int vpca_abort(vpca_ctx* ctx, int64_t partition_id) {
     int rc;
     vpca_ctx::Slot* s = find_slot(ctx, partition_id, false, &rc);
     if (s != nullptr) {
+        if (s->busy) return fail(ctx, VPCA_ERR_STATE, "partition %lld still has an accumulate call in flight", (long long)partition_id);
         ctx->st.variants_accumulated -= s->nv;
+        ctx->inflight_variants -= s->nv;
         s->used = false;
     }
     return VPCA_OK;
@@ -535,55 +770,69 @@ int vpca_abort(vpca_ctx* ctx, int64_t partition_id) {
 
 int vpca_accumulate_dense(vpca_ctx* ctx, const void* x, int64_t nv, int64_t ld, int on_device) {
     if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
-    std::lock_guard<std::mutex> lk(ctx->mu);
     if (x == nullptr || nv < 0 || ld < nv) return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_accumulate_dense: bad argument");
-    if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
-    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    if (nv == 0) return VPCA_OK;
-    int rc = check_overflow(ctx, nv);
-    if (rc != VPCA_OK) return rc;
     const int bits = ctx->elem_bits;
     if (bits == 4 && (ld % 128) != 0)
         return fail(ctx, VPCA_ERR_BAD_ARG, "packed e2m1 tiles need ld %% 128 == 0 (and zero padding up to a multiple of 128 variants)");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     if (on_device) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
+        if (nv == 0) return VPCA_OK;
+        int rc = check_overflow(ctx, nv);
+        if (rc != VPCA_OK) return rc;
         const int align = bits == 4 ? 31 : 15;
         if ((reinterpret_cast<uintptr_t>(x) & align) != 0 || ((ld * bits / 8) & align) != 0)
             return fail(ctx, VPCA_ERR_BAD_ARG, "device tile must be %d-byte aligned with a %d-byte multiple row pitch",
                         align + 1, align + 1);
-        rc = launch_gram(ctx, x, nv, ld, 0, ctx->d_S);
+        rc = launch_gram(ctx, ctx->plan, ctx->stream, ctx->ev_t0, ctx->ev_t1, x, nv, ld, 0, ctx->d_S);
         if (rc != VPCA_OK) return rc;
-    } else {
-        rc = ensure_staging(ctx);
-        if (rc != VPCA_OK) return rc;
+        ctx->gram_timed = true;
+        ctx->st.gram_cta_group = ctx->plan.cta_group;
+        ctx->st.gram_resident = ctx->plan.last_resident;
+        ctx->total_variants += nv;
+        ctx->st.variants_accumulated += nv;
+        return VPCA_OK;
+    }
+    if (nv == 0) return VPCA_OK;
+    CallScope sc{ctx, -1, nv};
+    int rc = sc.begin();
+    if (rc != VPCA_OK) return rc;
+    auto body = [&](vpca_ctx::Lane& L) -> int {
         int chunk = 0;
         for (int64_t v = 0; v < nv; v += ctx->chunk_variants, ++chunk) {
             const int64_t nvc = std::min(ctx->chunk_variants, nv - v);
             const int b = chunk & 1;
-            CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+            CUDA_OK(ctx, cudaStreamWaitEvent(L.copy_stream, L.ev_done[b], 0));
             // the caller's row-major tile -> panel layout, one 2-D copy per panel; a partial last panel is zeroed first
             const int64_t P = ctx->panel;
             if ((nvc % P) != 0)
-                CUDA_OK(ctx, cudaMemsetAsync(static_cast<char*>(ctx->d_x[b]) + (size_t)(nvc / P) * ctx->n * P * bits / 8, 0,
-                                             (size_t)ctx->n * P * bits / 8, ctx->copy_stream));
+                CUDA_OK(ctx, cudaMemsetAsync(static_cast<char*>(L.d_x[b]) + (size_t)(nvc / P) * ctx->n * P * bits / 8, 0,
+                                             (size_t)ctx->n * P * bits / 8, L.copy_stream));
             for (int64_t pv = 0; pv < nvc; pv += P) {
                 const int64_t wv = std::min(P, nvc - pv);
-                CUDA_OK(ctx, cudaMemcpy2DAsync(static_cast<char*>(ctx->d_x[b]) + (size_t)(pv / P) * ctx->n * P * bits / 8,
+                CUDA_OK(ctx, cudaMemcpy2DAsync(static_cast<char*>(L.d_x[b]) + (size_t)(pv / P) * ctx->n * P * bits / 8,
                                                (size_t)P * bits / 8, static_cast<const char*>(x) + (size_t)(v + pv) * bits / 8,
                                                (size_t)ld * bits / 8, (size_t)(wv * bits + 7) / 8, (size_t)ctx->n,
-                                               cudaMemcpyHostToDevice, ctx->copy_stream));
+                                               cudaMemcpyHostToDevice, L.copy_stream));
             }
-            CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
-            ctx->st.h2d_bytes += (nvc * bits + 7) / 8 * (int64_t)ctx->n;
-            CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
-            rc = launch_gram(ctx, ctx->d_x[b], nvc, P, P, ctx->d_S);
-            if (rc != VPCA_OK) return rc;
-            CUDA_OK(ctx, cudaEventRecord(ctx->ev_done[b], ctx->stream));
+            CUDA_OK(ctx, cudaEventRecord(L.ev_copy[b], L.copy_stream));
+            ctx->c_h2d += (nvc * bits + 7) / 8 * (int64_t)ctx->n;
+            CUDA_OK(ctx, cudaStreamWaitEvent(L.stream, L.ev_copy[b], 0));
+            int r = launch_gram(ctx, L.plan, L.stream, L.ev_t0, L.ev_t1, L.d_x[b], nvc, P, P, ctx->d_S);
+            if (r != VPCA_OK) return r;
+            CUDA_OK(ctx, cudaEventRecord(L.ev_done[b], L.stream));
         }
-        CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));   // caller's buffer is free to reuse on return
+        CUDA_OK(ctx, cudaStreamSynchronize(L.stream));   // caller's buffer is free to reuse on return
+        lane_gram_time(ctx, L);
+        return VPCA_OK;
+    };
+    {
+        LaneGuard lg(ctx);
+        rc = lg.rc;
+        if (rc == VPCA_OK) rc = body(*lg.lane);
     }
-    ctx->total_variants += nv;
-    ctx->st.variants_accumulated += nv;
-    return VPCA_OK;
+    return sc.end(rc);
 }
 
 int vpca_accumulate_panels(vpca_ctx* ctx, const void* d_x, int64_t nv, int64_t panel_variants) {
@@ -593,12 +842,17 @@ int vpca_accumulate_panels(vpca_ctx* ctx, const void* d_x, int64_t nv, int64_t p
         return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_accumulate_panels: panel_variants must be a positive multiple of 128");
     if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
     if ((reinterpret_cast<uintptr_t>(d_x) & 31) != 0) return fail(ctx, VPCA_ERR_BAD_ARG, "panels must be 32-byte aligned");
+    if (ctx->band_rows != ctx->n && !(ctx->plan.num_peers > 1 && ctx->plan.peer_mode == 1))
+        return fail(ctx, VPCA_ERR_STATE, "a band-only Gram needs vpca_gram_set_peers_local + VPCA_PEER_OWNER_ROWS first");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     if (nv == 0) return VPCA_OK;
     int rc = check_overflow(ctx, nv);
     if (rc != VPCA_OK) return rc;
-    rc = launch_gram(ctx, d_x, nv, panel_variants, panel_variants, ctx->d_S);
+    rc = launch_gram(ctx, ctx->plan, ctx->stream, ctx->ev_t0, ctx->ev_t1, d_x, nv, panel_variants, panel_variants, ctx->d_S);
     if (rc != VPCA_OK) return rc;
+    ctx->gram_timed = true;
+    ctx->st.gram_cta_group = ctx->plan.cta_group;
+    ctx->st.gram_resident = ctx->plan.last_resident;
     ctx->total_variants += nv;
     ctx->st.variants_accumulated += nv;
     return VPCA_OK;
@@ -614,7 +868,7 @@ int vpca_synth_panels_device(vpca_ctx* ctx, uint64_t seed, int64_t v0, int64_t n
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     cudaError_t e = synth_dense(seed, ctx->n, v0, nv, mode, ctx->elem_bits, d_x, panel_variants, panel_variants, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, VPCA_ERR_CUDA, "synthetic generator: %s", cudaGetErrorString(e));
-    ctx->st.kernel_launches += 2 * ((nv + (1 << 22) - 1) >> 22);
+    ctx->c_launches += 2 * ((nv + (1 << 22) - 1) >> 22);
     return VPCA_OK;
 }
 
@@ -631,11 +885,23 @@ int vpca_finalize_gram(vpca_ctx* ctx) {
     for (auto& s : ctx->slots)
         if (s.used)
             return fail(ctx, VPCA_ERR_STATE, "partition %lld is neither committed nor aborted", (long long)s.pid);
+    for (auto& L : ctx->lanes)
+        if (L.busy) return fail(ctx, VPCA_ERR_STATE, "vpca_finalize_gram while an accumulate call is in flight");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    CUDA_OK(ctx, gram_symmetrize(ctx->d_S, ctx->n, ctx->stream));
-    ctx->st.kernel_launches += 1;
+    if (ctx->band_rows == ctx->n) {   // a row band stays a band of the lower triangle: nothing to mirror into
+        CUDA_OK(ctx, gram_symmetrize(ctx->d_S, ctx->n, ctx->stream));
+        ctx->c_launches += 1;
+    }
     ctx->finalized = true;
     ctx->pca_done = false;
+    return VPCA_OK;
+}
+
+static int copy_gram_out(vpca_ctx* ctx, int32_t* out, size_t cells) {
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_S, cells * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->c_d2h += (int64_t)(cells * sizeof(int32_t));
     return VPCA_OK;
 }
 
@@ -643,52 +909,72 @@ int vpca_get_gram(vpca_ctx* ctx, int32_t* out) {
     if (ctx == nullptr || out == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "call vpca_finalize_gram first");
+    if (ctx->band_rows != ctx->n) return fail(ctx, VPCA_ERR_STATE, "this context stores a row band: use vpca_get_gram_band");
+    return copy_gram_out(ctx, out, (size_t)ctx->n * ctx->n);
+}
+
+int vpca_get_gram_band(vpca_ctx* ctx, int32_t row0, int32_t rows, int32_t* out) {
+    if (ctx == nullptr || out == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (rows <= 0 || row0 < ctx->band_row0 || row0 + rows > ctx->band_row0 + ctx->band_rows)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "rows [%d, %d) are outside the band [%d, %d) this context stores", row0, row0 + rows,
+                    ctx->band_row0, ctx->band_row0 + ctx->band_rows);
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    const size_t bytes = (size_t)ctx->n * ctx->n * sizeof(int32_t);
-    CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_S, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t cells = (size_t)rows * ctx->n;
+    CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_S + (size_t)(row0 - ctx->band_row0) * ctx->n, cells * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->st.d2h_bytes += (int64_t)bytes;
+    ctx->c_d2h += (int64_t)(cells * sizeof(int32_t));
     return VPCA_OK;
 }
 
-int vpca_get_partial_gram(vpca_ctx* ctx, int32_t* out) {
+int vpca_get_partial_gram(vpca_ctx* ctx, int32_t* out, int64_t* variants_in_gram) {
     if (ctx == nullptr || out == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized: use vpca_get_gram");
-    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    const size_t bytes = (size_t)ctx->n * ctx->n * sizeof(int32_t);
-    CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->d_S, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->st.d2h_bytes += (int64_t)bytes;
-    return VPCA_OK;
+    if (ctx->band_rows != ctx->n) return fail(ctx, VPCA_ERR_STATE, "this context stores a row band: use vpca_get_gram_band");
+    if (variants_in_gram) *variants_in_gram = ctx->total_variants;
+    return copy_gram_out(ctx, out, (size_t)ctx->n * ctx->n);
 }
 
-int vpca_load_partial_gram(vpca_ctx* ctx, const int32_t* gram) {
-    if (ctx == nullptr || gram == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
+int vpca_load_partial_gram(vpca_ctx* ctx, const int32_t* gram, int64_t variants_in_gram) {
+    if (ctx == nullptr || gram == nullptr || variants_in_gram < 0) return fail(ctx, VPCA_ERR_BAD_ARG, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
+    if (ctx->band_rows != ctx->n) return fail(ctx, VPCA_ERR_STATE, "this context stores a row band");
     for (auto& s : ctx->slots)
         if (s.used) return fail(ctx, VPCA_ERR_STATE, "partition %lld is in flight", (long long)s.pid);
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     const size_t bytes = (size_t)ctx->n * ctx->n * sizeof(int32_t);
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_S, gram, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->st.h2d_bytes += (int64_t)bytes;
-    return VPCA_OK;
+    ctx->c_h2d += (int64_t)bytes;
+    // the restored counts keep counting against the int32 bound (VariantsPca.scala:185)
+    ctx->total_variants = variants_in_gram;
+    ctx->inflight_variants = 0;
+    return check_overflow(ctx, 0);
 }
 
 int vpca_set_gram(vpca_ctx* ctx, const int32_t* gram) {
     if (ctx == nullptr || gram == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->band_rows != ctx->n) return fail(ctx, VPCA_ERR_STATE, "this context stores a row band");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     const size_t bytes = (size_t)ctx->n * ctx->n * sizeof(int32_t);
     CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_S, gram, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->st.h2d_bytes += (int64_t)bytes;
+    ctx->c_h2d += (int64_t)bytes;
     for (auto& s : ctx->slots) s.used = false;
+    ctx->inflight_variants = 0;
     ctx->finalized = true;
     ctx->pca_done = false;
     return VPCA_OK;
+}
+
+int64_t vpca_variant_count(vpca_ctx* ctx) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return ctx->total_variants;
 }
 
 static int run_center(vpca_ctx* ctx) {
@@ -701,7 +987,7 @@ static int run_center(vpca_ctx* ctx) {
         ctx->eig_ready = true;
     }
     CUDA_OK(ctx, center_gram(ctx->eig, ctx->d_S, ctx->stream));
-    ctx->st.kernel_launches += 3;
+    ctx->c_launches += 3;
     return VPCA_OK;
 }
 
@@ -711,6 +997,7 @@ int vpca_compute_pca(vpca_ctx* ctx, int32_t k, double* vecs, double* evals, int3
     if (vecs == nullptr || k < 1 || k > ctx->n || k > std::max(ctx->num_pc, 16))
         return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_compute_pca: k=%d out of range", k);
     if (!ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "call vpca_finalize_gram first");
+    if (ctx->band_rows != ctx->n) return fail(ctx, VPCA_ERR_STATE, "this context stores a row band of the Gram");
     if (ctx->n > 65535)
         return fail(ctx, VPCA_ERR_UNSUPPORTED, "computePca is limited to 65535 samples, like the reference (MLlib RowMatrix "
                     "behind VariantsPca.scala:226 refuses more columns); the Gram itself has no such limit");
@@ -722,7 +1009,9 @@ int vpca_compute_pca(vpca_ctx* ctx, int32_t k, double* vecs, double* evals, int3
         const char* em = getenv("VPCA_EIG");
         ctx->eig.mode = (em != nullptr && strcmp(em, "direct") == 0) ? 1 : (em != nullptr && strcmp(em, "lanczos") == 0) ? 2 : 0;
     }
-    CUDA_OK(ctx, eig_topk(ctx->eig, k, ctx->stream, &ctx->st.kernel_launches));
+    int64_t launches = 0;
+    CUDA_OK(ctx, eig_topk(ctx->eig, k, ctx->stream, &launches));
+    ctx->c_launches += launches;
     CUDA_OK(ctx, cudaEventRecord(ctx->ev_e1, ctx->stream));
     ctx->st.eig_method = ctx->eig.last_method;
     ctx->st.eig_iterations = ctx->eig.last_iters;
@@ -734,7 +1023,7 @@ int vpca_compute_pca(vpca_ctx* ctx, int32_t k, double* vecs, double* evals, int3
     CUDA_OK(ctx, cudaMemcpyAsync(&nz, ctx->eig.d_nz, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     if (non_zero_rows) *non_zero_rows = nz;
-    ctx->st.d2h_bytes += (int64_t)nb + (evals ? k * 8 : 0) + 4;
+    ctx->c_d2h += (int64_t)nb + (evals ? k * 8 : 0) + 4;
     ctx->pca_done = true;
     return VPCA_OK;
 }
@@ -743,13 +1032,14 @@ int vpca_get_centered(vpca_ctx* ctx, double* out) {
     if (ctx == nullptr || out == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "call vpca_finalize_gram first");
+    if (ctx->band_rows != ctx->n) return fail(ctx, VPCA_ERR_STATE, "this context stores a row band of the Gram");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     int rc = run_center(ctx);   // the eigensolve overwrites C, so recompute it
     if (rc != VPCA_OK) return rc;
     const size_t bytes = (size_t)ctx->n * ctx->n * sizeof(double);
     CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->eig.d_C, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->st.d2h_bytes += (int64_t)bytes;
+    ctx->c_d2h += (int64_t)bytes;
     ctx->pca_done = false;
     return VPCA_OK;
 }
@@ -777,7 +1067,7 @@ int vpca_synth_dense_device(vpca_ctx* ctx, uint64_t seed, int64_t v0, int64_t nv
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     cudaError_t e = synth_dense(seed, ctx->n, v0, nv, mode, ctx->elem_bits, d_x, ld, 0, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, VPCA_ERR_CUDA, "synthetic generator: %s", cudaGetErrorString(e));
-    ctx->st.kernel_launches += 2 * ((nv + (1 << 22) - 1) >> 22);
+    ctx->c_launches += 2 * ((nv + (1 << 22) - 1) >> 22);
     return VPCA_OK;
 }
 
@@ -788,11 +1078,17 @@ int vpca_get_stats(vpca_ctx* ctx, vpca_stats* out) {
     if (ctx->gram_timed && cudaEventSynchronize(ctx->ev_t1) == cudaSuccess) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) == cudaSuccess) ctx->st.last_gram_ms = ms;
+    } else if (!ctx->gram_timed) {
+        ctx->st.last_gram_ms = ctx->lane_gram_ms.load();
     }
     if (ctx->eig_timed && cudaEventSynchronize(ctx->ev_e1) == cudaSuccess) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev_e0, ctx->ev_e1) == cudaSuccess) ctx->st.last_eig_ms = ms;
     }
+    ctx->st.gram_launches = ctx->c_gram.load();
+    ctx->st.kernel_launches = ctx->c_launches.load();
+    ctx->st.h2d_bytes = ctx->c_h2d.load();
+    ctx->st.d2h_bytes = ctx->c_d2h.load();
     *out = ctx->st;
     return VPCA_OK;
 }
@@ -801,6 +1097,7 @@ int vpca_gram_export_ipc(vpca_ctx* ctx, void* handle64) {
     if (ctx == nullptr || handle64 == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->own_S) return fail(ctx, VPCA_ERR_STATE, "the peer-reduce mode needs a library-owned Gram (vpca_config.d_gram == NULL)");
+    if (ctx->band_rows != ctx->n) return fail(ctx, VPCA_ERR_STATE, "band-only Grams are shared with vpca_gram_set_peers_local");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     cudaIpcMemHandle_t h;
@@ -826,16 +1123,70 @@ int vpca_gram_set_peers(vpca_ctx* ctx, const void* handles, int32_t world, int32
             cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) {
                 for (int q = 0; q < d; ++q)
-                    if (q != rank) cudaIpcCloseMemHandle(ctx->plan.peer_S[q]);
-                return fail(ctx, VPCA_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", d, cudaGetErrorString(e));
+                    if (q != rank) cudaIpcCloseMemHandle(ctx->plan.peer_base[q]);
+                return fail(ctx, VPCA_ERR_NCCL, "cudaIpcOpenMemHandle(rank %d) failed: %s", d, cudaGetErrorString(e));
             }
             base = static_cast<int32_t*>(ptr);
         }
+        ctx->plan.peer_base[d] = base;
         ctx->plan.peer_S[d] = base;
         ctx->plan.peer_flags[d] = base + nn;
     }
+    ctx->plan.peers_ipc = true;
     ctx->plan.peer_rank = rank;
     ctx->plan.num_peers = world;
+    sync_peers_to_lanes(ctx);
+    return VPCA_OK;
+}
+
+// Same-process form of vpca_gram_set_peers: the caller owns all `world` contexts (one JVM driving the GPUs of the box,
+// SURVEY 8b "process model"), so the Gram buffers are shared by enabling peer access between the devices instead of
+// through IPC handles.  Contexts may also sit on the same device (tests on a 1-GPU box).
+int vpca_gram_set_peers_local(vpca_ctx* const* ctxs, int32_t world) {
+    if (ctxs == nullptr || world < 1 || world > 16) return fail(nullptr, VPCA_ERR_BAD_ARG, "vpca_gram_set_peers_local: world must be in [1, 16]");
+    for (int r = 0; r < world; ++r) {
+        if (ctxs[r] == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctxs[%d] is NULL", r);
+        if (!ctxs[r]->own_S) return fail(ctxs[r], VPCA_ERR_STATE, "the peer-reduce mode needs a library-owned Gram");
+        if (ctxs[r]->n != ctxs[0]->n) return fail(ctxs[r], VPCA_ERR_BAD_ARG, "all contexts must have the same n_samples");
+        if (ctxs[r]->plan.num_peers != 0) return fail(ctxs[r], VPCA_ERR_STATE, "peers already set");
+        for (int q = 0; q < r; ++q)
+            if (ctxs[q] == ctxs[r]) return fail(ctxs[r], VPCA_ERR_BAD_ARG, "ctxs[%d] and ctxs[%d] are the same context", q, r);
+    }
+    for (int r = 0; r < world; ++r) {
+        vpca_ctx* c = ctxs[r];
+        CUDA_OK(c, cudaSetDevice(c->cfg.device));
+        for (int d = 0; d < world; ++d) {
+            const int od = ctxs[d]->cfg.device;
+            if (od == c->cfg.device) continue;
+            int can = 0;
+            CUDA_OK(c, cudaDeviceCanAccessPeer(&can, c->cfg.device, od));
+            if (!can) return fail(c, VPCA_ERR_NCCL, "device %d cannot access device %d (no NVLink / PCIe peer path)", c->cfg.device, od);
+            cudaError_t e = cudaDeviceEnablePeerAccess(od, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+            } else if (e != cudaSuccess) {
+                return fail(c, VPCA_ERR_NCCL, "cudaDeviceEnablePeerAccess(%d -> %d): %s", c->cfg.device, od, cudaGetErrorString(e));
+            }
+        }
+    }
+    for (int r = 0; r < world; ++r) {
+        vpca_ctx* c = ctxs[r];
+        std::lock_guard<std::mutex> lk(c->mu);
+        for (int d = 0; d < world; ++d) {
+            vpca_ctx* o = ctxs[d];
+            // a band-only Gram is addressed through the virtual origin of the full matrix: row r of rank d lives at
+            // base + (r - band_row0) * n, so (base - band_row0 * n) + r * n is valid for every row the rank owns
+            c->plan.peer_base[d] = o->d_S;
+            c->plan.peer_S[d] = o->d_S - (ptrdiff_t)o->band_row0 * o->n;
+            c->plan.peer_flags[d] = o->d_S + (size_t)o->band_rows * o->n;
+            c->plan.band_row0[d] = o->band_row0;
+            c->plan.band_rows[d] = o->band_rows;
+        }
+        c->plan.peers_ipc = false;
+        c->plan.peer_rank = r;
+        c->plan.num_peers = world;
+        sync_peers_to_lanes(c);
+    }
     return VPCA_OK;
 }
 
@@ -849,18 +1200,38 @@ int vpca_gram_set_peer_mode(vpca_ctx* ctx, int32_t mode) {
     if (mode == VPCA_PEER_OWNER_ROWS) {
         if (n < 64 * world)
             return fail(ctx, VPCA_ERR_UNSUPPORTED, "owner-rows mode needs n_samples >= 64 x world (%d < %d)", n, 64 * world);
-        // equal shares of the lower triangle: rows [0, R) hold R^2 / 2 cells -> R_q = n sqrt(q / world), on multiples of 32
-        int prev = 0;
+        int ends[16];
+        vpca_owner_row_bands(n, world, ends);
+        for (int q = 0; q < 16; ++q) ctx->plan.own_end[q] = q < world ? ends[q] : n;
+        // band-only Grams must hold exactly the rows their rank owns
         for (int q = 0; q < world; ++q) {
-            int end = (q + 1 == world) ? n : (int)(std::sqrt((double)(q + 1) / world) * n / 32.0 + 0.5) * 32;
-            end = std::max(end, prev + 32);
-            if (q + 1 < world) end = std::min(end, n - 32 * (world - 1 - q));
-            ctx->plan.own_end[q] = end;
-            prev = end;
+            const int lo = q == 0 ? 0 : ends[q - 1];
+            if (ctx->plan.band_rows[q] != 0 && ctx->plan.band_rows[q] != n &&
+                (ctx->plan.band_row0[q] != lo || ctx->plan.band_rows[q] != ends[q] - lo))
+                return fail(ctx, VPCA_ERR_BAD_ARG, "rank %d stores rows [%d, %d) but owns [%d, %d) (see vpca_owner_row_bands)", q,
+                            ctx->plan.band_row0[q], ctx->plan.band_row0[q] + ctx->plan.band_rows[q], lo, ends[q]);
         }
-        for (int q = world; q < 16; ++q) ctx->plan.own_end[q] = n;
+    } else if (ctx->band_rows != n) {
+        return fail(ctx, VPCA_ERR_BAD_ARG, "a band-only Gram supports VPCA_PEER_OWNER_ROWS only");
     }
     ctx->plan.peer_mode = mode;
+    sync_peers_to_lanes(ctx);
+    return VPCA_OK;
+}
+
+int vpca_owner_row_bands(int32_t n_samples, int32_t world, int32_t* row_end) {
+    if (row_end == nullptr || world < 1 || world > 16 || n_samples < 64 * world)
+        return fail(nullptr, VPCA_ERR_BAD_ARG, "vpca_owner_row_bands: need 1 <= world <= 16 and n_samples >= 64 x world");
+    // equal shares of the lower triangle: rows [0, R) hold R^2 / 2 cells -> R_q = n sqrt(q / world), on multiples of 32
+    const int n = n_samples;
+    int prev = 0;
+    for (int q = 0; q < world; ++q) {
+        int end = (q + 1 == world) ? n : (int)(std::sqrt((double)(q + 1) / world) * n / 32.0 + 0.5) * 32;
+        end = std::max(end, prev + 32);
+        if (q + 1 < world) end = std::min(end, n - 32 * (world - 1 - q));
+        row_end[q] = end;
+        prev = end;
+    }
     return VPCA_OK;
 }
 
@@ -871,11 +1242,11 @@ int vpca_gram_gather(vpca_ctx* ctx) {
     if (ctx->plan.num_peers < 2) return VPCA_OK;
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     CUDA_OK(ctx, gram_peer_barrier(ctx->plan, ctx->stream));          // every rank's contributions have landed
-    ctx->st.kernel_launches += 1;
-    if (ctx->plan.peer_mode == 1) {
+    ctx->c_launches += 1;
+    if (ctx->plan.peer_mode == 1 && ctx->band_rows == ctx->n) {
         CUDA_OK(ctx, gram_gather_rows(ctx->plan, ctx->d_S, ctx->n, ctx->stream));
         CUDA_OK(ctx, gram_peer_barrier(ctx->plan, ctx->stream));      // nobody resets a Gram a peer is still reading
-        ctx->st.kernel_launches += 2;
+        ctx->c_launches += 2;
     }
     return VPCA_OK;
 }
@@ -886,7 +1257,7 @@ int vpca_peer_barrier(vpca_ctx* ctx) {
     if (ctx->plan.num_peers < 2) return VPCA_OK;
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     CUDA_OK(ctx, gram_peer_barrier(ctx->plan, ctx->stream));
-    ctx->st.kernel_launches += 1;
+    ctx->c_launches += 1;
     return VPCA_OK;
 }
 
@@ -896,6 +1267,25 @@ int vpca_debug_gram_profile(vpca_ctx* ctx, int64_t* out, int32_t max_ctas) {
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return gram_read_profile(ctx->plan, reinterpret_cast<long long*>(out), max_ctas);
+}
+
+/* Pinned host memory for callers that stage rows themselves (JNI direct ByteBuffers): the H2D copies of accumulate_*
+ * then run at full PCIe rate and truly asynchronously.  Portable across devices. */
+int vpca_host_alloc(size_t bytes, void** out) {
+    if (out == nullptr || bytes == 0) return fail(nullptr, VPCA_ERR_BAD_ARG, "vpca_host_alloc: bad argument");
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        *out = nullptr;
+        return fail(nullptr, VPCA_ERR_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return VPCA_OK;
+}
+
+int vpca_host_free(void* p) {
+    if (p == nullptr) return VPCA_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) return fail(nullptr, VPCA_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(e));
+    return VPCA_OK;
 }
 
 }  // extern "C"

@@ -31,8 +31,12 @@ struct GramPlan {
     int cum_workers = 0, cum_tiles = 0;
     // fused multi-GPU reduction: Gram buffers / barrier flags of all ranks, peer-mapped through CUDA IPC
     int num_peers = 0, peer_rank = 0, peer_epoch = 0;
-    int32_t* peer_S[16] = {};
+    int32_t* peer_S[16] = {};     // Gram of rank d as seen from this device: the address of row 0 (for a rank that stores
+                                  // only a row band this is a VIRTUAL origin, valid for the rows of the band only)
+    int32_t* peer_base[16] = {};  // start of rank d's allocation (what an IPC mapping must be closed with)
     int32_t* peer_flags[16] = {};
+    int band_row0[16] = {}, band_rows[16] = {};   // rows rank d stores (band_rows 0 or n: all of them)
+    bool peers_ipc = false;       // peer mappings came from cudaIpcOpenMemHandle (other processes), not from peer access
     int peer_mode = 0;        // 0: every flush goes to all ranks' Grams; 1: to the owner of the row only (+ gather)
     int own_end[16] = {};     // peer_mode 1: rank q owns Gram rows [own_end[q-1], own_end[q])
     bool profile = false;     // VPCA_GRAM_PROF=1: per-CTA timestamps in d_prof

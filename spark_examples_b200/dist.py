@@ -30,3 +30,14 @@ def allreduce_gram(gram_tensor):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(gram_tensor, op=dist.ReduceOp.SUM)
     return gram_tensor
+
+
+def allreduce_count(value: int, device=None) -> int:
+    """Sum of one integer over all ranks (variants per rank, for the int32 bound of the summed Gram)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())

@@ -1,11 +1,15 @@
 /*
- * NativePca -- JNI binding of libvpca.so (include/vpca.h), 1:1 with the C ABI.
+ * NativePca -- JNI binding of ONE vpca_ctx of libvpca.so (include/vpca.h), 1:1 with the C ABI.  A driver that uses
+ * all GPUs of its host holds a NativePcaPool (NativePcaPool.scala) instead; this class is the single-GPU form and the
+ * home of the pinned-buffer helpers.
  *
- * NOT COMPILED IN THIS REPOSITORY'S IMAGE: there is no JVM, scalac or jni.h here (SURVEY.md 8c).  This file and
- * vpca_jni.c are the binding a maintainer of googlegenomics/spark-examples adds; spark_examples_b200/native.py is the
- * same binding over ctypes and is what the tests exercise.
+ * No JVM, scalac or jni.h in this repository's image (SURVEY.md 8c): this file is source for the maintainer of
+ * googlegenomics/spark-examples.  Its native half, vpca_jni.c, IS compiled and executed here -- against a stub jni.h
+ * and a mock JNIEnv (tests/jni_harness.c); spark_examples_b200/native.py is the same binding over ctypes.
  */
 package com.google.cloud.genomics.spark.examples
+
+import java.nio.ByteBuffer
 
 object NativePca {
   System.loadLibrary("vpca_jni") // links against libvpca.so
@@ -14,7 +18,8 @@ object NativePca {
   val DTYPE_BF16 = 1
   val DTYPE_E2M1 = 2 // packed 4-bit cells (tcgen05 kind::mxf4 with unit scales; exact for 0/1/2)
 
-  // every native method throws RuntimeException(vpca_last_error) on a negative vpca_status
+  // every native method throws on a negative vpca_status: IndexOutOfBoundsException for a sample index outside [0, N)
+  // (what Breeze throws at VariantsPca.scala:188), IllegalArgumentException, OutOfMemoryError, else RuntimeException
   @native def create(nSamples: Int, device: Int, dtype: Int, numPc: Int, maxMultiplicity: Int,
                      partitionsInFlight: Int): Long
   @native def destroy(handle: Long): Unit
@@ -23,6 +28,10 @@ object NativePca {
   @native def accumulateCalls(handle: Long, partitionId: Long, offsets: Array[Long], sampleIdx: Array[Int], nv: Long): Unit
   /** Same rows with 16-bit sample indices (N <= 65536): half the PCIe bytes. */
   @native def accumulateCallsU16(handle: Long, partitionId: Long, offsets: Array[Long], sampleIdx: Array[Short], nv: Long): Unit
+  /** Same rows packed by the task straight into pinned direct buffers (allocPinned; little-endian longs / ints or
+   *  shorts): no copy on the host, the copy engines read the buffers at full PCIe rate. */
+  @native def accumulateCallsDirect(handle: Long, partitionId: Long, offsets: ByteBuffer, sampleIdx: ByteBuffer, nv: Long,
+                                    idxBytes: Int): Unit
   /** One N-bit bitmap per variant, bit s (LSB first) = hasVariation of sample s; rows strideBytes apart. */
   @native def accumulateBits(handle: Long, partitionId: Long, bits: Array[Byte], nv: Long, strideBytes: Long): Unit
   /** PLINK .bed rows as on disk (2 bits per sample); countedAllele 1 = A1, 2 = A2. */
@@ -32,10 +41,13 @@ object NativePca {
   @native def abort(handle: Long, partitionId: Long): Unit
   @native def finalizeGram(handle: Long): Unit
   /** Row-major N x N (the collected RDD[((Int, Int), Int)] of VariantsPca.scala:182-191 in key order). */
-  @native def getGram(handle: Long, out: Array[Int]): Unit
-  @native def setGram(handle: Long, gram: Array[Int]): Unit
-  /** Device address of the int32 Gram, for the NCCL all-reduce of NativePcaPool (INTEGRATION.md section 3). */
+  @native def getGram(handle: Long, nSamples: Int, out: Array[Int]): Unit
+  @native def setGram(handle: Long, nSamples: Int, gram: Array[Int]): Unit
   @native def gramDevicePtr(handle: Long): Long
   /** vecs: N x k column-major -- the layout of `pca.toArray` (VariantsPca.scala:227); returns nonZeroRows (:207). */
-  @native def computePca(handle: Long, k: Int, vecs: Array[Double], evals: Array[Double]): Int
+  @native def computePca(handle: Long, nSamples: Int, k: Int, vecs: Array[Double], evals: Array[Double]): Int
+
+  /** Page-locked host memory as a direct ByteBuffer (set order(ByteOrder.LITTLE_ENDIAN) before writing). */
+  @native def allocPinned(bytes: Long): ByteBuffer
+  @native def freePinned(buffer: ByteBuffer): Unit
 }

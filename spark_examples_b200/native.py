@@ -42,6 +42,12 @@ EXPORTED_SYMBOLS = (
     "vpca_gram_export_ipc", "vpca_gram_set_peers", "vpca_peer_barrier", "vpca_accumulate_panels",
     "vpca_synth_panels_device", "vpca_accumulate_calls_u16", "vpca_get_partial_gram", "vpca_load_partial_gram",
     "vpca_accumulate_bits", "vpca_gram_set_peer_mode", "vpca_gram_gather", "vpca_accumulate_bed",
+    "vpca_synchronize", "vpca_host_alloc", "vpca_host_free", "vpca_gram_set_peers_local", "vpca_owner_row_bands",
+    "vpca_get_gram_band", "vpca_variant_count",
+    "vpca_pool_create", "vpca_pool_destroy", "vpca_pool_size", "vpca_pool_ctx", "vpca_pool_last_error", "vpca_pool_reset",
+    "vpca_pool_accumulate_calls", "vpca_pool_accumulate_calls_u16", "vpca_pool_accumulate_bits", "vpca_pool_accumulate_bed",
+    "vpca_pool_commit", "vpca_pool_abort", "vpca_pool_reduce_and_finalize", "vpca_pool_get_gram", "vpca_pool_compute_pca",
+    "vpca_pool_get_stats",
 )
 
 
@@ -66,11 +72,13 @@ class VpcaConfig(ctypes.Structure):
         ("num_pc", ctypes.c_int32),
         ("max_multiplicity", ctypes.c_int32),
         ("partitions_in_flight", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32),
+        ("staging_lanes", ctypes.c_int32),
         ("chunk_variants", ctypes.c_int64),
         ("chunk_nnz", ctypes.c_int64),
         ("stream", ctypes.c_void_p),
         ("d_gram", ctypes.c_void_p),
+        ("gram_band_row0", ctypes.c_int32),
+        ("gram_band_rows", ctypes.c_int32),
     ]
 
 
@@ -143,9 +151,55 @@ def load_library() -> ctypes.CDLL:
     L.vpca_get_gram.restype = ctypes.c_int
     L.vpca_get_gram.argtypes = [vp, vp]
     L.vpca_get_partial_gram.restype = ctypes.c_int
-    L.vpca_get_partial_gram.argtypes = [vp, vp]
+    L.vpca_get_partial_gram.argtypes = [vp, vp, ctypes.POINTER(i64)]
     L.vpca_load_partial_gram.restype = ctypes.c_int
-    L.vpca_load_partial_gram.argtypes = [vp, vp]
+    L.vpca_load_partial_gram.argtypes = [vp, vp, i64]
+    L.vpca_variant_count.restype = i64
+    L.vpca_variant_count.argtypes = [vp]
+    L.vpca_synchronize.restype = ctypes.c_int
+    L.vpca_synchronize.argtypes = [vp]
+    L.vpca_host_alloc.restype = ctypes.c_int
+    L.vpca_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.vpca_host_free.restype = ctypes.c_int
+    L.vpca_host_free.argtypes = [vp]
+    L.vpca_gram_set_peers_local.restype = ctypes.c_int
+    L.vpca_gram_set_peers_local.argtypes = [ctypes.POINTER(vp), i32]
+    L.vpca_owner_row_bands.restype = ctypes.c_int
+    L.vpca_owner_row_bands.argtypes = [i32, i32, ctypes.POINTER(i32)]
+    L.vpca_get_gram_band.restype = ctypes.c_int
+    L.vpca_get_gram_band.argtypes = [vp, i32, i32, vp]
+    L.vpca_pool_create.restype = ctypes.c_int
+    L.vpca_pool_create.argtypes = [ctypes.POINTER(VpcaConfig), i32, ctypes.POINTER(i32), ctypes.POINTER(vp)]
+    L.vpca_pool_destroy.restype = ctypes.c_int
+    L.vpca_pool_destroy.argtypes = [vp]
+    L.vpca_pool_size.restype = i32
+    L.vpca_pool_size.argtypes = [vp]
+    L.vpca_pool_ctx.restype = vp
+    L.vpca_pool_ctx.argtypes = [vp, i64]
+    L.vpca_pool_last_error.restype = ctypes.c_char_p
+    L.vpca_pool_last_error.argtypes = [vp]
+    L.vpca_pool_reset.restype = ctypes.c_int
+    L.vpca_pool_reset.argtypes = [vp]
+    L.vpca_pool_accumulate_calls.restype = ctypes.c_int
+    L.vpca_pool_accumulate_calls.argtypes = [vp, i64, vp, vp, i64]
+    L.vpca_pool_accumulate_calls_u16.restype = ctypes.c_int
+    L.vpca_pool_accumulate_calls_u16.argtypes = [vp, i64, vp, vp, i64]
+    L.vpca_pool_accumulate_bits.restype = ctypes.c_int
+    L.vpca_pool_accumulate_bits.argtypes = [vp, i64, vp, i64, i64]
+    L.vpca_pool_accumulate_bed.restype = ctypes.c_int
+    L.vpca_pool_accumulate_bed.argtypes = [vp, i64, vp, i64, i64, i32]
+    L.vpca_pool_commit.restype = ctypes.c_int
+    L.vpca_pool_commit.argtypes = [vp, i64]
+    L.vpca_pool_abort.restype = ctypes.c_int
+    L.vpca_pool_abort.argtypes = [vp, i64]
+    L.vpca_pool_reduce_and_finalize.restype = ctypes.c_int
+    L.vpca_pool_reduce_and_finalize.argtypes = [vp]
+    L.vpca_pool_get_gram.restype = ctypes.c_int
+    L.vpca_pool_get_gram.argtypes = [vp, vp]
+    L.vpca_pool_compute_pca.restype = ctypes.c_int
+    L.vpca_pool_compute_pca.argtypes = [vp, i32, vp, vp, ctypes.POINTER(i32)]
+    L.vpca_pool_get_stats.restype = ctypes.c_int
+    L.vpca_pool_get_stats.argtypes = [vp, ctypes.POINTER(VpcaStats)]
     L.vpca_set_gram.restype = ctypes.c_int
     L.vpca_set_gram.argtypes = [vp, vp]
     L.vpca_compute_pca.restype = ctypes.c_int
@@ -187,14 +241,18 @@ class NativePca:
 
     def __init__(self, n_samples: int, device: int = 0, dtype: int = DTYPE_I8, num_pc: int = 2,
                  max_multiplicity: int = 2, partitions_in_flight: int = 4, chunk_variants: int = 0,
-                 chunk_nnz: int = 0, stream: int = 0, d_gram: int = 0):
+                 chunk_nnz: int = 0, stream: int = 0, d_gram: int = 0, staging_lanes: int = 0,
+                 gram_band: Optional[Tuple[int, int]] = None):
         self._lib = load_library()
         self.n = int(n_samples)
         self.dtype = int(dtype)
         self.elem_bits = {DTYPE_I8: 8, DTYPE_BF16: 16, DTYPE_E2M1: 4}[self.dtype]
         self.elem_bytes = self.elem_bits / 8
+        self.max_multiplicity = int(max_multiplicity) if max_multiplicity > 0 else 2
+        row0, rows = gram_band if gram_band is not None else (0, 0)
         cfg = VpcaConfig(ctypes.sizeof(VpcaConfig), n_samples, device, dtype, num_pc, max_multiplicity,
-                         partitions_in_flight, 0, chunk_variants, chunk_nnz, stream or None, d_gram or None)
+                         partitions_in_flight, staging_lanes, chunk_variants, chunk_nnz, stream or None, d_gram or None,
+                         row0, rows)
         handle = ctypes.c_void_p()
         rc = self._lib.vpca_create(ctypes.byref(cfg), ctypes.byref(handle))
         self._h = handle if rc == VPCA_OK else None
@@ -363,18 +421,36 @@ class NativePca:
         self._check(self._lib.vpca_get_gram(self._h, _host_ptr(out)))
         return out
 
-    def partialGram(self) -> np.ndarray:
-        """The accumulated (not yet finalized) Gram: lower triangle meaningful.  Checkpoint payload."""
+    def partialGram(self, with_count: bool = False):
+        """The accumulated (not yet finalized) Gram: lower triangle meaningful.  Checkpoint payload (with_count: also
+        the number of variants the counts stand for, which a resume hands back to loadPartialGram)."""
         out = np.empty((self.n, self.n), dtype=np.int32)
-        self._check(self._lib.vpca_get_partial_gram(self._h, _host_ptr(out)))
-        return out
+        nv = ctypes.c_int64(0)
+        self._check(self._lib.vpca_get_partial_gram(self._h, _host_ptr(out), ctypes.byref(nv)))
+        return (out, int(nv.value)) if with_count else out
 
-    def loadPartialGram(self, gram: np.ndarray):
-        """Restore a checkpointed partial Gram; accumulation continues on top of it."""
+    def loadPartialGram(self, gram: np.ndarray, variants_in_gram: int):
+        """Restore a checkpointed partial Gram; accumulation continues on top of it (and keeps counting against the
+        int32 bound of a similarity count from `variants_in_gram`)."""
         g = np.ascontiguousarray(gram, dtype=np.int32)
         if g.shape != (self.n, self.n):
             raise VpcaError(VPCA_ERR_BAD_ARG, "gram must be (n, n)")
-        self._check(self._lib.vpca_load_partial_gram(self._h, _host_ptr(g)))
+        self._check(self._lib.vpca_load_partial_gram(self._h, _host_ptr(g), int(variants_in_gram)))
+
+    def variantCount(self) -> int:
+        v = int(self._lib.vpca_variant_count(self._h))
+        if v < 0:
+            self._raise(v, self._h)
+        return v
+
+    def synchronize(self):
+        self._check(self._lib.vpca_synchronize(self._h))
+
+    def gramBand(self, row0: int, rows: int) -> np.ndarray:
+        """Rows [row0, row0 + rows) of the Gram as this context stores them (band-only contexts: their own band)."""
+        out = np.empty((rows, self.n), dtype=np.int32)
+        self._check(self._lib.vpca_get_gram_band(self._h, int(row0), int(rows), _host_ptr(out)))
+        return out
 
     def setGram(self, gram: np.ndarray):
         g = np.ascontiguousarray(gram, dtype=np.int32)
@@ -417,4 +493,132 @@ class NativePca:
     def stats(self) -> dict:
         st = VpcaStats()
         self._check(self._lib.vpca_get_stats(self._h, ctypes.byref(st)))
+        return {name: getattr(st, name) for name, _ in VpcaStats._fields_}
+
+
+def ownerRowBands(n_samples: int, world: int) -> list:
+    """Row bands of VPCA_PEER_OWNER_ROWS: [(row0, rows)] per rank (vpca_owner_row_bands)."""
+    L = load_library()
+    ends = (ctypes.c_int32 * world)()
+    rc = L.vpca_owner_row_bands(int(n_samples), int(world), ends)
+    if rc != VPCA_OK:
+        raise VpcaError(rc, L.vpca_last_error(None).decode("utf-8", "replace"))
+    out, prev = [], 0
+    for q in range(world):
+        out.append((prev, int(ends[q]) - prev))
+        prev = int(ends[q])
+    return out
+
+
+def setPeersLocal(contexts, mode: str = "owner_rows"):
+    """Wire NativePca objects that live in THIS process (any mix of devices) for the fused reduce
+    (vpca_gram_set_peers_local); contexts[r] becomes rank r."""
+    L = load_library()
+    arr = (ctypes.c_void_p * len(contexts))(*[c._h.value for c in contexts])
+    rc = L.vpca_gram_set_peers_local(arr, len(contexts))
+    if rc != VPCA_OK:
+        raise VpcaError(rc, L.vpca_last_error(None).decode("utf-8", "replace"))
+    for c in contexts:
+        c._check(L.vpca_gram_set_peer_mode(c._h, {"replicate": 0, "owner_rows": 1}[mode]))
+
+
+class NativePcaPool:
+    """One process driving all GPUs of the box: the ctypes twin of the JNI class ``NativePcaPool``
+    (spark_examples_b200/jvm/NativePcaPool.scala).  Partition p is served by GPU p % n_gpus; every method except
+    reset / reduceAndFinalize / getGram / computePca may be called from many threads at once."""
+
+    def __init__(self, n_samples: int, n_gpus: int, devices=None, dtype: int = DTYPE_I8, num_pc: int = 2,
+                 max_multiplicity: int = 2, partitions_in_flight: int = 4, staging_lanes: int = 0,
+                 chunk_variants: int = 0, chunk_nnz: int = 0):
+        self._lib = load_library()
+        self.n = int(n_samples)
+        cfg = VpcaConfig(ctypes.sizeof(VpcaConfig), n_samples, 0, dtype, num_pc, max_multiplicity, partitions_in_flight,
+                         staging_lanes, chunk_variants, chunk_nnz, None, None, 0, 0)
+        devs = None
+        if devices is not None:
+            devs = (ctypes.c_int32 * n_gpus)(*[int(d) for d in devices])
+        h = ctypes.c_void_p()
+        rc = self._lib.vpca_pool_create(ctypes.byref(cfg), int(n_gpus), devs, ctypes.byref(h))
+        self._h = h if rc == VPCA_OK else None
+        if rc != VPCA_OK:
+            self._raise(rc)
+
+    def _raise(self, rc: int):
+        msg = self._lib.vpca_pool_last_error(self._h).decode("utf-8", "replace")
+        if rc == VPCA_ERR_INDEX_OUT_OF_RANGE:
+            raise IndexOutOfRange(rc, msg)
+        raise VpcaError(rc, msg)
+
+    def _check(self, rc: int):
+        if rc != VPCA_OK:
+            self._raise(rc)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.vpca_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def size(self) -> int:
+        return int(self._lib.vpca_pool_size(self._h))
+
+    def reset(self):
+        self._check(self._lib.vpca_pool_reset(self._h))
+
+    def accumulateCalls(self, partition_id: int, offsets, sample_idx):
+        off, idx = NativePca._csr(offsets, sample_idx)
+        self._check(self._lib.vpca_pool_accumulate_calls(self._h, int(partition_id), _host_ptr(off),
+                                                         _host_ptr(idx) if len(idx) else None, len(off) - 1))
+
+    def accumulateCalls16(self, partition_id: int, offsets, sample_idx):
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        idx = np.ascontiguousarray(sample_idx, dtype=np.uint16)
+        self._check(self._lib.vpca_pool_accumulate_calls_u16(self._h, int(partition_id), _host_ptr(off),
+                                                             _host_ptr(idx) if len(idx) else None, len(off) - 1))
+
+    def accumulateBits(self, partition_id: int, bits: np.ndarray):
+        b = np.ascontiguousarray(bits, dtype=np.uint8)
+        self._check(self._lib.vpca_pool_accumulate_bits(self._h, int(partition_id), _host_ptr(b), b.shape[0], b.shape[1]))
+
+    def accumulateBed(self, partition_id: int, rows: np.ndarray, counted_allele: int = 1):
+        b = np.ascontiguousarray(rows, dtype=np.uint8)
+        self._check(self._lib.vpca_pool_accumulate_bed(self._h, int(partition_id), _host_ptr(b), b.shape[0], b.shape[1],
+                                                       int(counted_allele)))
+
+    def commit(self, partition_id: int):
+        self._check(self._lib.vpca_pool_commit(self._h, int(partition_id)))
+
+    def abort(self, partition_id: int):
+        self._check(self._lib.vpca_pool_abort(self._h, int(partition_id)))
+
+    def reduceAndFinalize(self):
+        self._check(self._lib.vpca_pool_reduce_and_finalize(self._h))
+
+    def getGram(self) -> np.ndarray:
+        out = np.empty((self.n, self.n), dtype=np.int32)
+        self._check(self._lib.vpca_pool_get_gram(self._h, _host_ptr(out)))
+        return out
+
+    def computePca(self, k: int = 2):
+        flat = np.empty(self.n * k, dtype=np.float64)
+        evals = np.empty(k, dtype=np.float64)
+        nz = ctypes.c_int32(0)
+        self._check(self._lib.vpca_pool_compute_pca(self._h, int(k), _host_ptr(flat), _host_ptr(evals), ctypes.byref(nz)))
+        return flat.reshape(k, self.n).T.copy(), evals, int(nz.value)
+
+    def stats(self) -> dict:
+        st = VpcaStats()
+        self._check(self._lib.vpca_pool_get_stats(self._h, ctypes.byref(st)))
         return {name: getattr(st, name) for name, _ in VpcaStats._fields_}

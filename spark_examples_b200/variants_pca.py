@@ -131,11 +131,21 @@ class CallsRdd:
 
 
 class SimilarityMatrix:
-    """The `RDD[((Int, Int), Int)]` of VariantsPca.scala:182-191, resident on the GPU (all N^2 keys present)."""
+    """The `RDD[((Int, Int), Int)]` of VariantsPca.scala:182-191 (all N^2 keys present), resident on the GPU: it
+    iterates / collects as ((row, col), count) records like the reference's RDD and additionally remembers the device
+    handle, so `computePca` can run on the resident matrix without the N^2 records ever being materialised (the
+    Scala twin is `GramRDD`, spark_examples_b200/jvm/GramRDD.scala)."""
 
     def __init__(self, nat: native.NativePca, n: int):
         self._nat, self.n = nat, n
         self._host: Optional[np.ndarray] = None
+
+    def __iter__(self):
+        S = self.toArray()
+        for i in range(self.n):
+            row = S[i]
+            for j in range(self.n):
+                yield ((i, j), int(row[j]))
 
     def toArray(self) -> np.ndarray:
         if self._host is None:
@@ -258,6 +268,11 @@ class VariantsPcaDriver:
             self._save_checkpoint(nat, callsets, done, every=16)
         self._save_checkpoint(nat, callsets, done, every=1)
         if self._world > 1:
+            # every count of the SUMMED matrix must stay a Java Int (VariantsPca.scala:185): bound it before the sum
+            total = vdist.allreduce_count(nat.variantCount(), self._gram_tensor.device)
+            if total * nat.max_multiplicity ** 2 > 2 ** 31 - 1:
+                raise native.VpcaError(native.VPCA_ERR_OVERFLOW, f"{total} variants over all ranks could overflow an "
+                                       "int32 similarity count")
             vdist.allreduce_gram(self._gram_tensor)            # VariantsPca.scala:190
         nat.finalizeGram()
         return SimilarityMatrix(nat, callsets.n_samples)
@@ -268,13 +283,24 @@ class VariantsPcaDriver:
         return self.getSimilarityMatrix(calls)
 
     # -- VariantsPca.scala:198-231 ----------------------------------------------------------------------------------
-    def computePca(self, matrixEntries: SimilarityMatrix) -> List[Tuple[str, float, float]]:
+    def computePca(self, matrixEntries) -> List[Tuple[str, float, float]]:
+        """`matrixEntries`: what getSimilarityMatrix returned (stays on the GPU), or -- the reference's signature,
+        `RDD[((Int, Int), Int)]` (:198) -- any iterable of ((row, col), count) records, which are loaded into the GPU
+        (absent keys count 0, like the rows `:216-221` never see)."""
         rowCount = len(self.common.indexes)
         numPc = self.conf.numPc()
         if numPc < 2:
             # the reference reads array(i + pca.numRows) (:230) and fails for numPc = 1
             raise IndexError("computePca reads the first two principal components; --num-pc must be >= 2")
-        vecs, evals, nonZeroRows = matrixEntries._nat.computePca(numPc)
+        if isinstance(matrixEntries, SimilarityMatrix):
+            nat = matrixEntries._nat
+        else:
+            S = np.zeros((rowCount, rowCount), np.int32)
+            for (i, j), v in matrixEntries:
+                S[i, j] = v                                                      # IndexError like Breeze at :216
+            nat = self._native(rowCount)
+            nat.setGram(S)
+        vecs, evals, nonZeroRows = nat.computePca(numPc)
         print(f"Non zero rows in matrix: {nonZeroRows} / {rowCount}.")           # :208
         self.eigenvalues = evals
         self.components = vecs                                                   # all numPc columns (Python twin prints them)
@@ -351,7 +377,7 @@ class VariantsPcaDriver:
         ck = np.load(path)
         if int(ck["n_samples"]) != callsets.n_samples or int(ck["n_partitions"]) != len(callsets.partitions):
             raise ValueError(f"checkpoint {path} belongs to a different cohort / partitioning")
-        nat.loadPartialGram(ck["gram"])
+        nat.loadPartialGram(ck["gram"], int(ck["variants"]))
         print(f"Resumed {len(ck['done'])} / {len(callsets.partitions)} partitions from {path}.")
         return set(int(p) for p in ck["done"])
 
@@ -360,7 +386,8 @@ class VariantsPcaDriver:
         if path is None or len(done) == 0 or len(done) % every:
             return
         tmp = path + ".tmp.npz"
-        np.savez(tmp, gram=nat.partialGram(), done=np.array(sorted(done), np.int64), n_samples=callsets.n_samples,
+        gram, variants = nat.partialGram(with_count=True)
+        np.savez(tmp, gram=gram, variants=variants, done=np.array(sorted(done), np.int64), n_samples=callsets.n_samples,
                  n_partitions=len(callsets.partitions))
         os.replace(tmp, path)
 

@@ -6,6 +6,10 @@ from pathlib import Path
 
 import pytest
 
+# many contexts (each with several streams) may share one device in the pool tests: give every stream its own hardware
+# queue so that a flag barrier between contexts can never sit behind the kernel it waits for (read at CUDA init)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))

@@ -42,10 +42,11 @@ def test_header_is_plain_c():
 
 def test_struct_layout_matches_header(lib):
     from spark_examples_b200 import native
-    assert ctypes.sizeof(native.VpcaConfig) == 64
+    assert ctypes.sizeof(native.VpcaConfig) == 72
     assert native.VpcaConfig.stream.offset == 48 and native.VpcaConfig.d_gram.offset == 56
+    assert native.VpcaConfig.gram_band_row0.offset == 64 and native.VpcaConfig.gram_band_rows.offset == 68
     assert ctypes.sizeof(native.VpcaStats) == 64
-    assert lib.vpca_version() == 1
+    assert lib.vpca_version() == 2
 
 
 def test_create_fails_loudly_without_gpu(lib):
