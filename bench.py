@@ -16,8 +16,12 @@ A step = one pass of the hot path over the rank's resident genotype matrix:
            device encode -> Gram -> centering -> eigensolve -> top-2 PCs back on the host, every step.
 `roofline` = the Gram kernel alone against the tensor-core peak (int8 peak taken as 2 x the measured bf16 figure of
            MEASURED_PEAKS.json); numerator = SYRK-minimal ops N (N+1) V.
-`cpu_baseline` = the oracle's restatement of VariantsPca.scala:182-191 timed on this box's host cores on a bounded
-           sample (rank 0, N = 1 only).
+`cpu_baseline` = the oracle's restatement of VariantsPca.scala:182-191 timed on this box's host cores on a FIXED
+           sample (32 768 variants, one partition matrix per physical core, median of 5; rank 0, N = 1 only).
+Extra legs in the same JSON line (BASELINE configs[2] and [4]; the headline fields above stay configs[1]):
+`c3`       = 2504 samples x 5 M variants PER GPU (at --gpus 8 this IS configs[2], 2504 x 40 M), int8 and packed e2m1,
+           timed back to back for >= 2 s with its own clock samples: the sustained number, against the sustained peak.
+`c5_bf16`  = 10 000 samples x 1.25 M variants per GPU in bf16 (configs[4] is this at 8 GPUs; 1/2/4/8 give the sweep).
 """
 from __future__ import annotations
 
@@ -58,7 +62,13 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=-1, help="-1: min(steps, 5); 0 disables the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eig-check", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per bounded sample")
+    ap.add_argument("--cpu-sample-variants", type=int, default=32768, help="fixed sample of the CPU arm (variants per pass)")
+    ap.add_argument("--cpu-repeats", type=int, default=5, help="passes of the CPU arm; the median is reported")
+    ap.add_argument("--c3-variants-per-gpu", type=int, default=5_000_000, help="0 disables the c3 / sustained leg")
+    ap.add_argument("--c3-seconds", type=float, default=2.0, help="back-to-back duration of the sustained leg")
+    ap.add_argument("--c5-samples", type=int, default=10_000)
+    ap.add_argument("--c5-variants-per-gpu", type=int, default=1_250_000, help="0 disables the c5_bf16 leg")
+    ap.add_argument("--no-legs", action="store_true", help="skip the c3 and c5_bf16 legs (quick kernel A/B runs)")
     return ap.parse_args()
 
 
@@ -138,25 +148,47 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_similarity_sample(n, seconds, threads=None):
-    """Time the oracle's getSimilarityMatrix restatement on a bounded sample; returns (cells/s, info).
-    One dense int32 N x N per thread = per Spark partition (VariantsPca.scala:185), summed at the end (:190)."""
+def physical_cores():
+    """Physical cores this process may run on: the partition count of the CPU arm (two hyper-threads of one core share
+    the L1/L2 their 25 MB partition matrix streams through, so logical threads only add noise)."""
+    logical = host_threads()
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or logical
+        total = psutil.cpu_count(logical=True) or logical
+        return max(1, min(logical, int(round(logical * phys / max(1, total)))))
+    except Exception:
+        return logical
+
+
+def numa_policy():
+    try:
+        nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+    except OSError:
+        nodes = 1
+    return f"default (first touch: every partition matrix is allocated and zeroed by the thread that fills it), {nodes} NUMA node(s)"
+
+
+def cpu_similarity_sample(n, variants=32768, threads=None, repeats=5):
+    """Time the oracle's getSimilarityMatrix restatement on a FIXED sample: `variants` variants of the benchmark cohort,
+    one dense int32 N x N per thread = per Spark partition (VariantsPca.scala:185), summed at the end (:190).
+    Returns (median cells/s, info).  A fixed sample keeps the fixed cost (allocating and summing `threads` matrices) in
+    the same proportion on every box, so two boxes give comparable numbers."""
     from oracle import oracle
     oracle.build()
-    threads = threads or host_threads()
+    threads = threads or physical_cores()
     oracle.c_set_threads(threads)          # also for the sample generator (torchrun exports OMP_NUM_THREADS=1)
-    # grow the sample geometrically until one pass costs about `seconds` (the fixed cost of allocating and summing
-    # `threads` dense matrices makes small probes useless for extrapolation on many-core hosts)
-    nv, dt = threads * 4, 0.0
-    while True:
-        off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
+    off, idx = oracle.c_synth_calls(SEED, n, 0, variants)
+    nv = len(off) - 1
+    times, S = [], None
+    for _ in range(max(1, repeats) + 1):   # the first pass warms the thread pool and the page tables: dropped
         t0 = time.perf_counter()
         S = oracle.c_similarity(n, off, idx, threads)
-        dt = time.perf_counter() - t0
-        if dt >= 0.5 * seconds or nv >= 200_000:
-            break
-        nv = int(min(200_000, max(nv * 2, nv * min(8.0, 0.8 * seconds / max(dt, 1e-3)))))
-    return n * nv / dt, {"variants": nv, "seconds": dt, "threads": threads, "checksum": int(S.trace())}
+        times.append(time.perf_counter() - t0)
+    times = sorted(times[1:]) if len(times) > 1 else times
+    med = times[len(times) // 2]
+    return n * nv / med, {"variants": nv, "seconds": med, "seconds_all": [round(t, 4) for t in times], "threads": threads,
+                          "numa": numa_policy(), "checksum": int(S.trace())}
 
 
 def cpu_blas_sample(n, nv=65_536, threads=None):
@@ -211,28 +243,28 @@ def run_reference(args):
     from oracle import oracle
     oracle.build()
     n = args.samples
-    threads = host_threads()
-    per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
-    vals, nvs = [], []
-    for i in range(args.warmup + args.steps):
-        v, info = cpu_similarity_sample(n, per_step, threads)
+    threads = physical_cores()
+    vals, info = [], None
+    for i in range(args.warmup + args.steps):        # a step = one pass over the fixed sample
+        v, info = cpu_similarity_sample(n, args.cpu_sample_variants, threads, repeats=1)
         if i >= args.warmup:
             vals.append(v)
-            nvs.append(info["variants"])
-    total_cells = sum(n * nv for nv in nvs)
-    total_time = sum(n * nv / v for nv, v in zip(nvs, vals))
-    value = total_cells / total_time
+    vals.sort()
+    value = vals[len(vals) // 2]                      # median over the timed steps
+    nv = info["variants"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total_time / max(1, args.steps), "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * n * nv / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": f"{n} samples x {args.variants_per_gpu} variants per GPU (BASELINE configs[1]); each "
-                               f"step is a bounded sample of {nvs[-1]} variants of that cohort",
+                               f"step is a fixed sample of {nv} variants of that cohort",
                    "samples": n, "variants_per_gpu": args.variants_per_gpu},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{nvs[-1]} variants x {n} samples per step, oracle/vpca_oracle.c vo_similarity "
-                                   f"(VariantsPca.scala:182-191 restated; Spark/JVM not runnable here), OpenMP "
-                                   f"{threads} threads; Gram only",
+                         "sample": f"{nv} variants x {n} samples per step (fixed), median of {len(vals)} steps, "
+                                   f"oracle/vpca_oracle.c vo_similarity (VariantsPca.scala:182-191 restated; Spark/JVM not "
+                                   f"runnable here), OpenMP, {threads} threads = physical cores of {host_threads()} logical; "
+                                   f"Gram only", "threads": threads, "numa": info["numa"],
+                         "min_max": [vals[0], vals[-1]],
                          "strong_cpu_blas": cpu_blas_sample(n, threads=threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -408,20 +440,32 @@ def run_b200(args):
     mxf4 = args.dtype == "e2m1" and os.environ.get("VPCA_E2M1_MXF4", "1") != "0"
     peak_mult = 1.0 if args.dtype == "bf16" else (4.0 if mxf4 else 2.0)      # dense nominal: bf16 2.25, int8/fp8 4.5, fp4 9 PF
     peak = peak_mult * peaks["bf16_tflops"]
-    traffic = None
-    tp = ROOT / "profiles" / "gram_traffic.json"
+    # DRAM traffic of one launch is an ncu number (dram__bytes_read.sum + dram__bytes_write.sum of `ncu --set full`); it
+    # cannot be measured inside this run.  The last capture is kept in profiles/r2_gram_traffic.json together with the
+    # hash of the kernel source it was taken from: a capture of a different kernel version reads as null, never as stale.
+    traffic, traffic_src = None, None
+    tp = ROOT / "profiles" / "r2_gram_traffic.json"
     if tp.exists():
         try:
+            import hashlib
             tj = json.loads(tp.read_text())
-            traffic = (tj.get("e2m1", {}) if args.dtype == "e2m1" else tj).get("dram_bytes_per_launch")
+            src_hash = hashlib.sha256((ROOT / "spark_examples_b200" / "csrc" / "gram_sm100.cu").read_bytes()).hexdigest()[:16]
+            ent = tj.get(args.dtype, {})
+            if ent.get("kernel_source_sha256_16") == src_hash:
+                traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
         except Exception:
             traffic = None
+    nominal = {1.0: 2250.0, 2.0: 4500.0, 4.0: 9000.0}[peak_mult]
     roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved_tops / peak, "traffic": traffic,
+                "frac": achieved_tops / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "gram_kernel<cta_group=%d>" % st1["gram_cta_group"], "kernel_ms": kernel_ms,
                 "ops_per_launch": ops, "ops_definition": "SYRK-minimal N(N+1)V (int8 MAC = 2 ops)",
                 "peak_source": "%g x %s bf16 burst TFLOP/s of MEASURED_PEAKS.json (nominal dense ratios: int8/fp8 = 2 x bf16, "
                                "fp4 = 4 x bf16)" % (peak_mult, peaks["source"]),
+                "frac_of_nominal": achieved_tops / nominal, "nominal_peak": nominal,
+                "peak_note": ("frac > 1: the denominator is cuBLAS bf16 throughput (x%g), which itself reaches ~75 %% of the "
+                              "nominal tensor peak on this pool; read frac_of_nominal as the utilisation" % peak_mult)
+                             if achieved_tops > peak else None,
                 "hbm_gbs_algorithmic": (n * vpg * eb + 4.0 * n * n) / (kernel_ms * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks["hbm_gbs"]}
 
@@ -697,12 +741,166 @@ def run_b200(args):
                    "gram_bit_identical_to_int8_path": bool(torch.equal(S4, S)) if world == 1 else None}
         del X4, S4
 
+
+    # ---- extra legs (BASELINE configs[2] and [4]); same step protocol as the headline, own contexts, own clock samples ----
+    def open_context(n_leg, dtype_code):
+        """A NativePca for `n_leg` samples wired like the headline context: fused owner-rows reduce over peer memory when it
+        is available on every rank, else a caller-owned Gram that NCCL all-reduces.  Collective: every rank calls it."""
+        S_leg = torch.zeros((n_leg, n_leg), dtype=torch.int32, device=dev)
+        want_fused = world > 1 and args.reduce in ("fused", "scatter") and n_leg >= 64 * world
+        nat_leg = native.NativePca(n_leg, device=local_rank, dtype=dtype_code, stream=stream,
+                                   d_gram=0 if want_fused else S_leg.data_ptr(), max_multiplicity=1)
+        is_fused = False
+        if want_fused:
+            handle = None
+            try:
+                handle = nat_leg.exportIpcHandle()
+            except Exception as exc:
+                print(f"[bench] rank {rank}: leg context: no IPC export ({exc!r})", file=sys.stderr)
+            hs = [None] * world
+            dist.all_gather_object(hs, handle)
+            ok = 0
+            if all(h is not None for h in hs):
+                try:
+                    nat_leg.setPeers(hs, rank, mode="owner_rows" if args.reduce == "scatter" else "replicate")
+                    ok = 1
+                except Exception as exc:
+                    print(f"[bench] rank {rank}: leg context: peer-memory reduce unavailable ({exc!r})", file=sys.stderr)
+            if agree(ok == 1):
+                is_fused = True
+            else:
+                nat_leg.close()
+                nat_leg = native.NativePca(n_leg, device=local_rank, dtype=dtype_code, stream=stream, d_gram=S_leg.data_ptr(),
+                                           max_multiplicity=1)
+        return nat_leg, S_leg, is_fused
+
+    def run_leg(label, n_leg, vpg_leg, dtype_name, min_seconds, max_steps=2000):
+        """`min_seconds` of back-to-back steps on a resident shard of vpg_leg variants per GPU."""
+        dcode = {"i8": native.DTYPE_I8, "bf16": native.DTYPE_BF16, "e2m1": native.DTYPE_E2M1}[dtype_name]
+        ebytes = {"i8": 1.0, "bf16": 2.0, "e2m1": 0.5}[dtype_name]
+        nat_l, S_l, fused_l = open_context(n_leg, dcode)
+        try:
+            Xl = torch.empty(nat_l.panelBytes(vpg_leg, P_leg), dtype=torch.uint8, device=dev)
+            nat_l.synthPanelsDevice(SEED, rank * vpg_leg, vpg_leg, 0, Xl.data_ptr(), P_leg)
+            torch.cuda.synchronize()
+
+            def leg_step():
+                nat_l.reset()
+                if fused_l:
+                    nat_l.peerBarrier()
+                    nat_l.accumulatePanels(Xl.data_ptr(), vpg_leg, P_leg)
+                    nat_l.gatherGram()
+                else:
+                    nat_l.accumulatePanels(Xl.data_ptr(), vpg_leg, P_leg)
+                    if world > 1:
+                        dist.all_reduce(S_l)
+                nat_l.finalizeGram()
+
+            for _ in range(3):
+                leg_step()
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            leg_step()
+            p1.record()
+            barrier()
+            est = torch.tensor([max(p0.elapsed_time(p1), 1e-3)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(est, op=dist.ReduceOp.MAX)       # every rank runs the same number of steps
+            k = int(min(max_steps, max(3, -(-min_seconds * 1e3 // float(est.item())))))
+            smp = ClockSampler(local_rank)
+            smp.start()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(k):
+                leg_step()
+            q1.record()
+            barrier()
+            clk = smp.stop()
+            ms_l = q0.elapsed_time(q1)
+            if world > 1:
+                t = torch.tensor([ms_l], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_l = float(t.item())
+            kern_ms = float(nat_l.stats()["last_gram_ms"])
+            if fused_l:
+                S_l.copy_(torch.from_numpy(nat_l.getGram()))
+            torch.cuda.synchronize()
+            # size-independent parity: symmetric, and diag(S)_i = number of variants sample i carries (over all ranks)
+            npan = (vpg_leg + P_leg - 1) // P_leg
+            carriers = torch.zeros(n_leg, dtype=torch.int64, device=dev)
+            for pn in range(npan):
+                if dtype_name == "e2m1":
+                    blk = Xl.view(npan, n_leg, P_leg // 2)[pn]
+                    carriers += ((blk & 0x0F) != 0).sum(dim=1) + ((blk >> 4) != 0).sum(dim=1)
+                elif dtype_name == "bf16":
+                    carriers += (Xl.view(torch.bfloat16).view(npan, n_leg, P_leg)[pn] != 0).sum(dim=1)
+                else:
+                    carriers += (Xl.view(torch.int8).view(npan, n_leg, P_leg)[pn] != 0).sum(dim=1)
+            if world > 1:
+                dist.all_reduce(carriers)
+            mult = {"i8": 2.0, "bf16": 1.0, "e2m1": 4.0 if os.environ.get("VPCA_E2M1_MXF4", "1") != "0" else 2.0}[dtype_name]
+            ops_l = float(n_leg) * (n_leg + 1) * vpg_leg                      # SYRK-minimal, per GPU
+            out = {"workload": f"{n_leg} samples x {vpg_leg} variants per GPU ({vpg_leg * world} total), {dtype_name}",
+                   "value": n_leg * vpg_leg * world * k / (ms_l * 1e-3), "unit": UNIT, "steps": k, "seconds": ms_l * 1e-3,
+                   "ms_per_step": ms_l / k, "gram_kernel_ms_last": kern_ms,
+                   "per_gpu_tops_step": ops_l / (ms_l / k * 1e-3) / 1e12,
+                   "per_gpu_tops_kernel": ops_l / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else None,
+                   "frac_of_sustained_peak": ops_l / (ms_l / k * 1e-3) / 1e12 / (mult * peaks["bf16_tflops_sustained"]),
+                   "frac_of_nominal_peak": ops_l / (ms_l / k * 1e-3) / 1e12 / (mult * 2250.0),
+                   "peak_source": "%g x bf16_tflops_sustained (%s) of MEASURED_PEAKS.json; nominal = %g x 2250 TFLOP/s dense"
+                                  % (mult, peaks["source"], mult),
+                   "hbm_gbs_algorithmic": (n_leg * vpg_leg * ebytes + 4.0 * n_leg * n_leg) / (ms_l / k * 1e-3) / 1e9,
+                   "reduce": "fused peer-memory reduce" if fused_l else ("nccl all-reduce" if world > 1 else "none (1 GPU)"),
+                   "clocks": clk,
+                   "checks": {"gram_symmetric": bool(torch.equal(S_l, S_l.t())),
+                              "diag_equals_carrier_counts": bool(torch.equal(torch.diagonal(S_l).to(torch.int64), carriers))}}
+            del Xl
+            return out, S_l
+        finally:
+            nat_l.close()
+
+    legs = {}
+    P_leg = args.panel_variants if args.panel_variants > 0 else 8192
+    if not args.no_legs and n <= 65535:
+        if args.c3_variants_per_gpu > 0:
+            for dn in ("i8", "e2m1"):
+                try:
+                    res, S3 = run_leg("c3", n, args.c3_variants_per_gpu, dn, args.c3_seconds if dn == "i8" else 0.5)
+                    if dn == "i8":
+                        res["is_baseline_config"] = ("configs[2] (2504 x 40 M at 8 GPUs)" if world == 8 and n == N_SAMPLES and
+                                                     args.c3_variants_per_gpu == 5_000_000 else "configs[2] per-GPU shard")
+                        legs["c3"] = res
+                        S3_i8 = S3
+                    else:
+                        res["gram_bit_identical_to_int8_leg"] = bool(torch.equal(S3, S3_i8)) if "c3" in legs else None
+                        legs["c3_e2m1"] = res
+                    del S3
+                except Exception as exc:                     # an auxiliary leg must never cost the headline line
+                    legs["c3" if dn == "i8" else "c3_e2m1"] = {"error": repr(exc)[:300]}
+                    if world > 1:
+                        break                                # ranks may be out of step after a failed collective leg
+            S3_i8 = None
+        if args.c5_variants_per_gpu > 0 and "error" not in legs.get("c3", {}) and "error" not in legs.get("c3_e2m1", {}):
+            try:
+                torch.cuda.empty_cache()
+                res, S5 = run_leg("c5_bf16", args.c5_samples, args.c5_variants_per_gpu, "bf16", 0.4, max_steps=50)
+                res["is_baseline_config"] = ("configs[4] (10 000 x 10 M at 8 GPUs)" if world == 8 else
+                                             f"configs[4] per-GPU shard: point {world} of the 1/2/4/8 sweep")
+                legs["c5_bf16"] = res
+                del S5
+            except Exception as exc:
+                legs["c5_bf16"] = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, info = cpu_similarity_sample(n, args.cpu_seconds)
+        v, info = cpu_similarity_sample(n, args.cpu_sample_variants, repeats=args.cpu_repeats)
         cpu = {"value": v, "unit": UNIT, "cores": info["threads"], "kind": "port",
-               "sample": f"{info['variants']} variants x {n} samples ({info['seconds']:.1f} s), oracle/vpca_oracle.c "
-                         f"vo_similarity = VariantsPca.scala:182-191 restated, OpenMP; Gram only"}
+               "sample": f"{info['variants']} variants x {n} samples (fixed sample; median {info['seconds']:.2f} s of "
+                         f"{len(info['seconds_all'])} passes), oracle/vpca_oracle.c vo_similarity = VariantsPca.scala:182-191 "
+                         f"restated, OpenMP, one partition matrix per physical core; Gram only",
+               "threads": info["threads"], "numa": info["numa"], "seconds_all": info["seconds_all"]}
         try:
             cpu["strong_cpu_blas"] = cpu_blas_sample(n)
         except Exception as exc:
@@ -719,8 +917,9 @@ def run_b200(args):
             "vs_baseline": None, "dtype": dname, "data": "synthetic",
             "config": {"workload": f"{n} samples x {vpg} variants per GPU ({vpg * world} total), "
                                    f"{dname} binary carrier genotypes, Gram"
-                                   f"{' + NCCL all-reduce' if world > 1 else ''} + symmetrize "
-                                   "(BASELINE configs[1] per GPU; 8 x 5M is configs[2])",
+                                   + ("" if world == 1 else (" + fused reduce-scatter / all-gather over peer memory" if scatter else
+                                                             " + fused peer-memory reduce" if fused else " + NCCL all-reduce"))
+                                   + " + symmetrize (BASELINE configs[1] per GPU; the c3 leg is configs[2]'s per-GPU shard)",
                        "samples": n, "variants_per_gpu": vpg, "parallelism": f"variant-sharded x{world}",
                        "hbm_layout": (f"panels of {P} variants x {n} samples (vpca_accumulate_panels)" if P > 0
                                       else "row-major samples x variants"),
@@ -732,6 +931,7 @@ def run_b200(args):
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
             "eig_ms": eig_ms, "eig": eig_info, "checks": checks, "fused_close_ms": fused_close_ms,
         }
+        line.update(legs)
         if alt is not None:
             line["packed_e2m1"] = alt
         if e2e is not None:

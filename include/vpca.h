@@ -303,6 +303,18 @@ int vpca_get_stats(vpca_ctx* ctx, vpca_stats* out);
  * or a negative vpca_status.  Synchronises the stream. */
 int vpca_debug_gram_profile(vpca_ctx* ctx, int64_t* out, int32_t max_ctas);
 
+/* Host-only introspection of the Gram schedule (works without a GPU; what tests/test_schedule.py checks).
+ * vpca_debug_tiles: the output tiles the kernel enumerates for n_samples -- 8 int32 per tile {rowA of CTA 0, rowA of CTA 1,
+ *   rowB, n_eff (MMA N), weight prefix, flags (1: a 128-block above the diagonal is written transposed, 2: CTA 1 is a
+ *   filler), 0, 0}; exact != 0: the exact 128-block cover of the lower triangle (every block of
+ *   `for (c1 <- callset; c2 <- callset)`, VariantsPca.scala:186-188, with c2 <= c1 computed exactly once), 0: the 256 x 240
+ *   rectangles kind::mxf4 uses.  Returns the tile count (may exceed max_tiles).
+ * vpca_debug_plan: the (worker, tile, first k-block, end k-block, TMEM column, TMEM columns of the worker) pieces of one
+ *   window of kb_window k-blocks under an equal split -- 6 int32 per piece; returns the piece count, or -(1 + worker) when
+ *   a worker would own more pieces than the kernel supports. */
+int vpca_debug_tiles(int32_t n_samples, int32_t cta_group, int32_t exact, int32_t* out, int32_t max_tiles);
+int vpca_debug_plan(const int32_t* tiles, int32_t num_tiles, int32_t workers, int32_t kb_window, int32_t* out, int32_t max_pieces);
+
 #ifdef __cplusplus
 }
 #endif

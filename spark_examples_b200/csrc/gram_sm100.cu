@@ -9,10 +9,16 @@
 //   ->  int32 / fp32 accumulators in TMEM  ->  tcgen05.ld  ->  red.global.add.s32 into the lower triangle of S.
 //
 // Work decomposition ("window-synchronous stream-K"):
-//   * output tiles are BM x BN blocks of S that touch the lower triangle (BM x BN = 256 x 256 per CTA pair with
-//     cta_group::2, 128 x 256 per CTA with cta_group::1); the accumulator of tile (a, b) holds
-//     D[m][n] = sum_v X[a*BM + m][v] * X[b*BN + n][v] and is written TRANSPOSED, S[b*BN + n][a*BM + m], so that the
-//     32 lanes of a warp (= 32 consecutive m) hit 32 consecutive int32 of one row of S;
+//   * an output tile is the product of A row blocks (128 samples each: one per CTA, so two with cta_group::2) and up to
+//     256 B rows; its accumulator holds D[m][n] = sum_v X[rowA + m][v] * X[rowB + n][v] and is written TRANSPOSED,
+//     S[rowB + n][rowA + m], so that the 32 lanes of a warp (= 32 consecutive m) hit 32 consecutive int32 of one row of S;
+//   * EXACT BLOCK COVER (int8 / bf16 / f8f6f4): in units of 128 x 128 blocks the lower triangle of S has nb (nb + 1) / 2
+//     blocks, and a tile always multiplies TWO A blocks (M = 256: an MMA costs 128 rows per CTA whatever it needs), so
+//     the square 256 x 256 tiling pays 4 blocks for each of the nb / 2 diagonal tiles although only 3 are needed.  The
+//     A blocks of a pair need not be adjacent and the B rows may be a single block (N = 128), and a block above the
+//     diagonal may be computed in place of its mirror image and written transposed; with that freedom the tile list of
+//     build_tiles covers every needed block exactly once (2504 samples: 210 blocks instead of 220, 4.5 % less MMA
+//     work).  kind::mxf4 keeps the square 256 x 240 tiling (its block scales take 16 TMEM columns);
 //   * the variant axis is cut into k-blocks of 128 bytes (one swizzle atom) and into windows of `kb_window`
 //     k-blocks; in every window the (tile, k-block) units are split evenly over the workers (CTA pairs), and all
 //     workers walk the windows in the same order, so the slice of X a window needs (n x kb_window*128 B, sized to
@@ -51,8 +57,6 @@ constexpr long long kWatchdogCycles = 20000000000LL;   // ~10 s: a stuck barrier
 
 template <int CG, int KIND = 0>
 struct Cfg {
-    static constexpr int BM = 128 * CG;
-    static constexpr int BN = (KIND == 3) ? kUmmaNScaled : kUmmaN;
     static constexpr int A_BYTES = kBoxBytes;                  // per CTA per stage
     static constexpr int B_BYTES = (kUmmaN / CG) * kKBytes;    // per CTA per stage (32 KiB / 16 KiB): whole 128-row boxes
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -63,16 +67,31 @@ struct Cfg {
 
 constexpr int kMaxPeers = 16;
 
+// One output tile: (A block of CTA 0, A block of CTA 1) x (n_eff B rows from rowB).
+struct TileDesc {
+    int rowA0, rowA1;   // first sample of the A block of CTA 0 / CTA 1 (cta_group::1: rowA0 only)
+    int rowB;           // first sample of the B rows
+    int n_eff;          // MMA N: B rows that exist, rounded up to 16
+    int wstart;         // sum of the weights (n_eff / 16) of the tiles before this one
+    int flags;          // kTileXpose: a 128-block above the diagonal is written transposed (it stands in for its mirror
+                        // image) instead of being skipped; kTileFiller: CTA 1's A block only pads the pair, drop its output
+    int pad0, pad1;
+};
+constexpr int kTileXpose = 1, kTileFiller = 2;
+constexpr int kMaxSegs = 4;   // (tile, k-range) pieces one worker may own per window in resident mode
+
 struct GramArgs {
     int32_t* S;
     int32_t* peer[kMaxPeers];   // num_peers > 0: the flush goes to peer-mapped Grams (own included) over NVLink:
     int num_peers;              //   peer_mode 0: into ALL of them (replicated reduce);
     int peer_mode;              //   peer_mode 1: only into the Gram of the rank that owns the row (reduce-scatter)
     int own_end[kMaxPeers];     // rank q owns Gram rows [own_end[q-1], own_end[q]); multiples of 32, >= 32 apart
-    const int2* tiles;
+    const TileDesc* tiles;
     int* err;          // mapped host memory: watchdog diagnostics
     int n;
     int num_tiles;
+    int num_full;      // leading tiles of full weight: what the large-N schedule deals out in whole-tile waves
+    int total_weight;  // sum of n_eff / 16 over all tiles
     int kb_total;
     int kb_window;
     int num_workers;
@@ -89,18 +108,67 @@ struct GramArgs {
 };
 
 struct Seg {
-    int tile, kb0, kb1, slot, first, flush, use, win, last_in_win;
+    int tile, kb0, kb1, col, slot, first, flush, use, win, last_in_win;   // slot: which accumulator barrier pair
+    int rowA0, rowA1, rowB, n_eff, flags;
 };
 
+// The pieces of a weighted unit range [u_begin, u_end) -- tile t occupies [wstart_t * len, (wstart_t + w_t) * len) and its
+// k-block q sits at wstart_t * len + q * w_t -- as (tile, k-range, TMEM column) triples.  Two workers that share a
+// boundary u agree on the k-block it falls in (both take floor((u - base) / w_t)), so the pieces partition every tile.
+// Shared by the kernel, by the host (which decides whether the accumulators of a worker fit TMEM) and by the rebalancer.
+struct SegPlan {
+    int n;
+    int tile[kMaxSegs], lo[kMaxSegs], hi[kMaxSegs], col[kMaxSegs];
+    int cols;      // TMEM columns needed
+    int overflow;  // more than kMaxSegs pieces
+};
+
+__host__ __device__ inline void plan_segments(const TileDesc* tiles, int num_tiles, int first_tile, long long u_begin,
+                                              long long u_end, int len, SegPlan& p) {
+    p.n = 0;
+    p.cols = 0;
+    p.overflow = 0;
+    const long long origin = (long long)tiles[first_tile].wstart * len;
+    long long u = u_begin;
+    int t = first_tile;
+    while (u < u_end && t < num_tiles) {
+        const int w = tiles[t].n_eff >> 4;
+        const long long base = (long long)tiles[t].wstart * len - origin;
+        const long long tend = base + (long long)w * len;
+        if (tend <= u) {
+            ++t;
+            continue;
+        }
+        const long long e = u_end < tend ? u_end : tend;
+        const int lo = (int)((u - base) / w);
+        const int hi = e == tend ? len : (int)((e - base) / w);
+        u = e;
+        if (lo >= hi) continue;   // a sliver thinner than one k-block: the neighbour owns that k-block
+        if (p.n == kMaxSegs) {
+            p.overflow = 1;
+            return;
+        }
+        p.tile[p.n] = t;
+        p.lo[p.n] = lo;
+        p.hi[p.n] = hi;
+        p.col[p.n] = p.cols;
+        p.cols += (tiles[t].n_eff + 31) & ~31;
+        ++p.n;
+    }
+}
+
 // Every role of a worker (TMA producer, MMA issuer, epilogue) replays the same deterministic schedule.
-//   resident (tiles <= workers):  window-synchronous stream-K, both accumulators live for the whole launch;
+//   resident (every worker's accumulators fit TMEM):  window-synchronous stream-K -- the worker owns the same pieces
+//               (tile, k-range) in every window, so its accumulators stay in TMEM for the whole launch;
 //   otherwise:  full tiles in waves (wave i = tiles [i W, (i+1) W), one per worker, whole K) -- the tile list is ordered
-//               so that a wave is a compact 2-D block of S and shares few row panels of X -- then the < W leftover
+//               so that a wave is a compact 2-D block of S and shares few row panels of X -- then the leftover
 //               tiles are split stream-K style over all workers; accumulators double-buffered against the epilogue.
 struct Sched {
+    SegPlan plan;
     long long u_begin, u_end, u;
-    int kbw, nwin, kb_total, resident, win, seg_in_win, nflush;
-    int worker, workers, num_tiles, wave, full_waves;
+    int kbw, nwin, kb_total, resident, win, seg_i, nflush;
+    int worker, workers, num_tiles, wave, full_waves, tail_first;
+    const TileDesc* tiles;
 
     __device__ void init(const GramArgs& a, int w) {
         kbw = a.kb_window;
@@ -109,23 +177,38 @@ struct Sched {
         worker = w;
         workers = a.num_workers;
         num_tiles = a.num_tiles;
+        tiles = a.tiles;
         nwin = (kb_total + kbw - 1) / kbw;
         win = 0;
-        seg_in_win = 0;
+        seg_i = 0;
         nflush = 0;
         wave = 0;
         if (resident) {
-            const long long uw = (long long)a.num_tiles * kbw;
+            const long long uw = (long long)a.total_weight * kbw;
             // speed-weighted split (equal shares until the first launches have been timed, see rebalance_kernel)
             u_begin = (long long)((double)uw * a.cum[worker]);
             u_end = (worker + 1 == a.num_workers) ? uw : (long long)((double)uw * a.cum[worker + 1]);
+            plan_segments(tiles, num_tiles, 0, u_begin, u_end, kbw, plan);
         } else {
-            full_waves = num_tiles / workers;
-            const long long tail_units = (long long)(num_tiles - full_waves * workers) * kb_total;
-            u_begin = tail_units * worker / workers;       // units of the leftover tiles, relative to the first of them
+            full_waves = a.num_full / workers;
+            tail_first = full_waves * workers;
+            const long long tail_units =
+                tail_first < num_tiles ? (long long)(a.total_weight - tiles[tail_first].wstart) * kb_total : 0;
+            u_begin = tail_units * worker / workers;       // weighted units of the leftover tiles
             u_end = tail_units * (worker + 1) / workers;
+            plan.n = 0;
         }
         u = u_begin;
+    }
+    __device__ void fill(Seg& s, int t) const {
+        const int4 lo = __ldg(reinterpret_cast<const int4*>(tiles + t));
+        const int4 hi = __ldg(reinterpret_cast<const int4*>(tiles + t) + 1);
+        s.tile = t;
+        s.rowA0 = lo.x;
+        s.rowA1 = lo.y;
+        s.rowB = lo.z;
+        s.n_eff = lo.w;
+        s.flags = hi.y;
     }
     __device__ bool next(Seg& s) {
         if (!resident) {
@@ -134,51 +217,56 @@ struct Sched {
             s.first = 1;
             s.flush = 1;
             s.slot = nflush & 1;
+            s.col = s.slot * kUmmaN;
             s.use = nflush >> 1;
             if (wave < full_waves) {                        // one whole tile of the current wave
-                s.tile = wave * workers + worker;
+                fill(s, wave * workers + worker);
                 s.kb0 = 0;
                 s.kb1 = kb_total;
                 ++wave;
                 ++nflush;
                 return true;
             }
-            if (u >= u_end) return false;                   // stream-K tail
-            const int t = (int)(u / kb_total);
-            const int lo = (int)(u - (long long)t * kb_total);
-            const long long rem = u_end - u;
-            const int hi = rem < (long long)(kb_total - lo) ? lo + (int)rem : kb_total;
-            u += hi - lo;
-            s.tile = full_waves * workers + t;
-            s.kb0 = lo;
-            s.kb1 = hi;
-            ++nflush;
-            return true;
+            // stream-K tail: at most kMaxSegs pieces are planned at a time
+            while (true) {
+                if (seg_i < plan.n) {
+                    fill(s, plan.tile[seg_i]);
+                    s.kb0 = plan.lo[seg_i];
+                    s.kb1 = plan.hi[seg_i];
+                    ++seg_i;
+                    ++nflush;
+                    return true;
+                }
+                if (u >= u_end) return false;
+                // plan the next pieces: advance u to the end of what was planned
+                plan_segments(tiles, num_tiles, tail_first, u, u_end, kb_total, plan);
+                seg_i = 0;
+                if (plan.n == 0) return false;
+                const int lt = plan.tile[plan.n - 1];
+                const long long base = (long long)(tiles[lt].wstart - tiles[tail_first].wstart) * kb_total;
+                const long long endu = base + (long long)plan.hi[plan.n - 1] * (tiles[lt].n_eff >> 4);
+                u = plan.overflow ? endu : u_end;
+            }
         }
-        if (u_begin >= u_end) return false;
-        if (u >= u_end) {
+        if (plan.n == 0) return false;
+        if (seg_i == plan.n) {
             ++win;
-            u = u_begin;
-            seg_in_win = 0;
+            seg_i = 0;
         }
         if (win >= nwin) return false;
-        const int tile = (int)(u / kbw);
-        const int lo = (int)(u - (long long)tile * kbw);
-        const long long rem = u_end - u;
-        const int hi = rem < (long long)(kbw - lo) ? lo + (int)rem : kbw;
-        u += hi - lo;
+        const int i = seg_i++;
+        fill(s, plan.tile[i]);
         const int base = win * kbw;
         const int cnt = min(kbw, kb_total - base);
-        s.tile = tile;
-        s.kb0 = base + min(lo, cnt);
-        s.kb1 = base + min(hi, cnt);
+        s.kb0 = base + min(plan.lo[i], cnt);
+        s.kb1 = base + min(plan.hi[i], cnt);
         s.win = win;
-        s.last_in_win = (u >= u_end);
-        s.slot = seg_in_win;
+        s.last_in_win = (seg_i == plan.n);
+        s.col = plan.col[i];
+        s.slot = i;
         s.first = (win == 0);
         s.flush = (win == nwin - 1);
         s.use = 0;
-        ++seg_in_win;
         return true;
     }
 };
@@ -239,7 +327,8 @@ __device__ __forceinline__ uint32_t make_instr_desc(uint32_t N) {
 }
 
 template <int CG, int KIND>
-__global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                           const __grid_constant__ CUtensorMap tmap_half, const GramArgs a) {
     using C = Cfg<CG, KIND>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -249,10 +338,12 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
     auto sB = [&](uint32_t st) { return smem_base + C::STAGES * C::A_BYTES + st * C::B_BYTES; };
     auto full_bar = [&](uint32_t i) { return bar_base + 8u * i; };
     auto empty_bar = [&](uint32_t i) { return bar_base + 8u * (C::STAGES + i); };
+    // accumulator barriers: resident schedule -- one "full" barrier per accumulator of the worker (each completes once);
+    // large-N schedule -- two accumulators double-buffered through full / empty pairs 0 and 1
     auto tfull_bar = [&](uint32_t i) { return bar_base + 8u * (2 * C::STAGES + i); };
-    auto tempty_bar = [&](uint32_t i) { return bar_base + 8u * (2 * C::STAGES + 2 + i); };
+    auto tempty_bar = [&](uint32_t i) { return bar_base + 8u * (2 * C::STAGES + kMaxSegs + i); };
     volatile uint32_t* tmem_ptr_smem =
-        reinterpret_cast<volatile uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+        reinterpret_cast<volatile uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + kMaxSegs + 2));
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const uint32_t lane = ptx::lane_id();
@@ -265,15 +356,14 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
 
     if (warp == 0 && issuer) {
         ptx::prefetch_tensormap(&tmap);
+        ptx::prefetch_tensormap(&tmap_half);
     } else if (warp == 1 && issuer) {
         for (uint32_t i = 0; i < (uint32_t)C::STAGES; ++i) {
             ptx::mbar_init(full_bar(i), CG);    // producer arrive(s): leader expect_tx (+ peer's remote arrive)
             ptx::mbar_init(empty_bar(i), 1);    // one tcgen05.commit per use
         }
-        for (uint32_t i = 0; i < 2; ++i) {
-            ptx::mbar_init(tfull_bar(i), 1);
-            ptx::mbar_init(tempty_bar(i), CG * 128);   // every epilogue thread of the pair arrives at the leader
-        }
+        for (uint32_t i = 0; i < (uint32_t)kMaxSegs; ++i) ptx::mbar_init(tfull_bar(i), 1);
+        for (uint32_t i = 0; i < 2; ++i) ptx::mbar_init(tempty_bar(i), CG * 128);   // every epilogue thread of the pair arrives at the leader
         ptx::fence_mbar_init();
     } else if (warp == 2) {
         ptx::tmem_alloc<CG>(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
@@ -305,12 +395,13 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
             uint32_t it = 0;
             int synced_win = -1;
             while (sc.next(s)) {
-                const int2 t = a.tiles[s.tile];
-                const int rowA = t.x * C::BM + (int)cta_rank * kBoxRows;
-                // Edge tiles issue a narrower MMA (N = rows of S that exist, rounded up to 16); with cta_group::2 each CTA
-                // supplies half of those N rows, so its box starts at half * N / 2 (= half * 128 for full tiles).
-                const int n_eff = min(C::BN, ((a.n - t.y * C::BN) + 15) & ~15);
-                const int rowB = t.y * C::BN + ((CG == 2) ? (int)cta_rank * (n_eff / 2) : 0);
+                // with cta_group::2 each CTA supplies its own A block and half of the N = n_eff B rows
+                const int rowA = (CG == 2 && cta_rank != 0) ? s.rowA1 : s.rowA0;
+                const int rowB = s.rowB + ((CG == 2) ? (int)cta_rank * (s.n_eff / 2) : 0);
+                // B rows per CTA: a 64-row box is enough for the N <= 128 tiles of the exact block cover (cta_group::2)
+                const bool half_box = (CG == 2) && (s.n_eff <= 128);
+                const bool two_boxes = (CG == 1) && (s.n_eff > kBoxRows);
+                const uint32_t tx_cta = (uint32_t)(C::A_BYTES + (half_box ? kBoxBytes / 2 : (two_boxes ? 2 * kBoxBytes : kBoxBytes)));
                 if (a.sync_lead > 0 && leader && s.win != synced_win) {
                     synced_win = s.win;
                     if (s.win >= a.sync_lead) wait_window(a.win_done, s.win - a.sync_lead, a.active_workers);
@@ -321,14 +412,14 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                     const int pnl = kb / a.kb_per_panel;
                     const int kc = (kb - pnl * a.kb_per_panel) * a.elems_per_kb;
                     if constexpr (CG == 1) {
-                        ptx::mbar_arrive_expect_tx(full_bar(st), (uint32_t)C::STAGE_BYTES >> a.tx_shift);
+                        ptx::mbar_arrive_expect_tx(full_bar(st), tx_cta >> a.tx_shift);
                         ptx::tma_load_3d(sA(st), &tmap, full_bar(st), kc, rowA, pnl);
                         ptx::tma_load_3d(sB(st), &tmap, full_bar(st), kc, rowB, pnl);
-                        ptx::tma_load_3d(sB(st) + kBoxBytes, &tmap, full_bar(st), kc, rowB + kBoxRows, pnl);
+                        if (two_boxes) ptx::tma_load_3d(sB(st) + kBoxBytes, &tmap, full_bar(st), kc, rowB + kBoxRows, pnl);
                     } else {
                         ptx::tma_load_3d_2sm(sA(st), &tmap, full_bar(st), kc, rowA, pnl);
-                        ptx::tma_load_3d_2sm(sB(st), &tmap, full_bar(st), kc, rowB, pnl);
-                        if (leader) ptx::mbar_arrive_expect_tx(full_bar(st), (uint32_t)(2 * C::STAGE_BYTES) >> a.tx_shift);
+                        ptx::tma_load_3d_2sm(sB(st), half_box ? &tmap_half : &tmap, full_bar(st), kc, rowB, pnl);
+                        if (leader) ptx::mbar_arrive_expect_tx(full_bar(st), (2u * tx_cta) >> a.tx_shift);
                         else ptx::mbar_arrive_cluster(full_bar(st), 0);
                     }
                 }
@@ -343,13 +434,12 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
         Seg s;
         uint32_t it = 0;
         while (sc.next(s)) {
-            if (s.first) {
-                mbar_wait(tempty_bar(s.slot), (uint32_t)(s.use & 1) ^ 1u, a.err, 2);
+            if (s.first && !a.resident) {   // resident accumulators are written once per launch: nothing to wait for
+                mbar_wait(tempty_bar((uint32_t)s.slot), (uint32_t)(s.use & 1) ^ 1u, a.err, 2);
                 ptx::tc_fence_after();
             }
-            const uint32_t d_tmem = tmem_base + (uint32_t)s.slot * C::BN;
-            const int by = a.tiles[s.tile].y;
-            const uint32_t idesc = make_instr_desc<CG, KIND>((uint32_t)min(C::BN, ((a.n - by * C::BN) + 15) & ~15));
+            const uint32_t d_tmem = tmem_base + (uint32_t)s.col;
+            const uint32_t idesc = make_instr_desc<CG, KIND>((uint32_t)s.n_eff);
             for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
                 const uint32_t st = it % C::STAGES, ph = (it / C::STAGES) & 1u;
                 mbar_wait(full_bar(st), ph, a.err, 3);
@@ -372,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                 __syncwarp();
             }
             if (s.flush) {
-                if (issuer) ptx::umma_commit<CG>(tfull_bar(s.slot));   // accumulator complete -> epilogue
+                if (issuer) ptx::umma_commit<CG>(tfull_bar((uint32_t)s.slot));   // accumulator complete -> epilogue
                 __syncwarp();
             }
         }
@@ -385,52 +475,64 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
         Seg s;
         while (sc.next(s)) {
             if (!s.flush) continue;
-            mbar_wait(tfull_bar(s.slot), (uint32_t)(s.use & 1), a.err, 4);
+            const uint32_t bar_i = (uint32_t)s.slot;
+            mbar_wait(tfull_bar(bar_i), (uint32_t)(s.use & 1), a.err, 4);
             ptx::tc_fence_after();
-            const int2 t = a.tiles[s.tile];
-            const int col = t.x * C::BM + (int)cta_rank * kBoxRows + q * 32 + (int)lane;   // sample of the A row
-            const int col_warp_min = col - (int)lane;
-            const int row0 = t.y * C::BN;                                                  // samples of the B rows
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s.slot * C::BN;
-            int32_t* out = a.S + col;
-            const int row_end = min(a.n, row0 + C::BN);                    // rows this tile owns (BN may be 240)
+            const bool filler = (CG == 2) && cta_rank != 0 && (s.flags & kTileFiller) != 0;
+            const int colbase = ((CG == 2 && cta_rank != 0) ? s.rowA1 : s.rowA0) + q * 32;   // sample of the A row, lane 0
+            const int col = colbase + (int)lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s.col;
+            const int row_end = min(a.n, s.rowB + s.n_eff);                 // B rows this tile owns
+            const int nchunks = filler ? 0 : (s.n_eff + 31) / 32;
 #pragma unroll 1
-            for (int c = 0; c < (C::BN + 31) / 32; ++c) {
-                const int rbase = row0 + c * 32;
-                if (rbase >= row_end || rbase + 31 < col_warp_min) continue;   // outside the tile or above the diagonal
+            for (int c = 0; c < nchunks; ++c) {
+                const int rbase = s.rowB + c * 32;
+                if (rbase >= row_end) break;
+                // A chunk wholly above the diagonal is the mirror image of a cell the lower triangle already gets --
+                // unless this tile computes a 128-block above the diagonal IN PLACE of its mirror image (exact block
+                // cover): then the chunk is written transposed, S[col][row].
+                bool xpose = false;
+                if (rbase + 31 < colbase) {
+                    if ((s.flags & kTileXpose) == 0 || (rbase >> 7) >= (colbase >> 7)) continue;
+                    xpose = true;
+                }
                 uint32_t r[32];
                 ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
                 ptx::tmem_ld_wait();
-                // owner-rows mode: the (at most two) ranks that own rows of this 32-row chunk
+                // owner-rows mode: the (at most two) ranks that own rows of this 32-row chunk; a transposed chunk
+                // writes row `col`, one owner per lane
                 int32_t* own_lo = nullptr;
                 int32_t* own_hi = nullptr;
                 int own_split = 0;
                 if (a.num_peers != 0 && a.peer_mode == 1) {
-                    int q = 0;
-                    while (q + 1 < a.num_peers && rbase >= a.own_end[q]) ++q;
-                    own_split = a.own_end[q];
-                    own_lo = a.peer[q];
-                    own_hi = a.peer[min(q + 1, a.num_peers - 1)];
+                    const int probe = xpose ? col : rbase;
+                    int o = 0;
+                    while (o + 1 < a.num_peers && probe >= a.own_end[o]) ++o;
+                    own_split = xpose ? 0x7fffffff : a.own_end[o];
+                    own_lo = a.peer[o];
+                    own_hi = a.peer[min(o + 1, a.num_peers - 1)];
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int row = rbase + j;
-                    if (row < row_end && col < a.n && row >= col) {
+                    if (row < row_end && col < a.n && (xpose || row >= col)) {
                         int v;
                         if constexpr (KIND == 0) v = (int)r[j];
                         else v = __float2int_rn(__uint_as_float(r[j]));
                         if (v != 0) {
-                            const size_t o = (size_t)row * (size_t)a.n;
+                            // cell (srow, scol) of S: the lower-triangle position of this product
+                            const int srow = xpose ? col : row, scol = xpose ? row : col;
+                            const size_t o = (size_t)srow * (size_t)a.n + (size_t)scol;
                             if (a.num_peers == 0) {
-                                asm volatile("red.global.add.s32 [%0], %1;" ::"l"(out + o), "r"(v) : "memory");
+                                asm volatile("red.global.add.s32 [%0], %1;" ::"l"(a.S + o), "r"(v) : "memory");
                             } else if (a.peer_mode == 1) {
                                 // fused reduce-scatter: one red, into the Gram of the rank that owns this row
-                                int32_t* dst = (row >= own_split ? own_hi : own_lo) + col + o;
+                                int32_t* dst = (srow >= own_split ? own_hi : own_lo) + o;
                                 asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(dst), "r"(v) : "memory");
                             } else {
                                 // fused reduceByKey: the same red, once per rank, on peer-mapped Gram buffers
                                 for (int d = 0; d < a.num_peers; ++d)
-                                    asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(a.peer[d] + col + o), "r"(v)
+                                    asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(a.peer[d] + o), "r"(v)
                                                  : "memory");
                             }
                         }
@@ -438,8 +540,10 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                 }
             }
             ptx::tc_fence_before();
-            if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(s.slot));
-            else ptx::mbar_arrive_cluster(tempty_bar(s.slot), 0);
+            if (!a.resident) {   // hand the accumulator back to the MMA issuer (double buffering of the large-N schedule)
+                if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(bar_i));
+                else ptx::mbar_arrive_cluster(tempty_bar(bar_i), 0);
+            }
         }
     }
 
@@ -457,9 +561,12 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
 // stays exact whatever the split is (integer atomics); shares are clamped so that a worker never spans more than
 // the two tiles it has TMEM accumulators for.
 __global__ void rebalance_kernel(const long long* __restrict__ prof, double* __restrict__ cum, int workers, int cta_group,
-                                 double max_share, long long min_ns, int* __restrict__ gen) {
+                                 double max_share, long long min_ns, int* __restrict__ gen, const TileDesc* __restrict__ tiles,
+                                 int num_tiles, int total_weight, int kbw, int col_limit) {
     __shared__ double sh[1024];
+    __shared__ double cand[1025];
     __shared__ double red_sum, red_min;
+    __shared__ int reject;
     const int w = threadIdx.x;
     const bool active = w < workers;
     double t = 0.0, share_old = 0.0;
@@ -469,6 +576,7 @@ __global__ void rebalance_kernel(const long long* __restrict__ prof, double* __r
         share_old = cum[w + 1] - cum[w];
     }
     sh[w] = active ? t : 1e30;
+    if (w == 0) reject = 0;
     __syncthreads();
     if (w == 0) {
         double mn = 1e30, mx = 0.0;
@@ -504,13 +612,26 @@ __global__ void rebalance_kernel(const long long* __restrict__ prof, double* __r
         double sum = 0.0;
         for (int i = 0; i < workers; ++i) sum += sh[i];
         double acc = 0.0;
-        cum[0] = 0.0;
+        cand[0] = 0.0;
         for (int i = 0; i < workers; ++i) {
             acc += sh[i] / sum;
-            cum[i + 1] = (i + 1 == workers) ? 1.0 : acc;
+            cand[i + 1] = (i + 1 == workers) ? 1.0 : acc;
         }
-        *gen += 1;
     }
+    __syncthreads();
+    // the new split is published only if every worker's accumulators still fit TMEM under it
+    if (active) {
+        const long long uw = (long long)total_weight * kbw;
+        const long long ub = (long long)((double)uw * cand[w]);
+        const long long ue = (w + 1 == workers) ? uw : (long long)((double)uw * cand[w + 1]);
+        SegPlan p;
+        plan_segments(tiles, num_tiles, 0, ub, ue, kbw, p);
+        if (p.overflow || p.cols > col_limit) atomicExch(&reject, 1);
+    }
+    __syncthreads();
+    if (reject) return;
+    if (w <= workers) cum[w] = cand[w];
+    if (w == 0) *gen += 1;
 }
 
 __global__ void init_cum_kernel(double* __restrict__ cum, int workers) {
@@ -659,7 +780,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 template <int CG, int KIND>
-cudaError_t launch(const CUtensorMap& tmap, const GramArgs& args, int grid, cudaStream_t stream) {
+cudaError_t launch(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const GramArgs& args, int grid, cudaStream_t stream) {
     using C = Cfg<CG, KIND>;
     // per launch, not cached: the attribute is per device and one process may drive several GPUs
     cudaError_t ea = cudaFuncSetAttribute(gram_kernel<CG, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -676,13 +797,14 @@ cudaError_t launch(const CUtensorMap& tmap, const GramArgs& args, int grid, cuda
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gram_kernel<CG, KIND>, tmap, args);
+    return cudaLaunchKernelEx(&cfg, gram_kernel<CG, KIND>, tmap, tmap_half, args);
 }
 
 }  // namespace
 
 void gram_plan_free(GramPlan& plan) {
     if (plan.d_tiles) cudaFree(plan.d_tiles);
+    plan.h_tiles.clear();
     if (plan.d_err) cudaFreeHost(plan.d_err);
     if (plan.d_win_done) cudaFree(plan.d_win_done);
     if (plan.d_prof) cudaFree(plan.d_prof);
@@ -702,32 +824,169 @@ int gram_read_profile(GramPlan& plan, long long* out, int max_ctas) {
     return ctas;
 }
 
-static cudaError_t build_tiles(GramPlan& plan, int n, int BN, cudaStream_t stream) {
-    const int BM = 128 * plan.cta_group;
-    std::vector<int2> tiles;
-    const int nbn = (n + BN - 1) / BN, nbm = (n + BM - 1) / BM;
-    // Strips of 8 row-blocks, walked column by column: any run of ~num_sms/2 consecutive tiles (one wave of the
-    // large-N schedule) is a compact 8 x 9 patch of S that needs 17 row panels of X instead of 75.
-    constexpr int kStrip = 8;
-    for (int bb = 0; bb < nbn; bb += kStrip)
-        for (int am = 0; am < nbm; ++am)
-            for (int b = bb; b < std::min(nbn, bb + kStrip); ++b) {
-                // tile covers output rows [b*BN, b*BN+BN) x cols [am*BM, am*BM+BM); keep it if it touches row >= col
-                const int max_row = std::min(n, b * BN + BN) - 1;
-                if (am * BM <= max_row) tiles.push_back(make_int2(am, b));
+// Tile list of the lower triangle of S.
+//   exact == false (kind::mxf4): BM x BN rectangles that touch row >= col, in strips of 8 row blocks walked column by
+//     column, so that a run of ~num_sms / 2 consecutive tiles (one wave of the large-N schedule) is a compact patch of S.
+//   exact == true: the exact block cover.  Units: 128 x 128 blocks (col block c, row block r), needed iff c <= r.  A tile
+//     multiplies `cg` A (column) blocks -- any blocks, one per CTA -- with one or two adjacent B (row) blocks.  With
+//     cta_group::2 a tile holds an even number of blocks of every row it touches, but row r needs r + 1 of them, so for
+//     r = 4t the block (col 4t, row 4t + 2) is taken out of row 4t + 2 and computed in row 4t as its mirror image
+//     (col 4t + 2, row 4t), written transposed: both rows become even and every needed block is covered exactly once.
+//     Two-row tiles come first, one-row tiles last (a worker's accumulators must fit the 512 TMEM columns).
+static void make_tiles(int n, int cg, bool exact, int bn, std::vector<TileDesc>& out, int* num_full) {
+    out.clear();
+    auto n_eff = [&](int row0, int want) { return std::min(want, ((n - row0) + 15) & ~15); };
+    if (!exact) {
+        const int BM = 128 * cg;
+        const int nbn = (n + bn - 1) / bn, nbm = (n + BM - 1) / BM;
+        constexpr int kStrip = 8;
+        for (int bb = 0; bb < nbn; bb += kStrip)
+            for (int am = 0; am < nbm; ++am)
+                for (int b = bb; b < std::min(nbn, bb + kStrip); ++b) {
+                    const int max_row = std::min(n, b * bn + bn) - 1;
+                    if (am * BM > max_row) continue;   // wholly above the diagonal
+                    TileDesc t{};
+                    t.rowA0 = am * BM;
+                    t.rowA1 = am * BM + 128;
+                    t.rowB = b * bn;
+                    t.n_eff = n_eff(b * bn, bn);
+                    out.push_back(t);
+                }
+    } else {
+        const int nb = (n + 127) / 128;
+        std::vector<TileDesc> two, one;
+        auto emit = [&](std::vector<TileDesc>& dst, int c0, int c1, int r0, int rows, bool filler) {
+            TileDesc t{};
+            t.rowA0 = c0 * 128;
+            t.rowA1 = c1 * 128;
+            t.rowB = r0 * 128;
+            t.n_eff = n_eff(r0 * 128, rows * 128);
+            t.flags = kTileXpose | (filler ? kTileFiller : 0);
+            dst.push_back(t);
+        };
+        // column blocks each row block needs (a value > the row index = the mirror image of a block of a later row)
+        std::vector<std::vector<int>> need(nb);
+        for (int r = 0; r < nb; ++r)
+            for (int c = 0; c <= r; ++c) need[r].push_back(c);
+        if (cg == 2)
+            for (int r = 0; r + 2 < nb; r += 4) {
+                need[r].push_back(r + 2);                                        // (col r + 2, row r): transposed
+                need[r + 2].erase(std::find(need[r + 2].begin(), need[r + 2].end(), r));
             }
+        for (int r0 = 0; r0 < nb; r0 += 2) {
+            const bool pair = r0 + 1 < nb;
+            std::vector<int> common, left0, left1;
+            if (pair) {
+                for (int c : need[r0])
+                    if (std::find(need[r0 + 1].begin(), need[r0 + 1].end(), c) != need[r0 + 1].end()) common.push_back(c);
+                if (cg == 2 && (common.size() & 1)) common.pop_back();          // an odd one out joins the one-row tiles
+            }
+            for (int c : need[r0])
+                if (std::find(common.begin(), common.end(), c) == common.end()) left0.push_back(c);
+            if (pair)
+                for (int c : need[r0 + 1])
+                    if (std::find(common.begin(), common.end(), c) == common.end()) left1.push_back(c);
+            for (size_t i = 0; i < common.size(); i += cg) emit(two, common[i], common[cg == 2 ? i + 1 : i], r0, 2, false);
+            for (int side = 0; side < (pair ? 2 : 1); ++side) {
+                const std::vector<int>& left = side == 0 ? left0 : left1;
+                for (size_t i = 0; i < left.size(); i += cg) {
+                    const bool filler = cg == 2 && i + 1 >= left.size();
+                    emit(one, left[i], filler ? left[i] : left[cg == 2 ? i + 1 : i], r0 + side, 1, filler);
+                }
+            }
+        }
+        // large-N schedule: whole-tile waves want equal tiles that share row panels of X -- the full-weight two-row
+        // tiles go in front, in strips of 8 row blocks walked column pair by column pair (a wave of ~74 consecutive
+        // tiles is then a compact patch of S that needs ~34 row blocks of X instead of ~150)
+        auto mid = std::stable_partition(two.begin(), two.end(), [&](const TileDesc& t) { return t.n_eff == 256; });
+        std::stable_sort(two.begin(), mid, [](const TileDesc& x, const TileDesc& y) {
+            const int sx = x.rowB / 1024, sy = y.rowB / 1024;
+            if (sx != sy) return sx < sy;
+            const int cx = std::min(x.rowA0, x.rowA1) / 256, cy = std::min(y.rowA0, y.rowA1) / 256;
+            if (cx != cy) return cx < cy;
+            return x.rowB < y.rowB;
+        });
+        *num_full = (int)(mid - two.begin());
+        out = two;
+        out.insert(out.end(), one.begin(), one.end());
+    }
+    if (!exact) *num_full = (int)out.size();   // the rectangles go out in whole-tile waves whatever their edge trim
+    int w = 0;
+    for (auto& t : out) {
+        t.wstart = w;
+        w += t.n_eff >> 4;
+    }
+}
+
+static cudaError_t build_tiles(GramPlan& plan, int n, bool exact, int BN, cudaStream_t stream) {
+    std::vector<TileDesc> tiles;
+    int num_full = 0;
+    make_tiles(n, plan.cta_group, exact, BN, tiles, &num_full);
     if (plan.d_tiles) cudaFree(plan.d_tiles);
     plan.d_tiles = nullptr;
-    cudaError_t e = cudaMalloc(&plan.d_tiles, tiles.size() * sizeof(int2));
+    cudaError_t e = cudaMalloc(&plan.d_tiles, tiles.size() * sizeof(TileDesc));
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyAsync(plan.d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, stream);
+    e = cudaMemcpyAsync(plan.d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
     e = cudaStreamSynchronize(stream);   // `tiles` is a stack vector
+    plan.h_tiles.assign(reinterpret_cast<const int32_t*>(tiles.data()),
+                        reinterpret_cast<const int32_t*>(tiles.data() + tiles.size()));
     plan.num_tiles = (int)tiles.size();
+    plan.num_full = num_full;
+    plan.total_weight = tiles.empty() ? 0 : tiles.back().wstart + (tiles.back().n_eff >> 4);
     plan.tiles_for_n = n;
     plan.tiles_for_cg = plan.cta_group;
-    plan.tiles_for_bn = BN;
+    plan.tiles_for_bn = exact ? -1 : BN;
+    plan.tiles_col_limit = exact ? (int)kTmemCols : (int)kSfCol;
     return e;
+}
+
+// Resident schedule (accumulators stay in TMEM for the whole launch) iff, under an equal split of windows of `kbw`
+// k-blocks, the pieces of every worker fit the TMEM columns (those left beside the block scales for kind::mxf4).
+static bool fits_resident(const GramPlan& plan, int workers, int kbw) {
+    if (plan.total_weight <= 0) return false;
+    const TileDesc* tiles = reinterpret_cast<const TileDesc*>(plan.h_tiles.data());
+    const long long uw = (long long)plan.total_weight * kbw;
+    for (int w = 0; w < workers; ++w) {
+        const long long ub = (long long)((double)uw * ((double)w / (double)workers));
+        const long long ue = (w + 1 == workers) ? uw : (long long)((double)uw * ((double)(w + 1) / (double)workers));
+        SegPlan p;
+        plan_segments(tiles, plan.num_tiles, 0, ub, ue, kbw, p);
+        if (p.overflow || p.cols > plan.tiles_col_limit) return false;
+    }
+    return true;
+}
+
+// Host-only introspection of the schedule (no device needed): the tile list for n samples, and the pieces
+// (tile, k-block range, TMEM column) each worker owns in a window of `kbw` k-blocks under an equal split.
+int gram_debug_tiles(int n, int cta_group, int exact, int32_t* out, int max_tiles) {
+    std::vector<TileDesc> tiles;
+    int num_full = 0;
+    make_tiles(n, cta_group == 1 ? 1 : 2, exact != 0, exact ? kUmmaN : kUmmaNScaled, tiles, &num_full);
+    const int cnt = std::min<int>((int)tiles.size(), max_tiles);
+    if (out != nullptr && cnt > 0) memcpy(out, tiles.data(), (size_t)cnt * sizeof(TileDesc));
+    return (int)tiles.size();
+}
+
+int gram_debug_plan(const int32_t* tiles8, int num_tiles, int workers, int kbw, int32_t* out, int max_pieces) {
+    const TileDesc* tiles = reinterpret_cast<const TileDesc*>(tiles8);
+    if (num_tiles <= 0) return 0;
+    const long long total = tiles[num_tiles - 1].wstart + (tiles[num_tiles - 1].n_eff >> 4);
+    const long long uw = total * kbw;
+    int cnt = 0;
+    for (int w = 0; w < workers; ++w) {
+        const long long ub = (long long)((double)uw * ((double)w / (double)workers));
+        const long long ue = (w + 1 == workers) ? uw : (long long)((double)uw * ((double)(w + 1) / (double)workers));
+        SegPlan p;
+        plan_segments(tiles, num_tiles, 0, ub, ue, kbw, p);
+        if (p.overflow) return -1 - w;
+        for (int i = 0; i < p.n; ++i, ++cnt)
+            if (cnt < max_pieces) {
+                int32_t* o = out + (size_t)cnt * 6;
+                o[0] = w; o[1] = p.tile[i]; o[2] = p.lo[i]; o[3] = p.hi[i]; o[4] = p.col[i]; o[5] = p.cols;
+            }
+    }
+    return cnt;
 }
 
 cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int n, int64_t nv, int64_t ld, int64_t panel,
@@ -754,6 +1013,8 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         if (ad != nullptr) plan.adaptive = atoi(ad) != 0;
         const char* mx = getenv("VPCA_E2M1_MXF4");
         if (mx != nullptr) plan.e2m1_mxf4 = atoi(mx) != 0;
+        const char* ex = getenv("VPCA_EXACT_COVER");
+        if (ex != nullptr) plan.exact_cover = atoi(ex) != 0;
     }
     if (plan.d_win_done == nullptr) {
         cudaError_t e = cudaMalloc(&plan.d_win_done, GramPlan::kMaxWindows * sizeof(int));
@@ -772,8 +1033,9 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     }
     const bool mxf4 = (elem_bits == 4 && plan.e2m1_mxf4);
     const int tile_bn = mxf4 ? kUmmaNScaled : kUmmaN;
-    if (plan.tiles_for_n != n || plan.tiles_for_cg != plan.cta_group || plan.tiles_for_bn != tile_bn) {
-        cudaError_t e = build_tiles(plan, n, tile_bn, stream);
+    const bool exact = !mxf4 && plan.exact_cover;   // kind::mxf4 keeps 256 x 240 rectangles (block scales in TMEM)
+    if (plan.tiles_for_n != n || plan.tiles_for_cg != plan.cta_group || plan.tiles_for_bn != (exact ? -1 : tile_bn)) {
+        cudaError_t e = build_tiles(plan, n, exact, tile_bn, stream);
         if (e != cudaSuccess) return e;
     }
     if (panel > 0) {
@@ -833,6 +1095,15 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
         return cudaErrorInvalidValue;
     }
+    // the same tensor with a 64-row box: the B operand of the N <= 128 tiles of the exact block cover (cta_group::2)
+    CUtensorMap tmap_half;
+    const cuuint32_t box_half[3] = {(cuuint32_t)elems_per_kb, (cuuint32_t)(kBoxRows / 2), 1};
+    r = encode(&tmap_half, tmtype, 3, const_cast<void*>(d_x), gdim, gstride, box_half, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled (64-row box) failed with CUresult " + std::to_string((int)r);
+        return cudaErrorInvalidValue;
+    }
 
     GramArgs args{};
     args.S = d_S;
@@ -840,16 +1111,17 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     for (int d = 0; d < kMaxPeers; ++d) args.peer[d] = d < plan.num_peers ? plan.peer_S[d] : nullptr;
     args.peer_mode = plan.peer_mode;
     for (int d = 0; d < kMaxPeers; ++d) args.own_end[d] = plan.own_end[d];
-    args.tiles = plan.d_tiles;
+    args.tiles = static_cast<const TileDesc*>(plan.d_tiles);
     cudaHostGetDevicePointer(reinterpret_cast<void**>(&args.err), plan.d_err, 0);
     args.n = n;
     args.num_tiles = plan.num_tiles;
+    args.num_full = plan.num_full;
+    args.total_weight = plan.total_weight;
     args.kb_total = (int)((nv + elems_per_kb - 1) / elems_per_kb);
     args.kb_per_panel = panel > 0 ? (int)(panel / elems_per_kb) : args.kb_total;
     args.num_workers = workers;
-    args.resident = plan.num_tiles <= workers ? 1 : 0;
     args.elems_per_kb = elems_per_kb;
-    if (args.resident) {
+    {
         int kbw = plan.kb_window;
         if (kbw <= 0 && panel > 0) kbw = args.kb_per_panel;   // one L2 window per panel
         if (kbw <= 0) {
@@ -857,18 +1129,18 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
             const long long target = 32ll << 20;
             kbw = (int)std::max<long long>(8, std::min<long long>(4096, target / ((long long)n * kKBytes)));
         }
-        args.kb_window = std::min(kbw, args.kb_total);
-    } else {
-        args.kb_window = args.kb_total;
+        kbw = std::min(kbw, args.kb_total);
+        // cheap upper bound first (a worker with less than a tile's worth of work can touch few tiles), then the exact test
+        args.resident = (plan.num_tiles <= 4 * workers && fits_resident(plan, workers, kbw)) ? 1 : 0;
+        args.kb_window = args.resident ? kbw : args.kb_total;
     }
     plan.last_resident = args.resident;
     const int nwin = (args.kb_total + args.kb_window - 1) / args.kb_window;
-    const long long uw = (long long)args.num_tiles * args.kb_window;
+    const long long uw = (long long)args.total_weight * args.kb_window;
     args.active_workers = (int)std::min<long long>(workers, uw);
     args.sync_lead = (args.resident && nwin <= GramPlan::kMaxWindows) ? plan.sync_lead : 0;
     args.win_done = plan.d_win_done;
-    const bool adapt = plan.adaptive && args.resident && workers <= 1024 && plan.num_tiles < workers &&
-                       args.active_workers == workers;
+    const bool adapt = plan.adaptive && args.resident && workers <= 1024 && args.active_workers == workers;
     args.prof = (plan.profile || adapt) ? plan.d_prof : nullptr;
     args.cum = plan.d_cum;
     args.tx_shift = (elem_bits == 4 && !mxf4 && getenv("VPCA_E2M1_TX_FULL") == nullptr) ? 1 : 0;
@@ -880,19 +1152,20 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     const int grid = workers * cgp;
     cudaError_t le;
     if (cgp == 2)
-        le = kind == 0 ? launch<2, 0>(tmap, args, grid, stream)
-                       : (kind == 1 ? launch<2, 1>(tmap, args, grid, stream)
-                                    : (kind == 2 ? launch<2, 2>(tmap, args, grid, stream) : launch<2, 3>(tmap, args, grid, stream)));
+        le = kind == 0 ? launch<2, 0>(tmap, tmap_half, args, grid, stream)
+                       : (kind == 1 ? launch<2, 1>(tmap, tmap_half, args, grid, stream)
+                                    : (kind == 2 ? launch<2, 2>(tmap, tmap_half, args, grid, stream) : launch<2, 3>(tmap, tmap_half, args, grid, stream)));
     else
-        le = kind == 0 ? launch<1, 0>(tmap, args, grid, stream)
-                       : (kind == 1 ? launch<1, 1>(tmap, args, grid, stream)
-                                    : (kind == 2 ? launch<1, 2>(tmap, args, grid, stream) : launch<1, 3>(tmap, args, grid, stream)));
+        le = kind == 0 ? launch<1, 0>(tmap, tmap_half, args, grid, stream)
+                       : (kind == 1 ? launch<1, 1>(tmap, tmap_half, args, grid, stream)
+                                    : (kind == 2 ? launch<1, 2>(tmap, tmap_half, args, grid, stream) : launch<1, 3>(tmap, tmap_half, args, grid, stream)));
     if (le != cudaSuccess) return le;
     if (adapt) {
-        // a worker may own at most one tile's worth of units per window (two resident accumulators)
-        const double max_share = std::min(1.35, 0.98 * (double)workers / (double)plan.num_tiles);
-        rebalance_kernel<<<1, 1024, 0, stream>>>(plan.d_prof, plan.d_cum, workers, cgp, max_share, 300000,
-                                                 reinterpret_cast<int*>(plan.d_cum + workers + 2));
+        // shares move towards the measured speeds, at most 35 % above the mean; a split under which some worker's
+        // accumulators would not fit TMEM is rejected by the kernel itself
+        rebalance_kernel<<<1, 1024, 0, stream>>>(plan.d_prof, plan.d_cum, workers, cgp, 1.35, 300000,
+                                                 reinterpret_cast<int*>(plan.d_cum + workers + 2), static_cast<const TileDesc*>(plan.d_tiles), plan.num_tiles,
+                                                 plan.total_weight, args.kb_window, plan.tiles_col_limit);
         le = cudaGetLastError();
     }
     return le;

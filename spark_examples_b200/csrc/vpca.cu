@@ -1269,6 +1269,17 @@ int vpca_debug_gram_profile(vpca_ctx* ctx, int64_t* out, int32_t max_ctas) {
     return gram_read_profile(ctx->plan, reinterpret_cast<long long*>(out), max_ctas);
 }
 
+int vpca_debug_tiles(int32_t n_samples, int32_t cta_group, int32_t exact, int32_t* out, int32_t max_tiles) {
+    if (n_samples < 2 || max_tiles < 0) return fail(nullptr, VPCA_ERR_BAD_ARG, "vpca_debug_tiles: bad argument");
+    return gram_debug_tiles(n_samples, cta_group, exact, out, max_tiles);
+}
+
+int vpca_debug_plan(const int32_t* tiles, int32_t num_tiles, int32_t workers, int32_t kb_window, int32_t* out, int32_t max_pieces) {
+    if (tiles == nullptr || num_tiles < 1 || workers < 1 || kb_window < 1 || (out == nullptr && max_pieces > 0))
+        return fail(nullptr, VPCA_ERR_BAD_ARG, "vpca_debug_plan: bad argument");
+    return gram_debug_plan(tiles, num_tiles, workers, kb_window, out, max_pieces);
+}
+
 /* Pinned host memory for callers that stage rows themselves (JNI direct ByteBuffers): the H2D copies of accumulate_*
  * then run at full PCIe rate and truly asynchronously.  Portable across devices. */
 int vpca_host_alloc(size_t bytes, void** out) {

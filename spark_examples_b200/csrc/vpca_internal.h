@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <string>
+#include <vector>
 
 #include "../../include/vpca.h"
 
@@ -13,8 +14,14 @@ struct GramPlan {
     int cta_group = 2;        // tcgen05 cta_group (1: 128x256 tiles per CTA, 2: 256x256 per CTA pair)
     int kb_window = 0;        // k-blocks per L2 window (0 -> automatic)
     int num_sms = 0;
-    int2* d_tiles = nullptr;  // device tile list (A row block, B row block)
+    void* d_tiles = nullptr;  // device tile list (TileDesc, gram_sm100.cu)
+    std::vector<int32_t> h_tiles;   // the same list on the host (8 ints per tile): resident / TMEM-fit decisions
     int num_tiles = 0;
+    int num_full = 0;         // leading full-weight tiles (whole-tile waves of the large-N schedule)
+    int total_weight = 0;     // sum over tiles of n_eff / 16
+    int tiles_col_limit = 512;   // TMEM columns the accumulators of one worker may take
+    bool exact_cover = true;  // VPCA_EXACT_COVER=0: square 256 x 256 tiles (pays 4 blocks per diagonal tile) instead of
+                              // the exact 128-block cover of the lower triangle
     int tiles_for_n = -1;     // n_samples the tile list was built for
     int tiles_for_cg = 0;
     int tiles_for_bn = 0;
@@ -63,6 +70,8 @@ cudaError_t gram_add_owners(GramPlan& plan, const int32_t* d_src, int n, cudaStr
 cudaError_t gram_gather_rows(GramPlan& plan, int32_t* d_S, int n, cudaStream_t stream);
 cudaError_t gram_peer_barrier(GramPlan& plan, cudaStream_t stream);
 void gram_plan_free(GramPlan& plan);
+int gram_debug_tiles(int n, int cta_group, int exact, int32_t* out, int max_tiles);
+int gram_debug_plan(const int32_t* tiles8, int num_tiles, int workers, int kbw, int32_t* out, int max_pieces);
 
 // ---- encode (encode.cu) ------------------------------------------------------------------------
 // CSR rows [0, nv) (d_off has nv+1 entries; entry e of row v is d_idx[d_off[v] - base + ...]) -> dense

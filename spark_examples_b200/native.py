@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = (
     "vpca_pool_create", "vpca_pool_destroy", "vpca_pool_size", "vpca_pool_ctx", "vpca_pool_last_error", "vpca_pool_reset",
     "vpca_pool_accumulate_calls", "vpca_pool_accumulate_calls_u16", "vpca_pool_accumulate_bits", "vpca_pool_accumulate_bed",
     "vpca_pool_commit", "vpca_pool_abort", "vpca_pool_reduce_and_finalize", "vpca_pool_get_gram", "vpca_pool_compute_pca",
-    "vpca_pool_get_stats",
+    "vpca_pool_get_stats", "vpca_debug_tiles", "vpca_debug_plan",
 )
 
 
@@ -200,6 +200,10 @@ def load_library() -> ctypes.CDLL:
     L.vpca_pool_compute_pca.argtypes = [vp, i32, vp, vp, ctypes.POINTER(i32)]
     L.vpca_pool_get_stats.restype = ctypes.c_int
     L.vpca_pool_get_stats.argtypes = [vp, ctypes.POINTER(VpcaStats)]
+    L.vpca_debug_tiles.restype = ctypes.c_int
+    L.vpca_debug_tiles.argtypes = [i32, i32, i32, vp, i32]
+    L.vpca_debug_plan.restype = ctypes.c_int
+    L.vpca_debug_plan.argtypes = [vp, i32, i32, i32, vp, i32]
     L.vpca_set_gram.restype = ctypes.c_int
     L.vpca_set_gram.argtypes = [vp, vp]
     L.vpca_compute_pca.restype = ctypes.c_int
@@ -494,6 +498,29 @@ class NativePca:
         st = VpcaStats()
         self._check(self._lib.vpca_get_stats(self._h, ctypes.byref(st)))
         return {name: getattr(st, name) for name, _ in VpcaStats._fields_}
+
+
+def debugTiles(n_samples: int, cta_group: int = 2, exact: bool = True) -> np.ndarray:
+    """(tiles, 8) int32: the Gram kernel's tile list for n_samples (host-only, no GPU needed; see vpca_debug_tiles)."""
+    L = load_library()
+    cnt = L.vpca_debug_tiles(int(n_samples), int(cta_group), 1 if exact else 0, None, 0)
+    if cnt < 0:
+        raise VpcaError(cnt, L.vpca_last_error(None).decode("utf-8", "replace"))
+    out = np.zeros((cnt, 8), dtype=np.int32)
+    L.vpca_debug_tiles(int(n_samples), int(cta_group), 1 if exact else 0, _host_ptr(out), cnt)
+    return out
+
+
+def debugPlan(tiles: np.ndarray, workers: int, kb_window: int) -> np.ndarray:
+    """(pieces, 6) int32 {worker, tile, kb_lo, kb_hi, tmem_col, tmem_cols_of_worker} of one window (vpca_debug_plan)."""
+    L = load_library()
+    t = np.ascontiguousarray(tiles, dtype=np.int32)
+    cap = 8 * int(workers) + 8
+    out = np.zeros((cap, 6), dtype=np.int32)
+    cnt = L.vpca_debug_plan(_host_ptr(t), len(t), int(workers), int(kb_window), _host_ptr(out), cap)
+    if cnt < 0:
+        raise VpcaError(VPCA_ERR_STATE, f"worker {-cnt - 1} would own more pieces than the kernel supports")
+    return out[:cnt]
 
 
 def ownerRowBands(n_samples: int, world: int) -> list:

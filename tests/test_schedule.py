@@ -1,0 +1,115 @@
+"""Host-side checks of the Gram kernel's work decomposition (no GPU needed): the tile list and the per-worker pieces
+are computed by the same code the kernel's three roles replay (plan_segments in csrc/gram_sm100.cu), exposed through
+vpca_debug_tiles / vpca_debug_plan.
+
+What must hold for S = sum_v x_v x_v^T (VariantsPca.scala:186-188) to come out exact:
+  * exact block cover: every 128 x 128 block (col block c <= row block r) of the lower triangle is produced by exactly
+    one (A block, B block) product -- directly, or as the mirror image (c > r, written transposed);
+  * the pieces of all workers partition every (tile, k-block) unit of a window: nothing twice, nothing missing;
+  * the accumulators of one worker fit the 512 TMEM columns whenever the schedule is declared resident.
+"""
+import numpy as np
+import pytest
+
+from spark_examples_b200 import native
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    import __graft_entry__ as entry
+    if not native.library_path().exists():
+        entry.build()
+    native.load_library()
+
+
+def _cover(tiles, n, cg):
+    nb = (n + 127) // 128
+    cover = np.zeros((nb, nb), int)            # [row block][col block]
+    mma_rows = 0
+    for a0, a1, rb, ne, ws, fl, _, _ in tiles:
+        assert a0 % 128 == 0 and a1 % 128 == 0 and rb % 128 == 0 and ne % 16 == 0 and 0 < ne <= 256
+        assert rb + ne <= ((n + 15) // 16) * 16
+        b_blocks = [rb // 128] + ([rb // 128 + 1] if ne > 128 else [])
+        a_blocks = [a0 // 128] + ([a1 // 128] if cg == 2 and not (fl & 2) else [])
+        mma_rows += cg * ne
+        for ca in a_blocks:
+            for r in b_blocks:
+                if r >= ca:
+                    cover[r, ca] += 1
+                else:
+                    assert fl & 1, "a block above the diagonal needs the transposed-write flag"
+                    cover[ca, r] += 1
+    return cover, mma_rows
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("n", [2, 70, 128, 129, 257, 385, 513, 600, 641, 769, 1092, 2504, 2560, 5000, 10000])
+def test_exact_block_cover(n, cg):
+    tiles = native.debugTiles(n, cg, True)
+    nb = (n + 127) // 128
+    cover, mma_rows = _cover(tiles, n, cg)
+    assert np.array_equal(cover, np.tril(np.ones((nb, nb), int)))
+    assert np.array_equal(tiles[:, 4], np.concatenate([[0], np.cumsum(tiles[:-1, 3] // 16)]))     # weight prefix
+    # no filler unless the number of blocks of a row is odd and there is no partner row to trade a block with
+    fillers = int(((tiles[:, 5] & 2) != 0).sum())
+    assert fillers <= (1 if cg == 2 else 0) * ((nb + 3) // 4 + 1)
+
+
+def test_exact_cover_saves_the_redundant_quarter_of_diagonal_tiles():
+    """2560 samples = 20 blocks: 210 needed blocks; the square 256 x 256 tiling issues 55 tiles x 4 = 220."""
+    tiles = native.debugTiles(2560, 2, True)
+    _, mma_rows = _cover(tiles, 2560, 2)
+    assert mma_rows == 210 * 128
+    assert len(tiles) == 60 and int((tiles[:, 3] == 256).sum()) == 45
+
+
+@pytest.mark.parametrize("cg,workers", [(2, 74), (1, 148)])
+@pytest.mark.parametrize("n,kbw", [(2504, 64), (2504, 32), (2504, 7), (1092, 64), (600, 16), (130, 64), (2000, 128)])
+def test_pieces_partition_every_window_and_fit_tmem(n, kbw, cg, workers):
+    tiles = native.debugTiles(n, cg, True)
+    pieces = native.debugPlan(tiles, workers, kbw)
+    seen = np.zeros((len(tiles), kbw), int)
+    for w, t, lo, hi, col, cols in pieces:
+        assert 0 <= lo < hi <= kbw
+        seen[t, lo:hi] += 1
+        assert col % 32 == 0 and col + tiles[t, 3] <= cols <= 512
+    assert (seen == 1).all()
+    # accumulators of one worker never overlap in TMEM
+    for w in np.unique(pieces[:, 0]):
+        mine = pieces[pieces[:, 0] == w]
+        spans = sorted((c, c + ((tiles[t, 3] + 31) // 32) * 32) for _, t, _, _, c, _ in mine)
+        assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+    # balance: a worker's share of the weighted work is within one k-block per piece of the mean
+    work = np.zeros(workers)
+    for w, t, lo, hi, _, _ in pieces:
+        work[w] += (hi - lo) * (tiles[t, 3] // 16)
+    mean = work.sum() / workers
+    assert work.max() - mean <= 16 * 3 + 1
+
+
+def test_large_cohorts_leave_the_resident_schedule():
+    """N = 5000: more accumulators per worker than TMEM holds -> the host must pick the wave schedule (debugPlan reports
+    the overflow instead of a plan)."""
+    tiles = native.debugTiles(5000, 2, True)
+    with pytest.raises(native.VpcaError):
+        native.debugPlan(tiles, 74, 64)
+    # whole-tile waves deal out only full-weight two-row tiles, in compact patches of S
+    full = tiles[tiles[:, 3] == 256]
+    lead = 0
+    while lead < len(tiles) and tiles[lead, 3] == 256:
+        lead += 1
+    assert lead == len(full)
+    wave = tiles[:74]
+    rows_of_x = set(wave[:, 0] // 128) | set(wave[:, 1] // 128) | set(wave[:, 2] // 128) | set(wave[:, 2] // 128 + 1)
+    assert len(rows_of_x) <= 40              # ~34 row blocks of X per wave instead of ~150 for a row-major tile order
+
+
+def test_mxf4_rectangles_cover_the_triangle():
+    """kind::mxf4 keeps 256 x 240 rectangles: every cell with row >= col lies in exactly one of them."""
+    n = 2504
+    tiles = native.debugTiles(n, 2, False)
+    hit = np.zeros((n, n), np.int8)
+    for a0, a1, rb, ne, ws, fl, _, _ in tiles:
+        assert fl == 0 and a1 == a0 + 128 and rb % 240 == 0
+        hit[rb:min(n, rb + ne), a0:min(n, a0 + 256)] += 1
+    assert (np.tril(hit) == np.tril(np.ones((n, n), np.int8))).all()
