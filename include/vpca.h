@@ -311,7 +311,13 @@ int vpca_debug_gram_profile(vpca_ctx* ctx, int64_t* out, int32_t max_ctas);
  *   rectangles kind::mxf4 uses.  Returns the tile count (may exceed max_tiles).
  * vpca_debug_plan: the (worker, tile, first k-block, end k-block, TMEM column, TMEM columns of the worker) pieces of one
  *   window of kb_window k-blocks under an equal split -- 6 int32 per piece; returns the piece count, or -(1 + worker) when
- *   a worker would own more pieces than the kernel supports. */
+ *   a worker would own more pieces than the kernel supports.
+ * vpca_debug_rebalance: what the on-device rebalancer does with a candidate speed-weighted split before it publishes it --
+ *   `cum` (workers + 1 fractions of a window, cum[0] = 0, cum[workers] = 1; in / out) is repaired so that the accumulators
+ *   of every worker fit `col_limit` TMEM columns (512; 480 for kind::mxf4), then the pieces are written like
+ *   vpca_debug_plan.  Returns the piece count, or VPCA_ERR_STATE when no repair exists (the device keeps the old split). */
+int vpca_debug_rebalance(const int32_t* tiles, int32_t num_tiles, int32_t workers, int32_t kb_window, int32_t col_limit,
+                         double* cum, int32_t* out, int32_t max_pieces);
 int vpca_debug_tiles(int32_t n_samples, int32_t cta_group, int32_t exact, int32_t* out, int32_t max_tiles);
 int vpca_debug_plan(const int32_t* tiles, int32_t num_tiles, int32_t workers, int32_t kb_window, int32_t* out, int32_t max_pieces);
 

@@ -75,7 +75,9 @@ struct TileDesc {
     int wstart;         // sum of the weights (n_eff / 16) of the tiles before this one
     int flags;          // kTileXpose: a 128-block above the diagonal is written transposed (it stands in for its mirror
                         // image) instead of being skipped; kTileFiller: CTA 1's A block only pads the pair, drop its output
-    int pad0, pad1;
+    int acc_cols;       // TMEM columns its accumulator takes: n_eff rounded up to 32 (exact cover), else the tiling's BN
+                        // (256, or 240 for kind::mxf4 whose two accumulators sit below the scale columns at 480)
+    int pad1;
 };
 constexpr int kTileXpose = 1, kTileFiller = 2;
 constexpr int kMaxSegs = 4;   // (tile, k-range) pieces one worker may own per window in resident mode
@@ -103,6 +105,8 @@ struct GramArgs {
     int* win_done;     // win_done[w] = number of workers whose producer has issued every load of window w
     long long* prof;   // optional per-CTA timestamps (globaltimer ns): start, first MMA, MMA done, end
     const double* cum; // cum[w] = fraction of every window's units owned by workers < w (cum[0] = 0, cum[W] = 1)
+    int col_limit;     // TMEM columns the accumulators of one worker may take (512; mxf4: 480)
+    int acc_stride;    // large-N schedule: TMEM columns between the two double-buffered accumulators (256; mxf4: 240)
     int tx_shift;      // TMA transaction bytes per stage = STAGE_BYTES >> tx_shift (1 for packed 4-bit sources: the
                        // mbarrier counts the 8 data bytes of every 16-byte shared-memory chunk, not the gap)
 };
@@ -152,9 +156,64 @@ __host__ __device__ inline void plan_segments(const TileDesc* tiles, int num_til
         p.lo[p.n] = lo;
         p.hi[p.n] = hi;
         p.col[p.n] = p.cols;
-        p.cols += (tiles[t].n_eff + 31) & ~31;
+        p.cols += tiles[t].acc_cols;
         ++p.n;
     }
+}
+
+// Largest e <= u_end such that the pieces of [u_begin, e) fit one worker's TMEM (at most kMaxSegs accumulators,
+// at most col_limit columns): u_end itself, or the start of the first tile whose accumulator no longer fits.
+// `hint`: a tile index at or before the tile that holds u_begin (advanced to it; callers walk u_begin upwards).
+__host__ __device__ inline long long feasible_end(const TileDesc* tiles, int num_tiles, long long u_begin, long long u_end,
+                                                  int len, int col_limit, int& hint) {
+    int n = 0, cols = 0;
+    long long u = u_begin;
+    int t = hint;
+    bool first = true;
+    while (u < u_end && t < num_tiles) {
+        const int w = tiles[t].n_eff >> 4;
+        const long long base = (long long)tiles[t].wstart * len;
+        const long long tend = base + (long long)w * len;
+        if (tend <= u) {
+            ++t;
+            continue;
+        }
+        if (first) {
+            hint = t;
+            first = false;
+        }
+        const long long e = u_end < tend ? u_end : tend;
+        const int lo = (int)((u - base) / w);
+        const int hi = e == tend ? len : (int)((e - base) / w);
+        if (lo < hi) {
+            if (n == kMaxSegs || cols + tiles[t].acc_cols > col_limit) return u;
+            ++n;
+            cols += tiles[t].acc_cols;
+        }
+        u = e;
+    }
+    return u_end;
+}
+
+// Makes a candidate split (cand[0] = 0 <= cand[1] <= ... <= cand[workers] = 1, fractions of the uw units of a window)
+// feasible: worker i ends where feasible_end says it must, and worker i + 1 starts there.  False if the last worker
+// cannot reach the end of the window (the caller keeps the old split).
+__host__ __device__ inline bool repair_split(const TileDesc* tiles, int num_tiles, int workers, long long uw, int len,
+                                             int col_limit, double* cand) {
+    long long ub = 0;
+    int hint = 0;
+    for (int i = 0; i < workers; ++i) {
+        long long ue = (i + 1 == workers) ? uw : (long long)((double)uw * cand[i + 1]);
+        if (ue < ub) ue = ub;
+        const long long fe = feasible_end(tiles, num_tiles, ub, ue, len, col_limit, hint);
+        if (fe < ue) {
+            if (i + 1 == workers) return false;
+            ue = fe;
+        }
+        if (i + 1 < workers) cand[i + 1] = ((double)ue + 0.5) / (double)uw;   // floor(uw * cand) == ue in the kernel
+        ub = ue;
+    }
+    return true;
 }
 
 // Every role of a worker (TMA producer, MMA issuer, epilogue) replays the same deterministic schedule.
@@ -166,7 +225,7 @@ __host__ __device__ inline void plan_segments(const TileDesc* tiles, int num_til
 struct Sched {
     SegPlan plan;
     long long u_begin, u_end, u;
-    int kbw, nwin, kb_total, resident, win, seg_i, nflush;
+    int kbw, nwin, kb_total, resident, win, seg_i, nflush, acc_stride;
     int worker, workers, num_tiles, wave, full_waves, tail_first;
     const TileDesc* tiles;
 
@@ -174,6 +233,7 @@ struct Sched {
         kbw = a.kb_window;
         kb_total = a.kb_total;
         resident = a.resident;
+        acc_stride = a.acc_stride;
         worker = w;
         workers = a.num_workers;
         num_tiles = a.num_tiles;
@@ -189,6 +249,16 @@ struct Sched {
             u_begin = (long long)((double)uw * a.cum[worker]);
             u_end = (worker + 1 == a.num_workers) ? uw : (long long)((double)uw * a.cum[worker + 1]);
             plan_segments(tiles, num_tiles, 0, u_begin, u_end, kbw, plan);
+            if (plan.overflow || plan.cols > a.col_limit) {   // overlapping accumulators would corrupt S silently
+                if (a.err != nullptr && threadIdx.x == 0) {
+                    a.err[0] = 9;
+                    a.err[1] = (int)blockIdx.x;
+                    a.err[2] = plan.cols;
+                    a.err[3] = plan.n;
+                    __threadfence_system();
+                }
+                __trap();
+            }
         } else {
             full_waves = a.num_full / workers;
             tail_first = full_waves * workers;
@@ -217,7 +287,7 @@ struct Sched {
             s.first = 1;
             s.flush = 1;
             s.slot = nflush & 1;
-            s.col = s.slot * kUmmaN;
+            s.col = s.slot * acc_stride;
             s.use = nflush >> 1;
             if (wave < full_waves) {                        // one whole tile of the current wave
                 fill(s, wave * workers + worker);
@@ -619,24 +689,15 @@ __global__ void rebalance_kernel(const long long* __restrict__ prof, double* __r
         }
     }
     __syncthreads();
-    // the new split is published only if every worker's accumulators still fit TMEM under it
-    if (active) {
-        const long long uw = (long long)total_weight * kbw;
-        const long long ub = (long long)((double)uw * cand[w]);
-        const long long ue = (w + 1 == workers) ? uw : (long long)((double)uw * cand[w + 1]);
-        SegPlan p;
-        plan_segments(tiles, num_tiles, 0, ub, ue, kbw, p);
-        if (p.overflow || p.cols > col_limit) atomicExch(&reject, 1);
-    }
+    // Repair, then publish: a worker whose pieces under the candidate split would not fit TMEM (more than kMaxSegs
+    // accumulators or more than col_limit columns: e.g. the tail of one tile, a whole 13-unit tile and the head of a
+    // third) stops at the edge of the tile that does not fit, and its neighbour starts there.  One thread walks the
+    // workers in order; the tile cursor only moves forward, so the walk is O(workers + tiles).
+    if (w == 0 && !repair_split(tiles, num_tiles, workers, (long long)total_weight * kbw, kbw, col_limit, cand)) reject = 1;
     __syncthreads();
     if (reject) return;
     if (w <= workers) cum[w] = cand[w];
     if (w == 0) *gen += 1;
-}
-
-__global__ void init_cum_kernel(double* __restrict__ cum, int workers) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= workers) cum[i] = (double)i / (double)workers;
 }
 
 __global__ void symmetrize_kernel(int32_t* __restrict__ S, int n) {
@@ -837,19 +898,26 @@ static void make_tiles(int n, int cg, bool exact, int bn, std::vector<TileDesc>&
     out.clear();
     auto n_eff = [&](int row0, int want) { return std::min(want, ((n - row0) + 15) & ~15); };
     if (!exact) {
+        // B strips of nearly equal width: ceil(n / 16) units of 16 rows dealt over ceil(n / bn) strips (2504 samples,
+        // bn = 240: 3 strips of 240 rows and 8 of 224 instead of 10 of 240 and one of 104).  Tiles of nearly equal
+        // weight keep every worker of the resident schedule inside two tiles (two accumulators) under an even split.
         const int BM = 128 * cg;
         const int nbn = (n + bn - 1) / bn, nbm = (n + BM - 1) / BM;
+        const int units = (n + 15) / 16;
+        std::vector<int> row0(nbn + 1, 0);
+        for (int b = 0; b < nbn; ++b) row0[b + 1] = row0[b] + 16 * (units / nbn + (b < units % nbn ? 1 : 0));
         constexpr int kStrip = 8;
         for (int bb = 0; bb < nbn; bb += kStrip)
             for (int am = 0; am < nbm; ++am)
                 for (int b = bb; b < std::min(nbn, bb + kStrip); ++b) {
-                    const int max_row = std::min(n, b * bn + bn) - 1;
+                    const int max_row = std::min(n, row0[b + 1]) - 1;
                     if (am * BM > max_row) continue;   // wholly above the diagonal
                     TileDesc t{};
                     t.rowA0 = am * BM;
                     t.rowA1 = am * BM + 128;
-                    t.rowB = b * bn;
-                    t.n_eff = n_eff(b * bn, bn);
+                    t.rowB = row0[b];
+                    t.n_eff = row0[b + 1] - row0[b];
+                    t.acc_cols = bn;
                     out.push_back(t);
                 }
     } else {
@@ -861,6 +929,7 @@ static void make_tiles(int n, int cg, bool exact, int bn, std::vector<TileDesc>&
             t.rowA1 = c1 * 128;
             t.rowB = r0 * 128;
             t.n_eff = n_eff(r0 * 128, rows * 128);
+            t.acc_cols = (t.n_eff + 31) & ~31;
             t.flags = kTileXpose | (filler ? kTileFiller : 0);
             dst.push_back(t);
         };
@@ -937,19 +1006,24 @@ static cudaError_t build_tiles(GramPlan& plan, int n, bool exact, int BN, cudaSt
     plan.tiles_for_n = n;
     plan.tiles_for_cg = plan.cta_group;
     plan.tiles_for_bn = exact ? -1 : BN;
-    plan.tiles_col_limit = exact ? (int)kTmemCols : (int)kSfCol;
+    plan.tiles_col_limit = (!exact && BN == kUmmaNScaled) ? (int)kSfCol : (int)kTmemCols;   // mxf4: scale columns at 480
     return e;
 }
 
-// Resident schedule (accumulators stay in TMEM for the whole launch) iff, under an equal split of windows of `kbw`
-// k-blocks, the pieces of every worker fit the TMEM columns (those left beside the block scales for kind::mxf4).
-static bool fits_resident(const GramPlan& plan, int workers, int kbw) {
+// Resident schedule (accumulators stay in TMEM for the whole launch) iff the equal split of a window of `kbw` k-blocks,
+// after the same repair the rebalancer applies (a worker stops at the edge of a tile whose accumulator would not fit any
+// more), lets every worker keep its pieces in the TMEM columns available (those beside the block scales for
+// kind::mxf4).  `cum` receives that initial split (workers + 1 fractions).
+static bool initial_split(const GramPlan& plan, int workers, int kbw, std::vector<double>& cum) {
     if (plan.total_weight <= 0) return false;
     const TileDesc* tiles = reinterpret_cast<const TileDesc*>(plan.h_tiles.data());
     const long long uw = (long long)plan.total_weight * kbw;
-    for (int w = 0; w < workers; ++w) {
-        const long long ub = (long long)((double)uw * ((double)w / (double)workers));
-        const long long ue = (w + 1 == workers) ? uw : (long long)((double)uw * ((double)(w + 1) / (double)workers));
+    cum.resize((size_t)workers + 1);
+    for (int w = 0; w <= workers; ++w) cum[w] = (double)w / (double)workers;
+    if (!repair_split(tiles, plan.num_tiles, workers, uw, kbw, plan.tiles_col_limit, cum.data())) return false;
+    for (int w = 0; w < workers; ++w) {   // belt and braces: what the kernel will plan from these fractions must fit
+        const long long ub = (long long)((double)uw * cum[w]);
+        const long long ue = (w + 1 == workers) ? uw : (long long)((double)uw * cum[w + 1]);
         SegPlan p;
         plan_segments(tiles, plan.num_tiles, 0, ub, ue, kbw, p);
         if (p.overflow || p.cols > plan.tiles_col_limit) return false;
@@ -969,17 +1043,31 @@ int gram_debug_tiles(int n, int cta_group, int exact, int32_t* out, int max_tile
 }
 
 int gram_debug_plan(const int32_t* tiles8, int num_tiles, int workers, int kbw, int32_t* out, int max_pieces) {
+    // the split a first launch uses: equal shares, repaired like initial_split does
+    const TileDesc* tiles = reinterpret_cast<const TileDesc*>(tiles8);
+    if (num_tiles <= 0) return 0;
+    const int col_limit = tiles[0].acc_cols == kUmmaNScaled ? (int)kSfCol : (int)kTmemCols;
+    std::vector<double> cum((size_t)workers + 1);
+    for (int w = 0; w <= workers; ++w) cum[w] = (double)w / (double)workers;
+    return gram_debug_repair(tiles8, num_tiles, workers, kbw, col_limit, cum.data(), out, max_pieces);
+}
+
+// Host-only: the rebalancer's repair step on a caller-supplied split (cum: workers + 1 fractions, in / out) followed by
+// the plan it yields, in the same format as gram_debug_plan.  -1000: no feasible repair.
+int gram_debug_repair(const int32_t* tiles8, int num_tiles, int workers, int kbw, int col_limit, double* cum, int32_t* out,
+                      int max_pieces) {
     const TileDesc* tiles = reinterpret_cast<const TileDesc*>(tiles8);
     if (num_tiles <= 0) return 0;
     const long long total = tiles[num_tiles - 1].wstart + (tiles[num_tiles - 1].n_eff >> 4);
     const long long uw = total * kbw;
+    if (!repair_split(tiles, num_tiles, workers, uw, kbw, col_limit, cum)) return -1000;
     int cnt = 0;
     for (int w = 0; w < workers; ++w) {
-        const long long ub = (long long)((double)uw * ((double)w / (double)workers));
-        const long long ue = (w + 1 == workers) ? uw : (long long)((double)uw * ((double)(w + 1) / (double)workers));
+        const long long ub = (long long)((double)uw * cum[w]);
+        const long long ue = (w + 1 == workers) ? uw : (long long)((double)uw * cum[w + 1]);
         SegPlan p;
         plan_segments(tiles, num_tiles, 0, ub, ue, kbw, p);
-        if (p.overflow) return -1 - w;
+        if (p.overflow || p.cols > col_limit) return -1 - w;
         for (int i = 0; i < p.n; ++i, ++cnt)
             if (cnt < max_pieces) {
                 int32_t* o = out + (size_t)cnt * 6;
@@ -1054,16 +1142,6 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
 
     const int cgp = plan.cta_group;
     const int workers = (cgp == 2) ? plan.num_sms / 2 : plan.num_sms;
-    if (plan.d_cum == nullptr || plan.cum_workers != workers || plan.cum_tiles != plan.num_tiles) {
-        if (plan.d_cum) cudaFree(plan.d_cum);
-        cudaError_t e = cudaMalloc(&plan.d_cum, (size_t)(workers + 2) * sizeof(double) + sizeof(int));
-        if (e != cudaSuccess) return e;
-        init_cum_kernel<<<(workers + 256) / 256, 256, 0, stream>>>(plan.d_cum, workers);
-        e = cudaMemsetAsync(plan.d_cum + workers + 2, 0, sizeof(int), stream);
-        if (e != cudaSuccess) return e;
-        plan.cum_workers = workers;
-        plan.cum_tiles = plan.num_tiles;
-    }
     // one k-block = one 128-byte swizzle atom of shared memory: 128 int8, 64 bf16 or 128 e2m1 cells (TMA expands
     // 4-bit cells to one byte each, CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B)
     const int elems_per_kb = (elem_bits == 16) ? 64 : (mxf4 ? 256 : 128);
@@ -1121,6 +1199,8 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     args.kb_per_panel = panel > 0 ? (int)(panel / elems_per_kb) : args.kb_total;
     args.num_workers = workers;
     args.elems_per_kb = elems_per_kb;
+    args.acc_stride = mxf4 ? kUmmaNScaled : kUmmaN;
+    args.col_limit = plan.tiles_col_limit;
     {
         int kbw = plan.kb_window;
         if (kbw <= 0 && panel > 0) kbw = args.kb_per_panel;   // one L2 window per panel
@@ -1131,8 +1211,27 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         }
         kbw = std::min(kbw, args.kb_total);
         // cheap upper bound first (a worker with less than a tile's worth of work can touch few tiles), then the exact test
-        args.resident = (plan.num_tiles <= 4 * workers && fits_resident(plan, workers, kbw)) ? 1 : 0;
+        std::vector<double> cum0;
+        args.resident = (plan.num_tiles <= 4 * workers && initial_split(plan, workers, kbw, cum0)) ? 1 : 0;
         args.kb_window = args.resident ? kbw : args.kb_total;
+        // the device-side split (speed-weighted by rebalance_kernel from launch to launch) starts from the repaired
+        // equal split; it is only meaningful for one (workers, tile list, window length)
+        if (args.resident && (plan.d_cum == nullptr || plan.cum_workers != workers || plan.cum_tiles != plan.num_tiles ||
+                              plan.cum_kbw != kbw || plan.cum_for_n != n)) {
+            if (plan.d_cum) cudaFree(plan.d_cum);
+            plan.d_cum = nullptr;
+            cudaError_t e = cudaMalloc(&plan.d_cum, (size_t)(workers + 2) * sizeof(double) + sizeof(int));
+            if (e != cudaSuccess) return e;
+            cum0.push_back(0.0);                                   // [workers + 1]: unused
+            cum0.push_back(0.0);                                   // [workers + 2]: the update counter (int)
+            e = cudaMemcpyAsync(plan.d_cum, cum0.data(), (size_t)(workers + 2) * sizeof(double) + sizeof(int),
+                                cudaMemcpyHostToDevice, stream);   // pageable source: staged before the call returns
+            if (e != cudaSuccess) return e;
+            plan.cum_workers = workers;
+            plan.cum_tiles = plan.num_tiles;
+            plan.cum_kbw = kbw;
+            plan.cum_for_n = n;
+        }
     }
     plan.last_resident = args.resident;
     const int nwin = (args.kb_total + args.kb_window - 1) / args.kb_window;

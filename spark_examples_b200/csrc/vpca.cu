@@ -1277,7 +1277,19 @@ int vpca_debug_tiles(int32_t n_samples, int32_t cta_group, int32_t exact, int32_
 int vpca_debug_plan(const int32_t* tiles, int32_t num_tiles, int32_t workers, int32_t kb_window, int32_t* out, int32_t max_pieces) {
     if (tiles == nullptr || num_tiles < 1 || workers < 1 || kb_window < 1 || (out == nullptr && max_pieces > 0))
         return fail(nullptr, VPCA_ERR_BAD_ARG, "vpca_debug_plan: bad argument");
-    return gram_debug_plan(tiles, num_tiles, workers, kb_window, out, max_pieces);
+    const int rc = gram_debug_plan(tiles, num_tiles, workers, kb_window, out, max_pieces);
+    if (rc < 0) return fail(nullptr, VPCA_ERR_STATE, "vpca_debug_plan: the accumulators of a worker do not fit TMEM (large-N schedule)");
+    return rc;
+}
+
+int vpca_debug_rebalance(const int32_t* tiles, int32_t num_tiles, int32_t workers, int32_t kb_window, int32_t col_limit,
+                         double* cum, int32_t* out, int32_t max_pieces) {
+    if (tiles == nullptr || num_tiles < 1 || workers < 1 || kb_window < 1 || cum == nullptr || col_limit < 32 ||
+        (out == nullptr && max_pieces > 0))
+        return fail(nullptr, VPCA_ERR_BAD_ARG, "vpca_debug_rebalance: bad argument");
+    const int rc = gram_debug_repair(tiles, num_tiles, workers, kb_window, col_limit, cum, out, max_pieces);
+    if (rc < 0) return fail(nullptr, VPCA_ERR_STATE, "vpca_debug_rebalance: no feasible repair of this split");
+    return rc;
 }
 
 /* Pinned host memory for callers that stage rows themselves (JNI direct ByteBuffers): the H2D copies of accumulate_*

@@ -35,7 +35,7 @@ struct GramPlan {
     int* d_win_done = nullptr;
     bool adaptive = true;     // VPCA_ADAPTIVE=0 keeps the stream-K split equal instead of speed-weighted
     double* d_cum = nullptr;  // cumulative worker shares (workers + 1 doubles) + update counter
-    int cum_workers = 0, cum_tiles = 0;
+    int cum_workers = 0, cum_tiles = 0, cum_kbw = 0, cum_for_n = 0;   // what the split in d_cum was made for
     // fused multi-GPU reduction: Gram buffers / barrier flags of all ranks, peer-mapped through CUDA IPC
     int num_peers = 0, peer_rank = 0, peer_epoch = 0;
     int32_t* peer_S[16] = {};     // Gram of rank d as seen from this device: the address of row 0 (for a rank that stores
@@ -72,6 +72,8 @@ cudaError_t gram_peer_barrier(GramPlan& plan, cudaStream_t stream);
 void gram_plan_free(GramPlan& plan);
 int gram_debug_tiles(int n, int cta_group, int exact, int32_t* out, int max_tiles);
 int gram_debug_plan(const int32_t* tiles8, int num_tiles, int workers, int kbw, int32_t* out, int max_pieces);
+int gram_debug_repair(const int32_t* tiles8, int num_tiles, int workers, int kbw, int col_limit, double* cum, int32_t* out,
+                      int max_pieces);
 
 // ---- encode (encode.cu) ------------------------------------------------------------------------
 // CSR rows [0, nv) (d_off has nv+1 entries; entry e of row v is d_idx[d_off[v] - base + ...]) -> dense

@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = (
     "vpca_synth_panels_device", "vpca_accumulate_calls_u16", "vpca_get_partial_gram", "vpca_load_partial_gram",
     "vpca_accumulate_bits", "vpca_gram_set_peer_mode", "vpca_gram_gather", "vpca_accumulate_bed",
     "vpca_synchronize", "vpca_host_alloc", "vpca_host_free", "vpca_gram_set_peers_local", "vpca_owner_row_bands",
-    "vpca_get_gram_band", "vpca_variant_count",
+    "vpca_get_gram_band", "vpca_variant_count", "vpca_debug_rebalance",
     "vpca_pool_create", "vpca_pool_destroy", "vpca_pool_size", "vpca_pool_ctx", "vpca_pool_last_error", "vpca_pool_reset",
     "vpca_pool_accumulate_calls", "vpca_pool_accumulate_calls_u16", "vpca_pool_accumulate_bits", "vpca_pool_accumulate_bed",
     "vpca_pool_commit", "vpca_pool_abort", "vpca_pool_reduce_and_finalize", "vpca_pool_get_gram", "vpca_pool_compute_pca",
@@ -204,6 +204,8 @@ def load_library() -> ctypes.CDLL:
     L.vpca_debug_tiles.argtypes = [i32, i32, i32, vp, i32]
     L.vpca_debug_plan.restype = ctypes.c_int
     L.vpca_debug_plan.argtypes = [vp, i32, i32, i32, vp, i32]
+    L.vpca_debug_rebalance.restype = ctypes.c_int
+    L.vpca_debug_rebalance.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32]
     L.vpca_set_gram.restype = ctypes.c_int
     L.vpca_set_gram.argtypes = [vp, vp]
     L.vpca_compute_pca.restype = ctypes.c_int
@@ -519,8 +521,23 @@ def debugPlan(tiles: np.ndarray, workers: int, kb_window: int) -> np.ndarray:
     out = np.zeros((cap, 6), dtype=np.int32)
     cnt = L.vpca_debug_plan(_host_ptr(t), len(t), int(workers), int(kb_window), _host_ptr(out), cap)
     if cnt < 0:
-        raise VpcaError(VPCA_ERR_STATE, f"worker {-cnt - 1} would own more pieces than the kernel supports")
+        raise VpcaError(VPCA_ERR_STATE, L.vpca_last_error(None).decode("utf-8", "replace"))
     return out[:cnt]
+
+
+def debugRebalance(tiles: np.ndarray, workers: int, kb_window: int, cum: np.ndarray, col_limit: int = 512):
+    """The rebalancer's repair of a candidate split (vpca_debug_rebalance): returns (repaired cum, pieces like debugPlan)."""
+    L = load_library()
+    t = np.ascontiguousarray(tiles, dtype=np.int32)
+    c = np.ascontiguousarray(cum, dtype=np.float64).copy()
+    assert c.shape == (workers + 1,)
+    cap = 8 * int(workers) + 8
+    out = np.zeros((cap, 6), dtype=np.int32)
+    cnt = L.vpca_debug_rebalance(_host_ptr(t), len(t), int(workers), int(kb_window), int(col_limit), _host_ptr(c),
+                                 _host_ptr(out), cap)
+    if cnt < 0:
+        raise VpcaError(cnt, L.vpca_last_error(None).decode("utf-8", "replace"))
+    return c, out[:cnt]
 
 
 def ownerRowBands(n_samples: int, world: int) -> list:

@@ -105,11 +105,51 @@ def test_large_cohorts_leave_the_resident_schedule():
 
 
 def test_mxf4_rectangles_cover_the_triangle():
-    """kind::mxf4 keeps 256 x 240 rectangles: every cell with row >= col lies in exactly one of them."""
+    """kind::mxf4 keeps 256 x (<= 240) rectangles: every cell with row >= col lies in exactly one of them, and the B strips
+    have nearly equal widths (so that tiles have nearly equal weights and an even split never spans three of them)."""
     n = 2504
     tiles = native.debugTiles(n, 2, False)
     hit = np.zeros((n, n), np.int8)
     for a0, a1, rb, ne, ws, fl, _, _ in tiles:
-        assert fl == 0 and a1 == a0 + 128 and rb % 240 == 0
+        assert fl == 0 and a1 == a0 + 128 and rb % 16 == 0 and ne % 16 == 0 and ne <= 240
         hit[rb:min(n, rb + ne), a0:min(n, a0 + 256)] += 1
     assert (np.tril(hit) == np.tril(np.ones((n, n), np.int8))).all()
+    assert set(tiles[:, 3]) == {224, 240}
+
+
+@pytest.mark.parametrize("n,exact,col_limit", [(2504, True, 512), (2504, False, 480), (1092, True, 512), (2000, True, 512)])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_rebalanced_splits_are_repaired_to_fit_tmem(n, exact, col_limit, seed):
+    """The speed-weighted split the device publishes (rebalance_kernel -> repair_split) must keep every worker inside its
+    TMEM budget whatever speeds were measured: skew the shares by up to +-35 % (the clamp of the rebalancer) and check that
+    the repaired split still partitions every (tile, k-block) unit and fits `col_limit` columns."""
+    workers, kbw = 74, 104
+    tiles = native.debugTiles(n, 2, exact)
+    rng = np.random.default_rng(seed)
+    share = rng.uniform(0.65, 1.35, workers)
+    cum = np.concatenate([[0.0], np.cumsum(share / share.sum())])
+    cum[-1] = 1.0
+    try:
+        native.debugPlan(tiles, workers, kbw)
+    except native.VpcaError:
+        pytest.skip("equal split is not resident for this shape")
+    cum2, pieces = native.debugRebalance(tiles, workers, kbw, cum, col_limit)
+    assert cum2[0] == 0.0 and cum2[-1] == 1.0 and (np.diff(cum2) >= 0).all()
+    seen = np.zeros((len(tiles), kbw), int)
+    for w, t, lo, hi, col, cols in pieces:
+        seen[t, lo:hi] += 1
+        assert col + tiles[t, 6] <= cols <= col_limit
+    assert (seen == 1).all()
+    assert np.bincount(pieces[:, 0], minlength=workers).max() <= 4
+    # the repair only trims: no worker gets more than the candidate gave it plus what its predecessors gave up
+    want = np.diff(cum)
+    got = np.diff(cum2)
+    assert got.max() <= want.max() + (want - got).clip(0).sum() + 1e-9
+
+
+def test_mxf4_accumulators_sit_below_the_scale_columns():
+    """kind::mxf4: 240-column accumulators at TMEM columns 0 and 240, block scales at 480 (gram_sm100.cu kSfCol)."""
+    tiles = native.debugTiles(2504, 2, False)
+    assert (tiles[:, 6] == 240).all()
+    pieces = native.debugPlan(tiles, 74, 104)
+    assert pieces[:, 5].max() <= 480 and set(pieces[:, 4]) <= {0, 240}
