@@ -830,6 +830,240 @@ __global__ void lz_verify_kernel(const double* __restrict__ theta, int k, const 
     st[1] = (theta2[0] > theta[k - 1] + 1e-9 * tnorm) ? 3 : 1;
 }
 
+
+// ------------------------------------------------------------------ Lanczos, persistent form (n <= kLzPersistMaxN)
+// The five launches of a step (and the 80 of a 16-step chunk) become ONE cooperative launch per chunk: 1024 threads on
+// every SM, block b owns the rows [b R, (b + 1) R) of everything (R = ceil(n / blocks)), and a step is three phases
+// separated by grid-wide barriers (an atomic counter in L2, ~1-2 us each instead of a kernel boundary):
+//   A  every block stages the whole w_in in shared memory (computing ||w_in||, sum(w_in) and rowmean . w_in on the way,
+//      all in one fixed order, so every block derives the same beta_j), then its rows of  y = C v_j  -- read from the
+//      int32 Gram S, not from the FP64 centred matrix: (C v)_i = (S v)_i - rbar_i sum(v) - rbar . v + mean sum(v) with
+//      rbar = rowSums / N (VariantsPca.scala:216-221 applied to a vector instead of to every entry).  That is half the
+//      bytes per step (25 MB instead of 50 MB at N = 2504: resident in both L2 partitions) and no rounding of the N^2
+//      centred entries.  v_j goes to row-major VT[i][j]; the block's share of h = V^T y to hpart[b][.];
+//   B  h = sum_b hpart[b] (fixed order), y -= V h on the own rows, the share of the second Gram-Schmidt pass to hpart2;
+//   C  the same with hpart2, alpha_j = h_j + h2_j, w_out rows = y.
+// VT is row-major (n x cap) so that one block's slice is contiguous in the Lanczos index q: the dot products and the
+// updates of a block read only its own R rows, coalesced.  Summation orders are fixed: run-to-run deterministic.
+constexpr int kLzPersistMaxN = 16384;   // w_in staged in shared memory: 8 n bytes
+constexpr int kLzThreads = 1024;
+constexpr int kLzSeg = 512;             // columns per warp task of the matvec
+
+struct LzArgs {
+    const int32_t* S;
+    const double* rowsum;
+    const double* scal;     // scal[0] = matrixMean
+    double* VT;             // n x cap, row-major
+    double* wbuf;           // 2 n
+    double* alpha;
+    double* beta;
+    double* hpart;          // 2 x blocks x cap
+    double* part;           // part[0] = ||w||^2 after the last step (one partial for lz_check_kernel)
+    int* st;                // st[0] = next step, st[1] = flag (0 run, 2 breakdown), st[3] = step cap
+    unsigned* bar;          // grid barrier counter, zero at launch
+    int n, cap, nsteps, pre;
+};
+
+__device__ __forceinline__ void lz_grid_barrier(unsigned* ctr, unsigned& target, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblocks;
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        unsigned v;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if (v < target && clock64() - t0 > 20000000000LL) __trap();   // a block that never arrives must not hang the box
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+// One Gram-Schmidt pass on the rows of this block: hs = sum over blocks of hin (columns [0, jc)), y -= VT hs, and
+// (hout != nullptr) this block's share of VT^T y.  Returns hs[jc - 1] (alpha contribution) in every thread.
+__device__ __forceinline__ double lz_orth_pass(const LzArgs& a, int nblocks, int i0, int R, int jc, const double* hin,
+                                               double* hout, double* hs, double* y) {
+    for (int q = threadIdx.x; q < jc; q += kLzThreads) {
+        double acc = 0.0;
+        for (int b = 0; b < nblocks; ++b) acc += __ldcg(hin + (size_t)b * a.cap + q);
+        hs[q] = acc;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int r = wid; r < R; r += kLzThreads / 32) {
+        const double* __restrict__ vt = a.VT + (size_t)(i0 + r) * a.cap;
+        double acc = 0.0;
+        for (int q = lane; q < jc; q += 32) acc += vt[q] * hs[q];
+        acc = warp_sum(acc);
+        if (lane == 0) y[r] -= acc;
+    }
+    __syncthreads();
+    if (hout != nullptr) {
+        for (int q = threadIdx.x; q < jc; q += kLzThreads) {
+            double acc = 0.0;
+            for (int r = 0; r < R; ++r) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
+            hout[(size_t)blockIdx.x * a.cap + q] = acc;
+        }
+    }
+    return hs[jc - 1];
+}
+
+__global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs a) {
+    extern __shared__ __align__(16) double lzsm[];
+    __shared__ double red[33];
+    const int n = a.n, nblocks = (int)gridDim.x;
+    const int rows_per = (n + nblocks - 1) / nblocks;
+    const int i0 = min(n, (int)blockIdx.x * rows_per);
+    const int R = min(rows_per, n - i0);
+    const int nseg = (n + kLzSeg - 1) / kLzSeg;
+    double* wsm = lzsm;                                  // n: w_in
+    double* hs = wsm + (((size_t)n + 1) & ~(size_t)1);   // cap
+    double* y = hs + a.cap;                              // rows_per
+    double* segp = y + rows_per;                         // rows_per x nseg
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double rc = (double)n;
+    const double mm = a.scal[0];
+    unsigned target = 0;
+    if (a.st[1] != 0) return;   // every block reads the same flag (nothing in this launch changes it before this point)
+    int j = a.st[0];
+    const int jend = min(j + a.nsteps, a.st[3]);
+    double* hp1 = a.hpart;
+    double* hp2 = a.hpart + (size_t)nblocks * a.cap;
+
+    if (a.pre && j > 0 && j < jend) {
+        // deflated restart: the start vector is made orthogonal to the j locked columns (two passes) before step j
+        double* w_in = a.wbuf + (size_t)(j & 1) * n;
+        for (int r = threadIdx.x; r < R; r += kLzThreads) y[r] = w_in[i0 + r];
+        __syncthreads();
+        for (int pass = 0; pass < 2; ++pass) {
+            double* hp = pass == 0 ? hp1 : hp2;
+            for (int q = threadIdx.x; q < j; q += kLzThreads) {
+                double acc = 0.0;
+                for (int r = 0; r < R; ++r) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
+                hp[(size_t)blockIdx.x * a.cap + q] = acc;
+            }
+            lz_grid_barrier(a.bar, target, nblocks);
+            lz_orth_pass(a, nblocks, i0, R, j, hp, nullptr, hs, y);
+        }
+        for (int r = threadIdx.x; r < R; r += kLzThreads) w_in[i0 + r] = y[r];
+        lz_grid_barrier(a.bar, target, nblocks);
+    }
+
+    bool broke = false;
+    for (; j < jend; ++j) {
+        const double* w_in = a.wbuf + (size_t)(j & 1) * n;
+        double* w_out = a.wbuf + (size_t)((j + 1) & 1) * n;
+        // ---- phase A: stage w_in, beta_j, y = C v_j on the own rows, share of V^T y
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int c = threadIdx.x; c < n; c += kLzThreads) {
+            const double wv = __ldcg(w_in + c);
+            wsm[c] = wv;
+            s0 += wv * wv;
+            s1 += wv;
+            s2 += __ddiv_rn(a.rowsum[c], rc) * wv;
+        }
+        s0 = block_sum(s0, red);
+        s1 = block_sum(s1, red);
+        s2 = block_sum(s2, red);   // (block_sum syncs: wsm is complete)
+        const double nrm = sqrt(s0);
+        if (!(nrm > 0.0) || !(nrm <= DBL_MAX)) {   // exact breakdown or non-finite: every block sees the same value
+            broke = true;
+            break;
+        }
+        const double inv = 1.0 / nrm;
+        const bool vec4 = (n & 3) == 0;
+        for (int task = wid; task < R * nseg; task += kLzThreads / 32) {
+            const int r = task / nseg, sg = task - r * nseg;
+            const int32_t* __restrict__ srow = a.S + (size_t)(i0 + r) * n;
+            const int c0 = sg * kLzSeg, c1 = min(n, c0 + kLzSeg);
+            double acc = 0.0;
+            if (vec4) {
+                double p[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int u = 0; u < kLzSeg / 128; ++u) {
+                    const int c = c0 + (u * 32 + lane) * 4;
+                    if (c < c1) {
+                        const int4 sv = __ldg(reinterpret_cast<const int4*>(srow + c));
+                        const double2 wa = *reinterpret_cast<const double2*>(wsm + c);
+                        const double2 wb = *reinterpret_cast<const double2*>(wsm + c + 2);
+                        p[u] = (double)sv.x * wa.x + (double)sv.y * wa.y + ((double)sv.z * wb.x + (double)sv.w * wb.y);
+                    }
+                }
+                acc = (p[0] + p[1]) + (p[2] + p[3]);
+            } else {
+                for (int c = c0 + lane; c < c1; c += 32) acc += (double)__ldg(srow + c) * wsm[c];
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) segp[r * nseg + sg] = acc;
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < R; r += kLzThreads) {
+            double acc = 0.0;
+            for (int sg = 0; sg < nseg; ++sg) acc += segp[r * nseg + sg];
+            const double rbar = __ddiv_rn(a.rowsum[i0 + r], rc);
+            y[r] = (acc - rbar * s1 - s2 + mm * s1) * inv;
+            a.VT[(size_t)(i0 + r) * a.cap + j] = wsm[i0 + r] * inv;
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q <= j; q += kLzThreads) {
+            double acc = 0.0;
+            for (int r = 0; r < R; ++r) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
+            hp1[(size_t)blockIdx.x * a.cap + q] = acc;
+        }
+        lz_grid_barrier(a.bar, target, nblocks);
+        // ---- phase B / C: classical Gram-Schmidt, applied twice
+        const double a1 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp1, hp2, hs, y);
+        lz_grid_barrier(a.bar, target, nblocks);
+        const double a2 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp2, nullptr, hs, y);
+        for (int r = threadIdx.x; r < R; r += kLzThreads) w_out[i0 + r] = y[r];
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.alpha[j] = a1 + a2;
+            a.beta[j] = nrm;
+        }
+        lz_grid_barrier(a.bar, target, nblocks);
+    }
+    if (blockIdx.x == 0) {
+        // ||w||^2 of the vector the next step would normalise: what lz_check_kernel turns into the residual bound
+        const double* w_last = a.wbuf + (size_t)(j & 1) * n;
+        double s0 = 0.0;
+        if (!broke)
+            for (int c = threadIdx.x; c < n; c += kLzThreads) {
+                const double wv = __ldcg(w_last + c);
+                s0 += wv * wv;
+            }
+        s0 = block_sum(s0, red);
+        if (threadIdx.x == 0) {
+            a.part[0] = s0;
+            a.st[0] = j;
+            if (broke) a.st[1] = 2;
+        }
+    }
+}
+
+// Z[:, c] = VT Y[:, c] for the row-major basis: one warp per (row, c).
+__global__ void __launch_bounds__(256) lz_ritz_rm_kernel(const double* __restrict__ VT, int n, int cap,
+                                                         const double* __restrict__ Y, int m, int k, double* __restrict__ Z) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const double* __restrict__ vt = VT + (size_t)row * cap;
+    for (int c = 0; c < k; ++c) {
+        const double* __restrict__ yc = Y + (size_t)c * m;
+        double acc = 0.0;
+        for (int q = lane; q < m; q += 32) acc += vt[q] * yc[q];
+        acc = warp_sum(acc);
+        if (lane == 0) Z[(size_t)c * n + row] = acc;
+    }
+}
+
+// VT[:, 0..k) = Z (the converged Ritz vectors become the locked leading columns of the deflated run)
+__global__ void lz_lock_kernel(double* __restrict__ VT, int n, int cap, const double* __restrict__ Z, int k) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < k; ++c) VT[(size_t)i * cap + c] = Z[(size_t)c * n + i];
+}
+
 }  // namespace
 
 cudaError_t eig_alloc(EigWork& w, int n, int kmax) {
@@ -859,7 +1093,7 @@ void eig_free(EigWork& w) {
     cudaFree(w.d_C); cudaFree(w.d_rowsum); cudaFree(w.d_v); cudaFree(w.d_w); cudaFree(w.d_p);
     cudaFree(w.d_diag); cudaFree(w.d_off); cudaFree(w.d_tau); cudaFree(w.d_scal); cudaFree(w.d_evals);
     cudaFree(w.d_evecs); cudaFree(w.d_lu); cudaFree(w.d_nz); cudaFree(w.d_step);
-    cudaFree(w.d_V); cudaFree(w.d_lzw); cudaFree(w.d_lzs); cudaFree(w.d_lzst);
+    cudaFree(w.d_V); cudaFree(w.d_lzw); cudaFree(w.d_lzs); cudaFree(w.d_lzst); cudaFree(w.d_lzbar);
     if (w.graph_exec != nullptr) cudaGraphExecDestroy(w.graph_exec);
     if (w.lz_graph != nullptr) cudaGraphExecDestroy(w.lz_graph);
     w = EigWork{};
@@ -867,6 +1101,7 @@ void eig_free(EigWork& w) {
 
 cudaError_t center_gram(EigWork& w, const int32_t* d_S, cudaStream_t stream) {
     const int n = w.n;
+    w.d_S = d_S;   // the persistent Lanczos applies the centring to vectors and reads the int32 Gram itself
     rowsum_kernel<<<(n + 7) / 8, 256, 0, stream>>>(d_S, n, w.d_rowsum);
     matrix_mean_kernel<<<1, 1024, 0, stream>>>(w.d_rowsum, n, w.d_scal, w.d_nz);
     const int bx = (n + 1023) / 1024 < 1 ? 1 : (n + 1023) / 1024;
@@ -883,12 +1118,23 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     const int kmax = w.kmax;
     cudaError_t e;
 #define VPCA_TRY(x) if ((e = (x)) != cudaSuccess) return e
-    const size_t small_doubles = 5 * (size_t)kLzCap + (size_t)kLzCap * kmax + 16 + 4 + 16 + (size_t)npart;
+    if (w.d_V == nullptr) {
+        // persistent form: one 1024-thread block per SM, launched cooperatively (all blocks co-resident)
+        int dev = 0, sms = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        const char* lp = getenv("VPCA_LZ_PERSIST");
+        w.lz_blocks = (coop != 0 && sms > 0 && !(lp != nullptr && atoi(lp) == 0)) ? sms : 0;
+    }
+    const size_t small_doubles = 5 * (size_t)kLzCap + (size_t)kLzCap * kmax + 16 + 4 + 16 + (size_t)npart +
+                                 2 * (size_t)w.lz_blocks * kLzCap;
     if (w.d_V == nullptr) {
         VPCA_TRY(cudaMalloc(&w.d_V, (size_t)n * kLzCap * sizeof(double)));
         VPCA_TRY(cudaMalloc(&w.d_lzw, 2 * (size_t)n * sizeof(double)));
         VPCA_TRY(cudaMalloc(&w.d_lzs, small_doubles * sizeof(double)));
         VPCA_TRY(cudaMalloc(&w.d_lzst, 4 * sizeof(int)));
+        VPCA_TRY(cudaMalloc(&w.d_lzbar, sizeof(unsigned)));
     }
     double* alpha = w.d_lzs;
     double* beta = alpha + kLzCap;
@@ -902,8 +1148,44 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     double* part = scal2 + 16;
     int64_t nl = 0;
     const int upd_blocks = npart, mv_blocks = (n + 3) / 4;
+    // persistent form: one cooperative launch per chunk (see lz_persist_kernel); the five-kernel graph is kept for
+    // cohorts whose start vector does not fit shared memory and as VPCA_LZ_PERSIST=0
+    const bool persist = w.lz_blocks > 0 && n <= kLzPersistMaxN;
+    double* hpart = part + npart;
+    const int rows_per = persist ? (n + w.lz_blocks - 1) / w.lz_blocks : 0;
+    const size_t persist_smem =
+        ((((size_t)n + 1) & ~(size_t)1) + kLzCap + rows_per + (size_t)rows_per * ((n + kLzSeg - 1) / kLzSeg)) * sizeof(double);
+    if (persist) VPCA_TRY(cudaFuncSetAttribute(lz_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
+    auto run_chunk = [&](int pre) -> cudaError_t {
+        if (!persist) {
+            nl += 5 * kLzChunk;
+            return cudaGraphLaunch(w.lz_graph, stream);
+        }
+        cudaError_t ce = cudaMemsetAsync(w.d_lzbar, 0, sizeof(unsigned), stream);
+        if (ce != cudaSuccess) return ce;
+        LzArgs a{};
+        a.S = w.d_S;
+        a.rowsum = w.d_rowsum;
+        a.scal = w.d_scal;
+        a.VT = w.d_V;
+        a.wbuf = w.d_lzw;
+        a.alpha = alpha;
+        a.beta = beta;
+        a.hpart = hpart;
+        a.part = part;
+        a.st = w.d_lzst;
+        a.bar = w.d_lzbar;
+        a.n = n;
+        a.cap = kLzCap;
+        a.nsteps = kLzChunk;
+        a.pre = pre;
+        void* params[] = {&a};
+        nl += 1;
+        return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lz_persist_kernel), dim3((unsigned)w.lz_blocks),
+                                           dim3(kLzThreads), params, persist_smem, stream);
+    };
 
-    if (w.lz_graph == nullptr) {
+    if (!persist && w.lz_graph == nullptr) {
         cudaGraph_t graph = nullptr;
         VPCA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         for (int g = 0; g < kLzChunk; ++g) {
@@ -933,15 +1215,14 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     double rho_prev = 0.0;
     const int max_chunks = std::min(max_iter, n - 1) / kLzChunk;
     for (int chunk = 1; chunk <= max_chunks; ++chunk) {
-        VPCA_TRY(cudaGraphLaunch(w.lz_graph, stream));
+        VPCA_TRY(run_chunk(0));
         m = chunk * kLzChunk;
-        nl += 5 * kLzChunk;
         // look at the residual after every replay up to 64 steps, then after every other one
         if (chunk > 4 && (chunk & 1) && chunk != max_chunks) continue;
         bisect_kernel<<<k, 256, 0, stream>>>(alpha, beta + 1, m, e2, w.d_evals, w.d_scal);
         invit_kernel<true><<<1, 256, 8 * (size_t)m * sizeof(double), stream>>>(alpha, beta + 1, m, k, w.d_evals, w.d_scal,
                                                                                 w.d_lu, Y);
-        lz_check_kernel<<<1, 32, 0, stream>>>(part, npart, Y, m, k, w.d_scal, w.d_lzst, res, tol);
+        lz_check_kernel<<<1, 32, 0, stream>>>(part, persist ? 1 : npart, Y, m, k, w.d_scal, w.d_lzst, res, tol);
         nl += 3;
         VPCA_TRY(cudaMemcpyAsync(hst, w.d_lzst, sizeof(hst), cudaMemcpyDeviceToHost, stream));
         VPCA_TRY(cudaMemcpyAsync(hres, res, sizeof(hres), cudaMemcpyDeviceToHost, stream));
@@ -966,7 +1247,8 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     nl = 0;
 
     // Ritz vectors, unit norm, sign rule
-    lz_ritz_kernel<<<dim3(npart, k), 256, 0, stream>>>(w.d_V, n, Y, m, w.d_evecs);
+    if (persist) lz_ritz_rm_kernel<<<(n + 7) / 8, 256, 0, stream>>>(w.d_V, n, kLzCap, Y, m, k, w.d_evecs);
+    else lz_ritz_kernel<<<dim3(npart, k), 256, 0, stream>>>(w.d_V, n, Y, m, w.d_evecs);
     lz_finish_kernel<<<k, 512, 0, stream>>>(w.d_evecs, n);
     nl += 2;
 
@@ -974,18 +1256,28 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     // lock the k Ritz vectors as the first k basis columns and run one more chunk from a fresh start vector that is
     // orthogonal to them.  Its top Ritz value is a lower bound of the largest eigenvalue of the deflated operator.
     if (k + kLzChunk < n) {
-        VPCA_TRY(cudaMemcpyAsync(w.d_V, w.d_evecs, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-        int vst[4] = {k - 1, 0, 0, k + kLzChunk};
-        VPCA_TRY(cudaMemcpyAsync(w.d_lzst, vst, sizeof(vst), cudaMemcpyHostToDevice, stream));
-        lz_init_kernel<<<npart, 32, 0, stream>>>(w.d_lzw + (size_t)(k & 1) * n, n, 0xfaceULL, part);
-        lz_dots_kernel<<<kLzCap, 128, 0, stream>>>(w.d_V, n, w.d_lzw, h1, w.d_lzst);
-        lz_update_kernel<<<upd_blocks, 256, 0, stream>>>(w.d_V, n, w.d_lzw, h1, alpha, part, w.d_lzst, 1);
-        lz_dots_kernel<<<kLzCap, 128, 0, stream>>>(w.d_V, n, w.d_lzw, h2, w.d_lzst);
-        lz_update_kernel<<<upd_blocks, 256, 0, stream>>>(w.d_V, n, w.d_lzw, h2, alpha, part, w.d_lzst, 2);
-        VPCA_TRY(cudaGraphLaunch(w.lz_graph, stream));
+        if (persist) {
+            lz_lock_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w.d_V, n, kLzCap, w.d_evecs, k);
+            int vst[4] = {k, 0, 0, k + kLzChunk};
+            VPCA_TRY(cudaMemcpyAsync(w.d_lzst, vst, sizeof(vst), cudaMemcpyHostToDevice, stream));
+            lz_init_kernel<<<npart, 32, 0, stream>>>(w.d_lzw + (size_t)(k & 1) * n, n, 0xfaceULL, part);
+            nl += 2;
+            VPCA_TRY(run_chunk(1));   // orthogonalises the start vector against the locked columns, then kLzChunk steps
+        } else {
+            VPCA_TRY(cudaMemcpyAsync(w.d_V, w.d_evecs, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+            int vst[4] = {k - 1, 0, 0, k + kLzChunk};
+            VPCA_TRY(cudaMemcpyAsync(w.d_lzst, vst, sizeof(vst), cudaMemcpyHostToDevice, stream));
+            lz_init_kernel<<<npart, 32, 0, stream>>>(w.d_lzw + (size_t)(k & 1) * n, n, 0xfaceULL, part);
+            lz_dots_kernel<<<kLzCap, 128, 0, stream>>>(w.d_V, n, w.d_lzw, h1, w.d_lzst);
+            lz_update_kernel<<<upd_blocks, 256, 0, stream>>>(w.d_V, n, w.d_lzw, h1, alpha, part, w.d_lzst, 1);
+            lz_dots_kernel<<<kLzCap, 128, 0, stream>>>(w.d_V, n, w.d_lzw, h2, w.d_lzst);
+            lz_update_kernel<<<upd_blocks, 256, 0, stream>>>(w.d_V, n, w.d_lzw, h2, alpha, part, w.d_lzst, 2);
+            nl += 5;
+            VPCA_TRY(run_chunk(0));
+        }
         bisect_kernel<<<1, 256, 0, stream>>>(alpha + k, beta + k + 1, kLzChunk, e2, theta2, scal2);
         lz_verify_kernel<<<1, 1, 0, stream>>>(w.d_evals, k, theta2, w.d_scal, w.d_lzst);
-        nl += 5 + 5 * kLzChunk + 2;
+        nl += 2;
         VPCA_TRY(cudaMemcpyAsync(hst, w.d_lzst, sizeof(hst), cudaMemcpyDeviceToHost, stream));
         VPCA_TRY(cudaStreamSynchronize(stream));
         if (launches) *launches += nl;

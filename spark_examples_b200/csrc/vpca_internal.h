@@ -20,8 +20,11 @@ struct GramPlan {
     int num_full = 0;         // leading full-weight tiles (whole-tile waves of the large-N schedule)
     int total_weight = 0;     // sum over tiles of n_eff / 16
     int tiles_col_limit = 512;   // TMEM columns the accumulators of one worker may take
-    bool exact_cover = true;  // VPCA_EXACT_COVER=0: square 256 x 256 tiles (pays 4 blocks per diagonal tile) instead of
-                              // the exact 128-block cover of the lower triangle
+    bool exact_cover = false; // VPCA_EXACT_COVER=1: the exact 128-block cover of the lower triangle (4.5 % fewer MMAs at
+                              // 2504 samples) instead of square 256 x 256 tiles.  Off by default: its N = 128 tiles need
+                              // 96 B/clk per SM from L2 (A 16 KB + B 8 KB per 256 MMA cycles) where the 256 x 256 tiles
+                              // need 64, and L2 -> SM bandwidth is what the kernel runs against -- measured on B200:
+                              // 2.06 ms vs 1.65 ms per 2504 x 1M Gram (profiles/README.md, round 2)
     int tiles_for_n = -1;     // n_samples the tile list was built for
     int tiles_for_cg = 0;
     int tiles_for_bn = 0;
@@ -114,6 +117,9 @@ struct EigWork {
     double* d_lzw = nullptr;    // 2 n: w ping-pong
     double* d_lzs = nullptr;    // alpha | beta | h | h2 | e2 | Y | theta2 | res | scal2 | part
     int* d_lzst = nullptr;      // {step, flag, ticket, step cap}
+    unsigned* d_lzbar = nullptr;   // grid barrier counter of the persistent Lanczos kernel
+    int lz_blocks = 0;          // blocks of the persistent kernel (= SMs; 0: cooperative launch unavailable or VPCA_LZ_PERSIST=0)
+    const int32_t* d_S = nullptr;   // the (symmetrised) int32 Gram the last center_gram() read
     cudaGraphExec_t lz_graph = nullptr;   // kLzChunk Lanczos steps
     int last_method = 0;        // 1 direct, 2 Lanczos, 3 Lanczos abandoned -> direct
     int last_iters = 0;         // Lanczos steps of the last solve
