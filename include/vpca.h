@@ -303,6 +303,36 @@ int vpca_get_stats(vpca_ctx* ctx, vpca_stats* out);
  * or a negative vpca_status.  Synchronises the stream. */
 int vpca_debug_gram_profile(vpca_ctx* ctx, int64_t* out, int32_t max_ctas);
 
+/* ---- Multi-dataset keying on the device ------------------------------------------------------------
+ * The 2-dataset and N-dataset branches of VariantsPcaDriver.getCallsRdd (VariantsPca.scala:153-168) key every variant by
+ * getVariantKey (:62-78: Guava Hashing.murmur3_128() over contig, start, end, reference bases, alternate bases) and then
+ * join (:115-128) or merge (:136-148) the datasets on that key.  Here the rows of ALL datasets are handed over as one CSR
+ * (rows of dataset 0 first) next to the key bytes of every row; hashing, the hash join / group-by and the concatenation
+ * of the calls run on the GPU, and the joined rows can be accumulated without leaving it.
+ *
+ * vpca_hash_keys: MurmurHash3_x64_128 (seed 0) of nkeys byte strings, key q = payload[key_offsets[q], key_offsets[q+1]);
+ *   out[2q], out[2q+1] = the two little-endian 64-bit halves of Guava's HashCode.asBytes() (HashCode.toString is their
+ *   bytes in hex).  Host buffers in and out.
+ * vpca_join_rows: mode VPCA_JOIN -- rows [0, n_left) are the left dataset, rows [n_left, nrows) the right one; one
+ *   output row per (left, right) pair with equal keys, left calls then right calls (`related._1 ++ related._2`, :127),
+ *   ordered by left row, then right row.  mode VPCA_MERGE -- n_left is ignored; keys that occur exactly
+ *   variant_set_count times (:144) yield one row: the calls of the group's rows in input order (:145), rows ordered by
+ *   the group's first input row.  sample_idx holds the calls that survive `_.hasVariation` (:164), already mapped to
+ *   [0, n_samples).  The result stays on the device inside the context until the next vpca_join_rows / vpca_reset;
+ *   *out_rows / *out_nnz report its size.  Driver-side step (the reference's join is a shuffle stage that precedes the
+ *   mapPartitions tasks): one join at a time per context.
+ * vpca_join_fetch: copies the retained result to the host (out_offsets: out_rows + 1, out_idx: out_nnz entries).
+ * vpca_accumulate_joined: encodes the retained rows and accumulates them into the staging Gram of partition_id, exactly
+ *   like vpca_accumulate_calls would for the same rows (commit / abort as usual); no host round trip of the joined rows. */
+#define VPCA_JOIN 0
+#define VPCA_MERGE 1
+int vpca_hash_keys(vpca_ctx* ctx, const uint8_t* payload, const int64_t* key_offsets, int64_t nkeys, uint64_t* out);
+int vpca_join_rows(vpca_ctx* ctx, int32_t mode, int32_t variant_set_count, int64_t n_left, const uint8_t* key_payload,
+                   const int64_t* key_offsets, const int64_t* offsets, const int32_t* sample_idx, int64_t nrows,
+                   int64_t* out_rows, int64_t* out_nnz);
+int vpca_join_fetch(vpca_ctx* ctx, int64_t* out_offsets, int32_t* out_idx);
+int vpca_accumulate_joined(vpca_ctx* ctx, int64_t partition_id);
+
 /* Host-only introspection of the Gram schedule (works without a GPU; what tests/test_schedule.py checks).
  * vpca_debug_tiles: the output tiles the kernel enumerates for n_samples -- 8 int32 per tile {rowA of CTA 0, rowA of CTA 1,
  *   rowB, n_eff (MMA N), weight prefix, flags (1: a 128-block above the diagonal is written transposed, 2: CTA 1 is a

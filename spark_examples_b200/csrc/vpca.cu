@@ -48,6 +48,8 @@ struct vpca_ctx {
     GramPlan plan;        // schedule state of the launches on `stream` (device-resident input)
     EigWork eig;
     bool eig_ready = false;
+    JoinWork join;        // multi-dataset keying (join.cu); one join at a time (join_mu)
+    std::mutex join_mu;
 
     struct Slot {
         int64_t pid = -1;
@@ -473,6 +475,19 @@ int process_calls(vpca_ctx* ctx, vpca_ctx::Lane& L, const int64_t* offsets, cons
     return VPCA_OK;
 }
 
+
+template <typename T>
+static cudaError_t grow_buffer(T** p, int64_t* cap, int64_t need) {
+    if (need <= *cap && *p != nullptr) return cudaSuccess;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    const int64_t c = need + need / 4 + 1024;
+    cudaError_t e = cudaMalloc(p, (size_t)c * sizeof(T));
+    if (e == cudaSuccess) *cap = c;
+    return e;
+}
+
 }  // namespace
 
 extern "C" {
@@ -584,6 +599,7 @@ int vpca_destroy(vpca_ctx* ctx) {
             if (d != ctx->plan.peer_rank && ctx->plan.peer_S[d] != nullptr) cudaIpcCloseMemHandle(ctx->plan.peer_base[d]);
     if (ctx->own_S) cudaFree(ctx->d_S);
     if (ctx->eig_ready) eig_free(ctx->eig);
+    join_free(ctx->join);
     gram_plan_free(ctx->plan);
     for (cudaEvent_t ev : {ctx->ev_t0, ctx->ev_t1, ctx->ev_e0, ctx->ev_e1})
         if (ev) cudaEventDestroy(ev);
@@ -725,6 +741,163 @@ int vpca_accumulate_bed(vpca_ctx* ctx, int64_t partition_id, const uint8_t* rows
     if (counted_allele != 1 && counted_allele != 2)
         return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_accumulate_bed: counted_allele must be 1 (A1) or 2 (A2)");
     return accumulate_packed(ctx, partition_id, rows, nv, stride_bytes, counted_allele);
+}
+
+// ---- multi-dataset keying (join.cu) -----------------------------------------------------------------------------
+int vpca_hash_keys(vpca_ctx* ctx, const uint8_t* payload, const int64_t* key_offsets, int64_t nkeys, uint64_t* out) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    if (nkeys < 0 || key_offsets == nullptr || (nkeys > 0 && out == nullptr))
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_hash_keys: bad argument");
+    if (nkeys == 0) return VPCA_OK;
+    for (int64_t q = 0; q < nkeys; ++q)
+        if (key_offsets[q + 1] < key_offsets[q] || key_offsets[0] < 0)
+            return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_hash_keys: key_offsets must be non-negative and non-decreasing (key %lld)", (long long)q);
+    const int64_t bytes = key_offsets[nkeys] - key_offsets[0];
+    if (bytes > 0 && payload == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_hash_keys: payload is NULL");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    uint8_t* d_pay = nullptr;
+    int64_t* d_koff = nullptr;
+    uint64_t* d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_pay, (size_t)bytes + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_koff, (size_t)(nkeys + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)nkeys * 16);
+    if (e == cudaSuccess && bytes > 0)
+        e = cudaMemcpyAsync(d_pay, payload + key_offsets[0], (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_koff, key_offsets, (size_t)(nkeys + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    // the device copy starts at the first key: shift the base pointer instead of rebasing the offsets
+    if (e == cudaSuccess) e = hash_keys(d_pay - key_offsets[0], d_koff, nkeys, d_out, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)nkeys * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_pay);
+    cudaFree(d_koff);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ctx, VPCA_ERR_CUDA, "vpca_hash_keys: %s", cudaGetErrorString(e));
+    ctx->c_launches += 1;
+    ctx->c_h2d += bytes + (nkeys + 1) * 8;
+    ctx->c_d2h += nkeys * 16;
+    return VPCA_OK;
+}
+
+int vpca_join_rows(vpca_ctx* ctx, int32_t mode, int32_t variant_set_count, int64_t n_left, const uint8_t* key_payload,
+                   const int64_t* key_offsets, const int64_t* offsets, const int32_t* sample_idx, int64_t nrows,
+                   int64_t* out_rows, int64_t* out_nnz) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    if ((mode != VPCA_JOIN && mode != VPCA_MERGE) || nrows < 0 || nrows > 0x7ffffff0ll || key_offsets == nullptr ||
+        offsets == nullptr || out_rows == nullptr || out_nnz == nullptr)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_join_rows: bad argument");
+    if (mode == VPCA_JOIN && (n_left < 0 || n_left > nrows))
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_join_rows: n_left must be in [0, nrows]");
+    if (mode == VPCA_MERGE && variant_set_count < 1)
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_join_rows: variant_set_count must be >= 1");
+    if (key_offsets[0] < 0 || offsets[0] < 0) return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_join_rows: negative offset");
+    for (int64_t q = 0; q < nrows; ++q)
+        if (key_offsets[q + 1] < key_offsets[q] || offsets[q + 1] < offsets[q])
+            return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_join_rows: offsets must be non-decreasing (row %lld)", (long long)q);
+    const int64_t kbytes = key_offsets[nrows] - key_offsets[0], nnz = offsets[nrows] - offsets[0];
+    if ((kbytes > 0 && key_payload == nullptr) || (nnz > 0 && sample_idx == nullptr))
+        return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_join_rows: NULL payload");
+    std::lock_guard<std::mutex> jl(ctx->join_mu);
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    JoinWork& w = ctx->join;
+    w.out_rows = -1;
+    CUDA_OK(ctx, grow_buffer(&w.d_payload, &w.cap_payload, kbytes + 16));
+    if (nrows + 1 > w.cap_in_rows || w.d_key_off == nullptr || w.d_off == nullptr) {
+        cudaFree(w.d_key_off);
+        cudaFree(w.d_off);
+        w.d_key_off = w.d_off = nullptr;
+        w.cap_in_rows = 0;
+        const int64_t c = nrows + nrows / 4 + 1024;
+        CUDA_OK(ctx, cudaMalloc(&w.d_key_off, (size_t)c * 8));
+        CUDA_OK(ctx, cudaMalloc(&w.d_off, (size_t)c * 8));
+        w.cap_in_rows = c;
+    }
+    CUDA_OK(ctx, grow_buffer(&w.d_idx, &w.cap_in_nnz, nnz + 1));
+    if (kbytes > 0)
+        CUDA_OK(ctx, cudaMemcpyAsync(w.d_payload, key_payload + key_offsets[0], (size_t)kbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(w.d_key_off, key_offsets, (size_t)(nrows + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(ctx, cudaMemcpyAsync(w.d_off, offsets, (size_t)(nrows + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz > 0)
+        CUDA_OK(ctx, cudaMemcpyAsync(w.d_idx, sample_idx + offsets[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->c_h2d += kbytes + 2 * (nrows + 1) * 8 + nnz * 4;
+    int64_t launches = 0, rows = 0, calls = 0;
+    // the device copies start at the first key / first call: shift the base pointers instead of rebasing the offsets
+    cudaError_t e = join_rows(w, mode, variant_set_count, n_left, w.d_payload - key_offsets[0], w.d_key_off, w.d_off,
+                              w.d_idx - offsets[0], nrows, ctx->stream, &rows, &calls, &launches);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // the caller's buffers were read asynchronously
+    ctx->c_launches += launches;
+    if (e != cudaSuccess)
+        return fail(ctx, e == cudaErrorMemoryAllocation ? VPCA_ERR_NOMEM : VPCA_ERR_CUDA, "vpca_join_rows: %s", cudaGetErrorString(e));
+    w.out_rows = rows;
+    w.out_nnz = calls;
+    *out_rows = rows;
+    *out_nnz = calls;
+    return VPCA_OK;
+}
+
+int vpca_join_fetch(vpca_ctx* ctx, int64_t* out_offsets, int32_t* out_idx) {
+    if (ctx == nullptr || out_offsets == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
+    std::lock_guard<std::mutex> jl(ctx->join_mu);
+    JoinWork& w = ctx->join;
+    if (w.out_rows < 0) return fail(ctx, VPCA_ERR_STATE, "no joined rows: call vpca_join_rows first");
+    if (w.out_nnz > 0 && out_idx == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "out_idx is NULL");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    CUDA_OK(ctx, cudaMemcpyAsync(out_offsets, w.d_out_off, (size_t)(w.out_rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (w.out_nnz > 0)
+        CUDA_OK(ctx, cudaMemcpyAsync(out_idx, w.d_out_idx, (size_t)w.out_nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->c_d2h += (w.out_rows + 1) * 8 + w.out_nnz * 4;
+    return VPCA_OK;
+}
+
+int vpca_accumulate_joined(vpca_ctx* ctx, int64_t partition_id) {
+    if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> jl(ctx->join_mu);
+    JoinWork& w = ctx->join;
+    if (w.out_rows < 0) return fail(ctx, VPCA_ERR_STATE, "no joined rows: call vpca_join_rows first");
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    const int64_t nv = w.out_rows;
+    if (nv == 0) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
+        return VPCA_OK;
+    }
+    CallScope sc{ctx, partition_id, nv};
+    int rc = sc.begin();
+    if (rc != VPCA_OK) return rc;
+    auto body = [&](vpca_ctx::Lane& L) -> int {
+        int r = prepare_slot(ctx, L, sc);
+        if (r != VPCA_OK) return r;
+        *L.h_flags = 0;
+        CUDA_OK(ctx, cudaMemsetAsync(L.d_flags, 0, sizeof(int), L.stream));
+        const int64_t P = ctx->panel;
+        int chunk = 0;
+        for (int64_t v = 0; v < nv; v += ctx->chunk_variants, ++chunk) {
+            const int64_t nvc = std::min(ctx->chunk_variants, nv - v);
+            const int b = chunk & 1;
+            // the joined CSR is device-resident: rows [v, v + nvc) are encoded straight from it (absolute offsets, base 0)
+            CUDA_OK(ctx, encode_calls(w.d_out_off + v, 0, w.d_out_idx, 4, nvc, ctx->n, ctx->elem_bits, ctx->max_mult, L.d_x[b],
+                                      P, P, L.d_flags, L.stream));
+            ctx->c_launches += 2;
+            r = launch_gram(ctx, L.plan, L.stream, L.ev_t0, L.ev_t1, L.d_x[b], nvc, P, P, sc.target);
+            if (r != VPCA_OK) return r;
+        }
+        CUDA_OK(ctx, cudaMemcpyAsync(L.h_flags, L.d_flags, sizeof(int), cudaMemcpyDeviceToHost, L.stream));
+        CUDA_OK(ctx, cudaStreamSynchronize(L.stream));
+        lane_gram_time(ctx, L);
+        if (*L.h_flags & 1)
+            return fail(ctx, VPCA_ERR_INDEX_OUT_OF_RANGE, "sample index outside [0, %d) (the reference throws at "
+                        "VariantsPca.scala:59/:188)", ctx->n);
+        if (*L.h_flags & 2)
+            return fail(ctx, VPCA_ERR_OVERFLOW, "a sample is listed more than max_multiplicity=%d times in one joined row "
+                        "(a sample present in both datasets counts twice, VariantsPca.scala:127/:187)", ctx->max_mult);
+        return VPCA_OK;
+    };
+    {
+        LaneGuard lg(ctx);   // orders the lane after the join kernels on the context's stream
+        rc = lg.rc;
+        if (rc == VPCA_OK) rc = body(*lg.lane);
+    }
+    return sc.end(rc);
 }
 
 int vpca_commit(vpca_ctx* ctx, int64_t partition_id) {

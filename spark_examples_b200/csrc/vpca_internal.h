@@ -91,6 +91,38 @@ cudaError_t encode_calls(const int64_t* d_off, int64_t base, const void* d_idx, 
 cudaError_t encode_bits(const uint8_t* d_bits, int64_t stride, int64_t nv, int n, int elem_bits, void* d_x, int64_t ld,
                         int64_t panel, int code, cudaStream_t stream);
 
+// ---- multi-dataset keying: variant keys, join, merge (join.cu) ---------------------------------------------
+struct JoinWork {
+    uint64_t* d_hash = nullptr;      // 2 per row: MurmurHash3_x64_128 of the variant key
+    int32_t* d_table = nullptr;      // open-addressing table of row indices (-1 = empty)
+    uint64_t table_slots = 0;
+    int64_t* d_rows = nullptr;       // output rows / calls each input row is responsible for, and their exclusive scans
+    int64_t* d_len = nullptr;
+    int64_t* d_row_base = nullptr;
+    int64_t* d_nnz_base = nullptr;
+    int32_t* d_leader = nullptr;
+    int64_t* d_prefix = nullptr;
+    int64_t* d_block = nullptr;      // scan scratch
+    int64_t* d_totals = nullptr;     // {output rows, output calls}
+    int64_t* h_totals = nullptr;     // pinned copy
+    int64_t cap_rows = 0;
+    int64_t* d_out_off = nullptr;    // the joined CSR: out_rows + 1 offsets, out_nnz sample indices
+    int32_t* d_out_idx = nullptr;
+    int64_t cap_out_rows = 0, cap_out_nnz = 0;
+    int64_t out_rows = -1, out_nnz = 0;   // result of the last join (-1: none)
+    // device copies of the caller's input (grow-only)
+    uint8_t* d_payload = nullptr;
+    int64_t* d_key_off = nullptr;
+    int64_t* d_off = nullptr;
+    int32_t* d_idx = nullptr;
+    int64_t cap_payload = 0, cap_in_rows = 0, cap_in_nnz = 0;
+};
+cudaError_t hash_keys(const uint8_t* d_payload, const int64_t* d_off, int64_t nkeys, uint64_t* d_hash, cudaStream_t stream);
+cudaError_t join_rows(JoinWork& w, int mode, int variant_set_count, int64_t n_left, const uint8_t* d_payload,
+                      const int64_t* d_key_off, const int64_t* d_off, const int32_t* d_idx, int64_t nrows, cudaStream_t stream,
+                      int64_t* out_rows, int64_t* out_nnz, int64_t* launches);
+void join_free(JoinWork& w);
+
 // ---- centering + eigensolve (eig.cu) ---------------------------------------------------------------
 struct EigWork {
     int n = 0;

@@ -37,6 +37,12 @@ object NativePca {
   /** PLINK .bed rows as on disk (2 bits per sample); countedAllele 1 = A1, 2 = A2. */
   @native def accumulateBed(handle: Long, partitionId: Long, rows: Array[Byte], nv: Long, strideBytes: Long,
                             countedAllele: Int): Unit
+  /** joinDatasets (mode 0, VariantsPca.scala:115-128) / mergeDatasets (mode 1, :136-148) on the GPU: rows of all datasets
+   *  (dataset 0 first; the calls with variation as callset indices) and the bytes getVariantKey (:65-73) would hash, per
+   *  row.  The joined rows stay on the device; returns their number.  Follow with accumulateJoined + commit. */
+  @native def joinRows(handle: Long, mode: Int, variantSetCount: Int, nLeft: Long, keyBytes: Array[Byte],
+                       keyOffsets: Array[Long], offsets: Array[Long], sampleIdx: Array[Int], nRows: Long): Long
+  @native def accumulateJoined(handle: Long, partitionId: Long): Unit
   @native def commit(handle: Long, partitionId: Long): Unit
   @native def abort(handle: Long, partitionId: Long): Unit
   @native def finalizeGram(handle: Long): Unit

@@ -287,6 +287,53 @@ JNIEXPORT jint JNICALL PCA(computePca)(JNIEnv* env, jobject self, jlong h, jint 
 }
 
 /* pinned host memory as direct ByteBuffers (shared by both classes) */
+/* joinDatasets / mergeDatasets (VariantsPca.scala:115-148) on the device: key bytes + rows of all datasets in, the joined
+ * rows stay in the context (accumulateJoined).  Returns the number of joined rows. */
+JNIEXPORT jlong JNICALL PCA(joinRows)(JNIEnv* env, jobject self, jlong h, jint mode, jint variantSetCount, jlong nLeft,
+                                      jbyteArray keyBytes, jlongArray keyOffsets, jlongArray offsets, jintArray idx, jlong nrows) {
+    (void)self;
+    target t = from_ctx(h);
+    if (keyBytes == NULL || keyOffsets == NULL || offsets == NULL || idx == NULL) { throw_arg(env, "joinRows: null array%lld%lld", 0, 0); return 0; }
+    const jlong kb_len = (*env)->GetArrayLength(env, keyBytes), ko_len = (*env)->GetArrayLength(env, keyOffsets);
+    const jlong off_len = (*env)->GetArrayLength(env, offsets), idx_len = (*env)->GetArrayLength(env, idx);
+    if (nrows < 0 || nrows + 1 > ko_len || nrows + 1 > off_len) {
+        throw_arg(env, "joinRows: nrows = %lld needs nrows + 1 key offsets and row offsets (%lld present)", nrows, ko_len < off_len ? ko_len : off_len);
+        return 0;
+    }
+    int64_t* ko = (int64_t*)xmalloc(env, (size_t)(nrows + 1) * 8);
+    int64_t* off = ko ? (int64_t*)xmalloc(env, (size_t)(nrows + 1) * 8) : NULL;
+    if (ko == NULL || off == NULL) { free(ko); return 0; }
+    (*env)->GetLongArrayRegion(env, keyOffsets, 0, (jsize)(nrows + 1), (jlong*)ko);
+    (*env)->GetLongArrayRegion(env, offsets, 0, (jsize)(nrows + 1), (jlong*)off);
+    jlong rows = 0;
+    if (ko[0] != 0 || off[0] != 0 || ko[nrows] < 0 || ko[nrows] > kb_len || off[nrows] < 0 || off[nrows] > idx_len) {
+        throw_arg(env, "joinRows: offsets must start at 0 and end inside the arrays (%lld key bytes, %lld calls)", kb_len, idx_len);
+    } else {
+        uint8_t* kb = (uint8_t*)xmalloc(env, (size_t)ko[nrows]);
+        int32_t* ix = kb ? (int32_t*)xmalloc(env, (size_t)off[nrows] * 4) : NULL;
+        if (kb != NULL && ix != NULL) {
+            if (ko[nrows] > 0) (*env)->GetByteArrayRegion(env, keyBytes, 0, (jsize)ko[nrows], (jbyte*)kb);
+            if (off[nrows] > 0) (*env)->GetIntArrayRegion(env, idx, 0, (jsize)off[nrows], (jint*)ix);
+            int64_t out_rows = 0, out_nnz = 0;
+            const int rc = vpca_join_rows(t.ctx, mode, variantSetCount, nLeft, kb, ko, off, ix, nrows, &out_rows, &out_nnz);
+            if (rc != VPCA_OK) throw_rc(env, t, rc);
+            rows = out_rows;
+        }
+        free(ix);
+        free(kb);
+    }
+    free(off);
+    free(ko);
+    return rows;
+}
+
+JNIEXPORT void JNICALL PCA(accumulateJoined)(JNIEnv* env, jobject self, jlong h, jlong pid) {
+    (void)self;
+    target t = from_ctx(h);
+    const int rc = vpca_accumulate_joined(t.ctx, pid);
+    if (rc != VPCA_OK) throw_rc(env, t, rc);
+}
+
 JNIEXPORT jobject JNICALL PCA(allocPinned)(JNIEnv* env, jobject self, jlong bytes) {
     (void)self;
     void* p = NULL;

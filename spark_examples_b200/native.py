@@ -23,6 +23,7 @@ VPCA_ERR_OVERFLOW = -5
 VPCA_ERR_STATE = -6
 VPCA_ERR_NOMEM = -7
 VPCA_ERR_UNSUPPORTED = -8
+JOIN, MERGE = 0, 1    # vpca_join_rows modes (VPCA_JOIN / VPCA_MERGE)
 
 DTYPE_I8 = 0
 DTYPE_BF16 = 1
@@ -44,6 +45,7 @@ EXPORTED_SYMBOLS = (
     "vpca_accumulate_bits", "vpca_gram_set_peer_mode", "vpca_gram_gather", "vpca_accumulate_bed",
     "vpca_synchronize", "vpca_host_alloc", "vpca_host_free", "vpca_gram_set_peers_local", "vpca_owner_row_bands",
     "vpca_get_gram_band", "vpca_variant_count", "vpca_debug_rebalance",
+    "vpca_hash_keys", "vpca_join_rows", "vpca_join_fetch", "vpca_accumulate_joined",
     "vpca_pool_create", "vpca_pool_destroy", "vpca_pool_size", "vpca_pool_ctx", "vpca_pool_last_error", "vpca_pool_reset",
     "vpca_pool_accumulate_calls", "vpca_pool_accumulate_calls_u16", "vpca_pool_accumulate_bits", "vpca_pool_accumulate_bed",
     "vpca_pool_commit", "vpca_pool_abort", "vpca_pool_reduce_and_finalize", "vpca_pool_get_gram", "vpca_pool_compute_pca",
@@ -134,6 +136,14 @@ def load_library() -> ctypes.CDLL:
     L.vpca_accumulate_calls.argtypes = [vp, i64, vp, vp, i64]
     L.vpca_accumulate_calls_u16.restype = ctypes.c_int
     L.vpca_accumulate_calls_u16.argtypes = [vp, i64, vp, vp, i64]
+    L.vpca_hash_keys.restype = ctypes.c_int
+    L.vpca_hash_keys.argtypes = [vp, vp, vp, i64, vp]
+    L.vpca_join_rows.restype = ctypes.c_int
+    L.vpca_join_rows.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.vpca_join_fetch.restype = ctypes.c_int
+    L.vpca_join_fetch.argtypes = [vp, vp, vp]
+    L.vpca_accumulate_joined.restype = ctypes.c_int
+    L.vpca_accumulate_joined.argtypes = [vp, i64]
     L.vpca_accumulate_bits.restype = ctypes.c_int
     L.vpca_accumulate_bits.argtypes = [vp, i64, vp, i64, i64]
     L.vpca_accumulate_bed.restype = ctypes.c_int
@@ -324,6 +334,50 @@ class NativePca:
         off, idx = self._csr(offsets, sample_idx)
         self._check(self._lib.vpca_accumulate_calls(self._h, int(partition_id), _host_ptr(off),
                                                     _host_ptr(idx) if len(idx) else None, len(off) - 1))
+
+    # -- multi-dataset keying on the device (VariantsPca.scala:62-78, :115-148) --------------------------------------
+    @staticmethod
+    def _keys(keys):
+        """list of bytes -> (payload uint8, key_offsets int64)"""
+        lens = np.fromiter((len(k) for k in keys), dtype=np.int64, count=len(keys))
+        koff = np.zeros(len(keys) + 1, dtype=np.int64)
+        np.cumsum(lens, out=koff[1:])
+        payload = np.frombuffer(b"".join(keys), dtype=np.uint8) if len(keys) else np.zeros(0, np.uint8)
+        return np.ascontiguousarray(payload), koff
+
+    def hashKeys(self, keys) -> np.ndarray:
+        """MurmurHash3_x64_128 of every byte string in `keys`, computed on the GPU: (len(keys), 2) uint64 (h1, h2);
+        `bytes(row).hex()` of a little-endian row is Guava's HashCode.toString (vpca_hash_keys)."""
+        payload, koff = self._keys(keys)
+        out = np.zeros((len(keys), 2), dtype=np.uint64)
+        self._check(self._lib.vpca_hash_keys(self._h, _host_ptr(payload) if len(payload) else None, _host_ptr(koff),
+                                             len(keys), _host_ptr(out) if len(keys) else None))
+        return out
+
+    def joinRows(self, mode: int, keys, offsets, sample_idx, n_left: int = 0, variant_set_count: int = 2):
+        """Join (mode JOIN: rows [0, n_left) x rows [n_left, ...)) or merge (mode MERGE) of the rows of several datasets on
+        their variant keys, on the GPU; the joined rows stay there (accumulateJoined / joinFetch).  Returns (rows, calls)."""
+        payload, koff = self._keys(keys)
+        off, idx = self._csr(offsets, sample_idx)
+        if len(off) - 1 != len(keys):
+            raise VpcaError(VPCA_ERR_BAD_ARG, "one key per row")
+        rows, nnz = ctypes.c_int64(0), ctypes.c_int64(0)
+        self._check(self._lib.vpca_join_rows(self._h, int(mode), int(variant_set_count), int(n_left),
+                                             _host_ptr(payload) if len(payload) else None, _host_ptr(koff), _host_ptr(off),
+                                             _host_ptr(idx) if len(idx) else None, len(keys), ctypes.byref(rows),
+                                             ctypes.byref(nnz)))
+        return int(rows.value), int(nnz.value)
+
+    def joinFetch(self, rows: int, nnz: int):
+        """The joined rows of the last joinRows as a host CSR (offsets int64, sample indices int32)."""
+        off = np.zeros(rows + 1, dtype=np.int64)
+        idx = np.zeros(max(nnz, 1), dtype=np.int32)
+        self._check(self._lib.vpca_join_fetch(self._h, _host_ptr(off), _host_ptr(idx)))
+        return off, idx[:nnz]
+
+    def accumulateJoined(self, partition_id: int):
+        """Encode + Gram of the joined rows of the last joinRows, straight from device memory (vpca_accumulate_joined)."""
+        self._check(self._lib.vpca_accumulate_joined(self._h, int(partition_id)))
 
     def accumulateCallsRaw(self, partition_id: int, off_ptr: int, idx_ptr: int, nv: int, idx_bytes: int = 4):
         """Same, from raw host addresses (e.g. pinned torch tensors) -- no copies on the Python side.

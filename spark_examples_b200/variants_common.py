@@ -28,6 +28,19 @@ class CallsBatch:
 
 
 @dataclass
+class JoinedSlice:
+    """The rows of several datasets (dataset 0 first) with the bytes of their variant keys, to be joined (2 datasets,
+    VariantsPca.scala:115-128) or merged (N datasets, :136-148) on the GPU (vpca_join_rows); `offsets` / `idx` hold the
+    calls that pass `_.hasVariation` (:164) as callset indices."""
+    mode: int                # native.JOIN | native.MERGE
+    keys: list               # bytes per row: contig, start, end, reference bases, alternate bases (:65-73)
+    offsets: np.ndarray      # int64, rows + 1
+    idx: np.ndarray          # int32
+    n_left: int              # JOIN: rows of the left dataset
+    variant_set_count: int   # MERGE: group size a key must have (:144)
+
+
+@dataclass
 class SyntheticSlice:
     """Variants [v0, v0 + nv) of the synthetic cohort; materialised on the device, never on the host."""
     seed: int

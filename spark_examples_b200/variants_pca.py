@@ -30,7 +30,7 @@ from .conf import PcaConf
 from .jformat import jdouble
 from .records import Call, CallData, Variant
 from .parquet_calls import ParquetSlice
-from .variants_common import BedSlice, CallsBatch, SyntheticSlice, VariantsCommon, VariantsDataset
+from .variants_common import BedSlice, CallsBatch, JoinedSlice, SyntheticSlice, VariantsCommon, VariantsDataset
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -90,15 +90,21 @@ def murmur3_128(data: bytes, seed: int = 0) -> str:
     return (struct.pack("<QQ", h1, h2)).hex()
 
 
-def getVariantKey(variant: Variant, debug: bool = False) -> str:
-    """VariantsPca.scala:62-78: murmur3_128 of contig, start, end, reference bases, joined alternate bases."""
+def variantKeyBytes(variant: Variant, debug: bool = False) -> bytes:
+    """The bytes VariantsPca.scala:65-73 feeds the hasher: putString(contig), putLong(start), putLong(end),
+    putString(referenceBases), putString(alternateBases.mkString("")) -- Guava writes longs little-endian."""
     alternate = "".join(variant.alternateBases) if variant.alternateBases is not None else ""
     reference = variant.referenceBases if variant.referenceBases is not None else ""
     if debug:
         print(f"{variant.contig}: ({variant.start}, {variant.end}) ref={reference} alt={alternate}")
-    payload = (variant.contig.encode("utf-8") + struct.pack("<q", variant.start) + struct.pack("<q", variant.end) +
-               reference.encode("utf-8") + alternate.encode("utf-8"))
-    return murmur3_128(payload)
+    return (variant.contig.encode("utf-8") + struct.pack("<q", variant.start) + struct.pack("<q", variant.end) +
+            reference.encode("utf-8") + alternate.encode("utf-8"))
+
+
+def getVariantKey(variant: Variant, debug: bool = False) -> str:
+    """VariantsPca.scala:62-78: murmur3_128 of contig, start, end, reference bases, joined alternate bases (host
+    restatement; the product path hashes the same bytes on the GPU, vpca_hash_keys / vpca_join_rows)."""
+    return murmur3_128(variantKeyBytes(variant, debug))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -121,6 +127,8 @@ class CallsRdd:
                 p = CallsBatch(*plink.rows_to_calls(p.rows(), self.n_samples, p.counted))
             if isinstance(p, ParquetSlice):
                 p = p.load()
+            if isinstance(p, JoinedSlice):
+                p = joined_rows_on_host(p)
             for v in range(len(p.offsets) - 1):
                 rows.append(p.idx[p.offsets[v]:p.offsets[v + 1]].tolist())
         return rows
@@ -222,6 +230,27 @@ class VariantsPcaDriver:
                     groups.setdefault(getVariantKey(v), []).append(extractCallInfo(v, mapping))
         return [[c for calls in g for c in calls] for g in groups.values() if len(g) == variantSetCount]
 
+    def _joined_slice(self, datasets: List[VariantsDataset], variantSetCount: int) -> JoinedSlice:
+        """What joinDatasets / mergeDatasets shuffle, laid out for vpca_join_rows: per variant its key bytes (:65-73) and
+        the callset indices with variation (:56-60, :164), datasets in order."""
+        mapping, debug = self.common.indexes, self.conf.debugDatasets()
+        join = variantSetCount == 2
+        keys, lens, idx, n_left = [], [], [], 0
+        for d, ds in enumerate(datasets[:2] if join else datasets):
+            for part in ds.partitions:
+                if isinstance(part, (CallsBatch, SyntheticSlice, BedSlice, ParquetSlice)):
+                    raise ValueError("joining datasets needs Variant records (the key is made of contig / start / end / bases)")
+                for v in part:
+                    keys.append(variantKeyBytes(v, debug and join))
+                    row = [c.callsetId for c in extractCallInfo(v, mapping) if c.hasVariation]
+                    lens.append(len(row))
+                    idx.extend(row)
+            if d == 0:
+                n_left = len(keys)
+        off = np.zeros(len(keys) + 1, np.int64)
+        np.cumsum(np.asarray(lens, np.int64), out=off[1:])
+        return JoinedSlice(native.JOIN if join else native.MERGE, keys, off, np.asarray(idx, np.int32), n_left, variantSetCount)
+
     # -- VariantsPca.scala:153-168 ----------------------------------------------------------------------------------
     def getCallsRdd(self, data: List[VariantsDataset]) -> CallsRdd:
         n = len(self.common.indexes)
@@ -236,6 +265,9 @@ class VariantsPcaDriver:
                 else:
                     parts.append(_rows_to_batch([extractCallInfo(v, mapping) for v in part]))
             return CallsRdd(parts, n)
+        if os.environ.get("VPCA_HOST_JOIN") != "1":
+            # keying, join / merge and the concatenation of the calls run on the GPU and feed the encoder there
+            return CallsRdd([self._joined_slice(data, variantSetCount)], n)
         callsets = self.joinDatasets(data) if variantSetCount == 2 else self.mergeDatasets(data, variantSetCount)
         per = self.conf.variantsPerPartition()
         return CallsRdd([_rows_to_batch(callsets[i:i + per]) for i in range(0, max(len(callsets), 1), per)], n)
@@ -256,7 +288,10 @@ class VariantsPcaDriver:
             if isinstance(part, ParquetSlice):
                 part = part.load()                              # row group -> CSR rows, no per-record work
             try:
-                if isinstance(part, BedSlice):
+                if isinstance(part, JoinedSlice):
+                    nat.joinRows(part.mode, part.keys, part.offsets, part.idx, part.n_left, part.variant_set_count)
+                    nat.accumulateJoined(pid)                   # the joined rows never leave the device
+                elif isinstance(part, BedSlice):
                     nat.accumulateBed(pid, part.rows(), part.counted)
                 else:
                     nat.accumulateCalls(pid, part.offsets, part.idx)
@@ -398,6 +433,33 @@ class VariantsPcaDriver:
         nat.synthPanelsDevice(part.seed, part.v0, part.nv, 0, buf.data_ptr(), panel)
         nat.accumulatePanels(buf.data_ptr(), part.nv, panel)
         torch.cuda.current_stream().synchronize()      # `buf` must outlive the kernels that read it
+
+
+def joined_rows_on_host(p: JoinedSlice) -> CallsBatch:
+    """The rows vpca_join_rows produces for `p`, computed with Python dicts (CallsRdd.collect and the tests' reference;
+    same order: join by left row then right row, merge by first row of the group), empty rows dropped like :166."""
+    rows = [p.idx[p.offsets[i]:p.offsets[i + 1]].tolist() for i in range(len(p.keys))]
+    hashed = [murmur3_128(k) for k in p.keys]
+    out: List[List[int]] = []
+    if p.mode == native.JOIN:
+        right: Dict[str, List[int]] = {}
+        for j in range(p.n_left, len(rows)):
+            right.setdefault(hashed[j], []).append(j)
+        for i in range(p.n_left):
+            for j in right.get(hashed[i], ()):
+                out.append(rows[i] + rows[j])
+    else:
+        groups: Dict[str, List[int]] = {}
+        for i, h in enumerate(hashed):
+            groups.setdefault(h, []).append(i)
+        for members in groups.values():
+            if len(members) == p.variant_set_count:
+                out.append([c for i in members for c in rows[i]])
+    out = [r for r in out if len(r) > 0]
+    off = np.zeros(len(out) + 1, np.int64)
+    if out:
+        off[1:] = np.cumsum([len(r) for r in out])
+    return CallsBatch(off, np.asarray([c for r in out for c in r], np.int32))
 
 
 def _rows_to_batch(rows: Iterable[Sequence[CallData]]) -> CallsBatch:

@@ -184,3 +184,24 @@ def test_compute_pca_needs_two_components():
     d = VariantsPcaDriver(conf, common=pkg.VariantsCommon(conf, callsets=[("a-0", "A"), ("a-1", "B")], datasets=[[]]))
     with pytest.raises(IndexError):
         d.computePca(None)
+
+
+def test_joined_slice_rows_equal_the_record_level_join_and_merge(monkeypatch):
+    """getCallsRdd hands 2+ datasets to the GPU as a JoinedSlice; its host rendering (collect) must equal what the
+    record-level joinDatasets / mergeDatasets (VPCA_HOST_JOIN=1, the dict-based restatement of :115-148) produce."""
+    rng = np.random.default_rng(17)
+    callsets = [(f"p-{i}", f"P{i}") for i in range(9)] + [(f"q-{i}", f"Q{i}") for i in range(7)]
+
+    def ds(cs, positions):
+        return [pkg.Variant("1", start=int(p), end=int(p) + 1, referenceBases="A", alternateBases=["G"],
+                            calls=[pkg.Call(cid, genotype=[int(rng.random() < 0.4), 0]) for cid, _ in cs]) for p in positions]
+
+    d1, d2 = ds(callsets[:9], rng.integers(0, 60, 80)), ds(callsets[9:], rng.integers(0, 60, 80))   # repeated positions
+    for datasets in ([d1, d2], [d1, d2, d2[:30]]):
+        got = {}
+        for host in ("0", "1"):
+            monkeypatch.setenv("VPCA_HOST_JOIN", host)
+            conf = pkg.PcaConf([])
+            d = VariantsPcaDriver(conf, common=pkg.VariantsCommon(conf, callsets=callsets, datasets=datasets))
+            got[host] = sorted(d.getCallsRdd(d.getData).collect())
+        assert got["0"] == got["1"] and len(got["0"]) > 5
