@@ -862,7 +862,14 @@ struct LzArgs {
     int* st;                // st[0] = next step, st[1] = flag (0 run, 2 breakdown), st[3] = step cap
     unsigned* bar;          // grid barrier counter, zero at launch
     int n, cap, nsteps, pre;
+    long long* prof;        // optional (VPCA_LZ_PROF=1): block 0's globaltimer at the phase boundaries of each step, 4 per step
 };
+
+__device__ __forceinline__ long long lz_timer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void lz_grid_barrier(unsigned* ctr, unsigned& target, unsigned nblocks) {
     __syncthreads();
@@ -883,11 +890,37 @@ __device__ __forceinline__ void lz_grid_barrier(unsigned* ctr, unsigned& target,
 // One Gram-Schmidt pass on the rows of this block: hs = sum over blocks of hin (columns [0, jc)), y -= VT hs, and
 // (hout != nullptr) this block's share of VT^T y.  Returns hs[jc - 1] (alpha contribution) in every thread.
 __device__ __forceinline__ double lz_orth_pass(const LzArgs& a, int nblocks, int i0, int R, int jc, const double* hin,
-                                               double* hout, double* hs, double* y) {
-    for (int q = threadIdx.x; q < jc; q += kLzThreads) {
-        double acc = 0.0;
-        for (int b = 0; b < nblocks; ++b) acc += __ldcg(hin + (size_t)b * a.cap + q);
-        hs[q] = acc;
+                                               double* hout, double* hs, double* y, double* red2) {
+    // hs[q] = sum over blocks of hin[b][q].  148 dependent-latency L2 loads per column if one thread walked the blocks;
+    // instead warp w takes the blocks b = w, w + 32, ... (a handful of independent coalesced loads per lane, 32 columns
+    // at a time) and the 32 partial sums of a column are added in a fixed order: deterministic and ~1 L2 latency deep.
+    {
+        const int lane_ = threadIdx.x & 31, wid_ = threadIdx.x >> 5;
+        for (int qc = 0; qc < jc; qc += 32) {
+            const int q = qc + lane_;
+            double acc = 0.0;
+            if (q < jc) {
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+                int b = wid_;
+                for (; b + 96 < nblocks; b += 128) {
+                    p0 += __ldcg(hin + (size_t)b * a.cap + q);
+                    p1 += __ldcg(hin + (size_t)(b + 32) * a.cap + q);
+                    p2 += __ldcg(hin + (size_t)(b + 64) * a.cap + q);
+                    p3 += __ldcg(hin + (size_t)(b + 96) * a.cap + q);
+                }
+                for (; b < nblocks; b += 32) p0 += __ldcg(hin + (size_t)b * a.cap + q);
+                acc = (p0 + p1) + (p2 + p3);
+            }
+            __syncthreads();                 // red2 of the previous column chunk has been consumed
+            red2[wid_ * 33 + lane_] = acc;
+            __syncthreads();
+            if (wid_ == 0 && q < jc) {
+                double t = 0.0;
+#pragma unroll 8
+                for (int w2 = 0; w2 < kLzThreads / 32; ++w2) t += red2[w2 * 33 + lane_];
+                hs[q] = t;
+            }
+        }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -912,6 +945,7 @@ __device__ __forceinline__ double lz_orth_pass(const LzArgs& a, int nblocks, int
 __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs a) {
     extern __shared__ __align__(16) double lzsm[];
     __shared__ double red[33];
+    __shared__ double red2[(kLzThreads / 32) * 33];
     const int n = a.n, nblocks = (int)gridDim.x;
     const int rows_per = (n + nblocks - 1) / nblocks;
     const int i0 = min(n, (int)blockIdx.x * rows_per);
@@ -944,7 +978,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
                 hp[(size_t)blockIdx.x * a.cap + q] = acc;
             }
             lz_grid_barrier(a.bar, target, nblocks);
-            lz_orth_pass(a, nblocks, i0, R, j, hp, nullptr, hs, y);
+            lz_orth_pass(a, nblocks, i0, R, j, hp, nullptr, hs, y, red2);
         }
         for (int r = threadIdx.x; r < R; r += kLzThreads) w_in[i0 + r] = y[r];
         lz_grid_barrier(a.bar, target, nblocks);
@@ -955,6 +989,8 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         const double* w_in = a.wbuf + (size_t)(j & 1) * n;
         double* w_out = a.wbuf + (size_t)((j + 1) & 1) * n;
         // ---- phase A: stage w_in, beta_j, y = C v_j on the own rows, share of V^T y
+        const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && j < 64;
+        if (prof) a.prof[j * 4 + 0] = lz_timer();
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         for (int c = threadIdx.x; c < n; c += kLzThreads) {
             const double wv = __ldcg(w_in + c);
@@ -1011,11 +1047,14 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
             for (int r = 0; r < R; ++r) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
             hp1[(size_t)blockIdx.x * a.cap + q] = acc;
         }
+        if (prof) a.prof[j * 4 + 1] = lz_timer();
         lz_grid_barrier(a.bar, target, nblocks);
         // ---- phase B / C: classical Gram-Schmidt, applied twice
-        const double a1 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp1, hp2, hs, y);
+        if (prof) a.prof[j * 4 + 2] = lz_timer();
+        const double a1 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp1, hp2, hs, y, red2);
+        if (prof) a.prof[j * 4 + 3] = lz_timer();
         lz_grid_barrier(a.bar, target, nblocks);
-        const double a2 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp2, nullptr, hs, y);
+        const double a2 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp2, nullptr, hs, y, red2);
         for (int r = threadIdx.x; r < R; r += kLzThreads) w_out[i0 + r] = y[r];
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             a.alpha[j] = a1 + a2;
@@ -1093,7 +1132,7 @@ void eig_free(EigWork& w) {
     cudaFree(w.d_C); cudaFree(w.d_rowsum); cudaFree(w.d_v); cudaFree(w.d_w); cudaFree(w.d_p);
     cudaFree(w.d_diag); cudaFree(w.d_off); cudaFree(w.d_tau); cudaFree(w.d_scal); cudaFree(w.d_evals);
     cudaFree(w.d_evecs); cudaFree(w.d_lu); cudaFree(w.d_nz); cudaFree(w.d_step);
-    cudaFree(w.d_V); cudaFree(w.d_lzw); cudaFree(w.d_lzs); cudaFree(w.d_lzst); cudaFree(w.d_lzbar);
+    cudaFree(w.d_V); cudaFree(w.d_lzw); cudaFree(w.d_lzs); cudaFree(w.d_lzst); cudaFree(w.d_lzbar); cudaFree(w.d_lzprof);
     if (w.graph_exec != nullptr) cudaGraphExecDestroy(w.graph_exec);
     if (w.lz_graph != nullptr) cudaGraphExecDestroy(w.lz_graph);
     w = EigWork{};
@@ -1135,6 +1174,10 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
         VPCA_TRY(cudaMalloc(&w.d_lzs, small_doubles * sizeof(double)));
         VPCA_TRY(cudaMalloc(&w.d_lzst, 4 * sizeof(int)));
         VPCA_TRY(cudaMalloc(&w.d_lzbar, sizeof(unsigned)));
+        if (const char* pf = getenv("VPCA_LZ_PROF"); pf != nullptr && atoi(pf) != 0) {
+            VPCA_TRY(cudaMalloc(&w.d_lzprof, 64 * 4 * sizeof(long long)));
+            VPCA_TRY(cudaMemset(w.d_lzprof, 0, 64 * 4 * sizeof(long long)));
+        }
     }
     double* alpha = w.d_lzs;
     double* beta = alpha + kLzCap;
@@ -1179,6 +1222,7 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
         a.cap = kLzCap;
         a.nsteps = kLzChunk;
         a.pre = pre;
+        a.prof = w.d_lzprof;
         void* params[] = {&a};
         nl += 1;
         return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lz_persist_kernel), dim3((unsigned)w.lz_blocks),

@@ -280,4 +280,18 @@ static cudaError_t encode_launch(const int64_t* d_off, int64_t base, const IdxT*
     return cudaGetLastError();
 }
 
+// Loads the encode kernels on the current device (see gram_preload_kernels: a first launch must never be the thing a host
+// thread blocks on while a peer barrier of the same process is spinning).
+cudaError_t encode_preload_kernels() {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaSuccess;
+#define VPCA_LOAD(k) if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k)
+    VPCA_LOAD((encode_i8_kernel<int32_t>)); VPCA_LOAD((encode_i8_kernel<uint16_t>));
+    VPCA_LOAD((encode_bf16_kernel<int32_t>)); VPCA_LOAD((encode_bf16_kernel<uint16_t>));
+    VPCA_LOAD((encode_e2m1_kernel<int32_t>)); VPCA_LOAD((encode_e2m1_kernel<uint16_t>));
+    VPCA_LOAD((bits_to_cells_kernel<8>)); VPCA_LOAD((bits_to_cells_kernel<4>)); VPCA_LOAD((bits_to_cells_kernel<16>));
+#undef VPCA_LOAD
+    return e;
+}
+
 }  // namespace vpca

@@ -1270,6 +1270,35 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     return le;
 }
 
+// Loads every kernel of this translation unit on the current device.  With CUDA's lazy module loading the FIRST launch of
+// a kernel loads it, and that load can wait for the device to go idle; a host thread that has just enqueued a spinning
+// peer_barrier_kernel for one context and then launches a not-yet-loaded kernel (for this or another context of the same
+// process) would wait for a barrier that can only complete once the thread has enqueued the other contexts' barriers --
+// a deadlock (observed on B200 with two contexts in one process: the 30 s barrier watchdog fired).  One process driving
+// several contexts (vpca_gram_set_peers_local, vpca_pool) therefore loads everything up front: cudaFuncGetAttributes
+// for all kernels, plus an empty launch of those that are enqueued behind a barrier.
+cudaError_t gram_preload_kernels(cudaStream_t stream) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaSuccess;
+#define VPCA_LOAD(k) if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k)
+    VPCA_LOAD((gram_kernel<1, 0>)); VPCA_LOAD((gram_kernel<1, 1>)); VPCA_LOAD((gram_kernel<1, 2>)); VPCA_LOAD((gram_kernel<1, 3>));
+    VPCA_LOAD((gram_kernel<2, 0>)); VPCA_LOAD((gram_kernel<2, 1>)); VPCA_LOAD((gram_kernel<2, 2>)); VPCA_LOAD((gram_kernel<2, 3>));
+    VPCA_LOAD(rebalance_kernel); VPCA_LOAD(symmetrize_kernel); VPCA_LOAD(add_i32_kernel); VPCA_LOAD(add_i32_peers_kernel);
+    VPCA_LOAD(add_i32_owner_kernel); VPCA_LOAD(gather_rows_kernel); VPCA_LOAD(push_rows_kernel); VPCA_LOAD(peer_barrier_kernel);
+#undef VPCA_LOAD
+    if (e != cudaSuccess) return e;
+    PeerPtrs pp{};
+    OwnEnds own{};
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(pp, 0, 0, 0);                 // npeers = 0: no thread touches a flag
+    push_rows_kernel<<<1, 32, 0, stream>>>(pp, nullptr, own, 0, 0, 0);        // own.e[0] = 0: no rows
+    gather_rows_kernel<<<1, 32, 0, stream>>>(pp, nullptr, own, 0, 0, 0);      // n = 0
+    add_i32_owner_kernel<<<1, 32, 0, stream>>>(pp, own, 0, nullptr, 0);       // n = 0
+    add_i32_peers_kernel<<<1, 32, 0, stream>>>(pp, 0, nullptr, 0);            // count = 0
+    add_i32_kernel<<<1, 32, 0, stream>>>(nullptr, nullptr, 0);
+    symmetrize_kernel<<<dim3(1, 1), dim3(32, 8), 0, stream>>>(nullptr, 0);    // n = 0: every access is masked
+    return cudaGetLastError();
+}
+
 cudaError_t gram_symmetrize(int32_t* d_S, int n, cudaStream_t stream) {
     const int nb = (n + 31) / 32;
     symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, stream>>>(d_S, n);

@@ -1305,6 +1305,9 @@ int vpca_gram_set_peers(vpca_ctx* ctx, const void* handles, int32_t world, int32
         ctx->plan.peer_S[d] = base;
         ctx->plan.peer_flags[d] = base + nn;
     }
+    CUDA_OK(ctx, gram_preload_kernels(ctx->stream));   // nothing is loaded lazily behind a spinning barrier
+    CUDA_OK(ctx, encode_preload_kernels());
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->plan.peers_ipc = true;
     ctx->plan.peer_rank = rank;
     ctx->plan.num_peers = world;
@@ -1341,6 +1344,14 @@ int vpca_gram_set_peers_local(vpca_ctx* const* ctxs, int32_t world) {
                 return fail(c, VPCA_ERR_NCCL, "cudaDeviceEnablePeerAccess(%d -> %d): %s", c->cfg.device, od, cudaGetErrorString(e));
             }
         }
+    }
+    // one host thread will enqueue barriers for several contexts: no kernel may be loaded lazily behind a spinning one
+    for (int r = 0; r < world; ++r) {
+        vpca_ctx* c = ctxs[r];
+        CUDA_OK(c, cudaSetDevice(c->cfg.device));
+        CUDA_OK(c, gram_preload_kernels(c->stream));
+        CUDA_OK(c, encode_preload_kernels());
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
     }
     for (int r = 0; r < world; ++r) {
         vpca_ctx* c = ctxs[r];
@@ -1440,6 +1451,17 @@ int vpca_debug_gram_profile(vpca_ctx* ctx, int64_t* out, int32_t max_ctas) {
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return gram_read_profile(ctx->plan, reinterpret_cast<long long*>(out), max_ctas);
+}
+
+int vpca_debug_lanczos_profile(vpca_ctx* ctx, int64_t* out, int32_t max_steps) {
+    if (ctx == nullptr || out == nullptr || max_steps <= 0) return fail(ctx, VPCA_ERR_BAD_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->eig_ready || ctx->eig.d_lzprof == nullptr) return 0;
+    CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
+    CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    const int steps = std::min(max_steps, 64);
+    CUDA_OK(ctx, cudaMemcpy(out, ctx->eig.d_lzprof, (size_t)steps * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return steps;
 }
 
 int vpca_debug_tiles(int32_t n_samples, int32_t cta_group, int32_t exact, int32_t* out, int32_t max_tiles) {

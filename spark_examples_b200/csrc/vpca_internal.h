@@ -72,6 +72,8 @@ cudaError_t gram_add_peers(GramPlan& plan, const int32_t* d_src, int64_t count, 
 cudaError_t gram_add_owners(GramPlan& plan, const int32_t* d_src, int n, cudaStream_t stream);
 cudaError_t gram_gather_rows(GramPlan& plan, int32_t* d_S, int n, cudaStream_t stream);
 cudaError_t gram_peer_barrier(GramPlan& plan, cudaStream_t stream);
+cudaError_t gram_preload_kernels(cudaStream_t stream);   // see gram_sm100.cu: lazy module loading vs spinning barriers
+cudaError_t encode_preload_kernels();
 void gram_plan_free(GramPlan& plan);
 int gram_debug_tiles(int n, int cta_group, int exact, int32_t* out, int max_tiles);
 int gram_debug_plan(const int32_t* tiles8, int num_tiles, int workers, int kbw, int32_t* out, int max_pieces);
@@ -150,6 +152,7 @@ struct EigWork {
     double* d_lzs = nullptr;    // alpha | beta | h | h2 | e2 | Y | theta2 | res | scal2 | part
     int* d_lzst = nullptr;      // {step, flag, ticket, step cap}
     unsigned* d_lzbar = nullptr;   // grid barrier counter of the persistent Lanczos kernel
+    long long* d_lzprof = nullptr; // VPCA_LZ_PROF=1: phase timestamps of block 0 (first 64 steps)
     int lz_blocks = 0;          // blocks of the persistent kernel (= SMs; 0: cooperative launch unavailable or VPCA_LZ_PERSIST=0)
     const int32_t* d_S = nullptr;   // the (symmetrised) int32 Gram the last center_gram() read
     cudaGraphExec_t lz_graph = nullptr;   // kLzChunk Lanczos steps

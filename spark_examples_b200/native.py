@@ -45,7 +45,7 @@ EXPORTED_SYMBOLS = (
     "vpca_accumulate_bits", "vpca_gram_set_peer_mode", "vpca_gram_gather", "vpca_accumulate_bed",
     "vpca_synchronize", "vpca_host_alloc", "vpca_host_free", "vpca_gram_set_peers_local", "vpca_owner_row_bands",
     "vpca_get_gram_band", "vpca_variant_count", "vpca_debug_rebalance",
-    "vpca_hash_keys", "vpca_join_rows", "vpca_join_fetch", "vpca_accumulate_joined",
+    "vpca_debug_lanczos_profile", "vpca_hash_keys", "vpca_join_rows", "vpca_join_fetch", "vpca_accumulate_joined",
     "vpca_pool_create", "vpca_pool_destroy", "vpca_pool_size", "vpca_pool_ctx", "vpca_pool_last_error", "vpca_pool_reset",
     "vpca_pool_accumulate_calls", "vpca_pool_accumulate_calls_u16", "vpca_pool_accumulate_bits", "vpca_pool_accumulate_bed",
     "vpca_pool_commit", "vpca_pool_abort", "vpca_pool_reduce_and_finalize", "vpca_pool_get_gram", "vpca_pool_compute_pca",
@@ -214,6 +214,8 @@ def load_library() -> ctypes.CDLL:
     L.vpca_debug_tiles.argtypes = [i32, i32, i32, vp, i32]
     L.vpca_debug_plan.restype = ctypes.c_int
     L.vpca_debug_plan.argtypes = [vp, i32, i32, i32, vp, i32]
+    L.vpca_debug_lanczos_profile.restype = ctypes.c_int
+    L.vpca_debug_lanczos_profile.argtypes = [vp, vp, i32]
     L.vpca_debug_rebalance.restype = ctypes.c_int
     L.vpca_debug_rebalance.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32]
     L.vpca_set_gram.restype = ctypes.c_int
@@ -374,6 +376,14 @@ class NativePca:
         idx = np.zeros(max(nnz, 1), dtype=np.int32)
         self._check(self._lib.vpca_join_fetch(self._h, _host_ptr(off), _host_ptr(idx)))
         return off, idx[:nnz]
+
+    def lanczosProfile(self) -> np.ndarray:
+        """(steps, 4) int64 ns timestamps of block 0 of the persistent Lanczos kernel (VPCA_LZ_PROF=1)."""
+        out = np.zeros((64, 4), dtype=np.int64)
+        cnt = self._lib.vpca_debug_lanczos_profile(self._h, _host_ptr(out), 64)
+        if cnt < 0:
+            self._check(cnt)
+        return out[:cnt]
 
     def accumulateJoined(self, partition_id: int):
         """Encode + Gram of the joined rows of the last joinRows, straight from device memory (vpca_accumulate_joined)."""

@@ -37,6 +37,16 @@ def main():
                     i = int(np.argmax(np.abs(Vt[:, c])));  Vt[:, c] *= (1 if Vt[i, c] > 0 else -1)
                 err = float((np.abs(vecs - Vt).max(0) / np.abs(Vt).max(0)).max())
                 times.sort()
+                if os.environ.get("VPCA_LZ_PROF") == "1":
+                    pr = nat.lanczosProfile()
+                    pr = pr[(pr[:, 0] > 0)]
+                    if len(pr) > 2:
+                        step = np.diff(pr[:, 0])
+                        print(json.dumps({"n": n, "lanczos_phase_us": {
+                            "step_total_med": round(float(np.median(step[step > 0])) / 1e3, 2),
+                            "A_matvec_and_share": round(float(np.median(pr[:, 1] - pr[:, 0])) / 1e3, 2),
+                            "barrier_1": round(float(np.median(pr[:, 2] - pr[:, 1])) / 1e3, 2),
+                            "B_gram_schmidt_pass": round(float(np.median(pr[:, 3] - pr[:, 2])) / 1e3, 2)}}), flush=True)
                 print(json.dumps({"n": n, "mode": mode, "k": k, "method": st["eig_method"], "iters": st["eig_iterations"],
                                   "device_ms": round(st["last_eig_ms"], 3), "eig_ms_med": round(times[len(times)//2], 3), "eig_ms_min": round(times[0], 3),
                                   "us_per_step": round(times[len(times)//2] * 1e3 / n, 2), "max_rel_err": err}), flush=True)
