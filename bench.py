@@ -299,6 +299,20 @@ def build_host_calls(torch, cells, n, nv, dev, chunk=50_000):
     return off_h, idx_h, nnz
 
 
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Pins this rank's threads to the CPUs NVML reports as local to its GPU, so that the pinned staging buffers of the
+    e2e legs are first-touched on the GPU's own NUMA node (8 ranks copying 4 GB each per step otherwise cross sockets)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return "rank threads bound to the %d CPUs local to GPU %d (NVML ideal affinity: %d..%d)" % (len(cpus), index, cpus[0], cpus[-1])
+    except Exception as exc:
+        return "default affinity (%s)" % repr(exc)[:80]
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -312,6 +326,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_note = bind_to_gpu_numa_node(local_rank)      # before any pinned host allocation: first touch on the GPU's node
     if world > 1:
         # keep stdout to the one JSON line: NCCL's version / debug banner goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -701,6 +716,10 @@ def run_b200(args):
                    "steps": e2e_steps, "ms_per_step": ems / e2e_steps, "wall_ms_per_step": 1e3 * wall / e2e_steps,
                    "includes": "pinned host CSR rows -> H2D -> encode -> Gram -> centering -> eigensolve -> PCs on host",
                    "nnz": nnz, "pcs_match_resident_path": bool(np.allclose(pcs[0], vecs, atol=1e-9)),
+                   # per rank: every rank copies its own shard from its own pinned buffers (this rank's figure; the
+                   # step time is the max over ranks)
+                   "h2d_gbs_per_rank": (s21["h2d_bytes"] - s20["h2d_bytes"]) / e2e_steps / (ems / e2e_steps * 1e-3) / 1e9,
+                   "host_numa": numa_note,
                    "with_uint16_indices": u16, "with_bitmap_rows": bitleg}
             nat2.close()
         except Exception as exc:      # an auxiliary leg must never cost the headline line

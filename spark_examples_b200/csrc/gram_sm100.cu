@@ -33,6 +33,9 @@
 #include <cstring>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -582,6 +585,41 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                     own_lo = a.peer[o];
                     own_hi = a.peer[min(o + 1, a.num_peers - 1)];
                 }
+                // Two cells per atomic: counts are non-negative and every sum stays below 2^31, so a 64-bit add of
+                // (cell c | cell c + 1 << 32) never carries between the halves.  Lane pairs trade one value per two
+                // rows (the even lane takes row 2 jj of both columns, the odd lane row 2 jj + 1), which halves the
+                // number of reds -- the L2 / NVLink atomic rate, not bytes, is what the flush runs against.  Needs an
+                // even row pitch (8-byte alignment of an even column); transposed chunks scatter and stay 32-bit.
+                if (!xpose && (a.n & 1) == 0) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const int row0 = rbase + 2 * jj, row1 = row0 + 1;
+                        int v0, v1;
+                        if constexpr (KIND == 0) { v0 = (int)r[2 * jj]; v1 = (int)r[2 * jj + 1]; }
+                        else { v0 = __float2int_rn(__uint_as_float(r[2 * jj])); v1 = __float2int_rn(__uint_as_float(r[2 * jj + 1])); }
+                        if (!(row0 < row_end && col < a.n && row0 >= col)) v0 = 0;
+                        if (!(row1 < row_end && col < a.n && row1 >= col)) v1 = 0;
+                        const int got = __shfl_xor_sync(0xffffffffu, (lane & 1) ? v0 : v1, 1);
+                        const int srow = (lane & 1) ? row1 : row0;
+                        const unsigned long long packed = (lane & 1)
+                            ? ((unsigned long long)(unsigned)got | ((unsigned long long)(unsigned)v1 << 32))
+                            : ((unsigned long long)(unsigned)v0 | ((unsigned long long)(unsigned)got << 32));
+                        if (packed != 0ull) {
+                            const size_t o = (size_t)srow * (size_t)a.n + (size_t)(col & ~1);
+                            if (a.num_peers == 0) {
+                                asm volatile("red.global.add.u64 [%0], %1;" ::"l"(a.S + o), "l"(packed) : "memory");
+                            } else if (a.peer_mode == 1) {
+                                int32_t* dst = (srow >= own_split ? own_hi : own_lo) + o;
+                                asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(dst), "l"(packed) : "memory");
+                            } else {
+                                for (int d = 0; d < a.num_peers; ++d)
+                                    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(a.peer[d] + o), "l"(packed)
+                                                 : "memory");
+                            }
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int row = rbase + j;
@@ -671,7 +709,7 @@ __global__ void rebalance_kernel(const long long* __restrict__ prof, double* __r
     double share = 0.0;
     if (active) {
         const double est = speed / red_sum;
-        share = 0.5 * share_old + 0.5 * est;
+        share = 0.3 * share_old + 0.7 * est;
         const double avg = 1.0 / workers;
         share = fmin(fmax(share, 0.5 * avg), max_share * avg);
     }
@@ -863,7 +901,33 @@ cudaError_t launch(const CUtensorMap& tmap, const CUtensorMap& tmap_half, const 
 
 }  // namespace
 
+// Process-wide memory of the speed-weighted splits the rebalancer converged to: the per-worker speeds it measures are a
+// property of the device (which SMs get how much L2 bandwidth), so a new context for the same (device, cohort size, tile
+// list, window) starts from the split the last one ended with instead of relearning it over its first launches.
+namespace {
+struct SplitKey {
+    int dev, n, tiles, kbw, workers, elem;
+    bool operator<(const SplitKey& o) const {
+        return std::tie(dev, n, tiles, kbw, workers, elem) < std::tie(o.dev, o.n, o.tiles, o.kbw, o.workers, o.elem);
+    }
+};
+std::mutex g_split_mu;
+std::map<SplitKey, std::vector<double>> g_splits;
+}  // namespace
+
+static void remember_split(GramPlan& plan) {
+    if (plan.d_cum == nullptr || plan.cum_workers <= 0 || !plan.adaptive) return;
+    std::vector<double> cum((size_t)plan.cum_workers + 1);
+    if (cudaMemcpy(cum.data(), plan.d_cum, cum.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    std::lock_guard<std::mutex> lk(g_split_mu);
+    g_splits[SplitKey{plan.cum_dev, plan.cum_for_n, plan.cum_tiles, plan.cum_kbw, plan.cum_workers, plan.cum_elem}] = std::move(cum);
+}
+
 void gram_plan_free(GramPlan& plan) {
+    remember_split(plan);
     if (plan.d_tiles) cudaFree(plan.d_tiles);
     plan.h_tiles.clear();
     if (plan.d_err) cudaFreeHost(plan.d_err);
@@ -1213,11 +1277,25 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         // cheap upper bound first (a worker with less than a tile's worth of work can touch few tiles), then the exact test
         std::vector<double> cum0;
         args.resident = (plan.num_tiles <= 4 * workers && initial_split(plan, workers, kbw, cum0)) ? 1 : 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
         args.kb_window = args.resident ? kbw : args.kb_total;
         // the device-side split (speed-weighted by rebalance_kernel from launch to launch) starts from the repaired
         // equal split; it is only meaningful for one (workers, tile list, window length)
         if (args.resident && (plan.d_cum == nullptr || plan.cum_workers != workers || plan.cum_tiles != plan.num_tiles ||
-                              plan.cum_kbw != kbw || plan.cum_for_n != n)) {
+                              plan.cum_kbw != kbw || plan.cum_for_n != n || plan.cum_elem != elem_bits)) {
+            remember_split(plan);
+            if (plan.adaptive) {   // a split learned earlier on this device for the same schedule, if it still fits TMEM
+                std::lock_guard<std::mutex> lk(g_split_mu);
+                auto it = g_splits.find(SplitKey{dev, n, plan.num_tiles, kbw, workers, elem_bits});
+                if (it != g_splits.end()) {
+                    std::vector<double> learned = it->second;
+                    const TileDesc* tiles = reinterpret_cast<const TileDesc*>(plan.h_tiles.data());
+                    if (repair_split(tiles, plan.num_tiles, workers, (long long)plan.total_weight * kbw, kbw, plan.tiles_col_limit,
+                                     learned.data()))
+                        cum0 = learned;
+                }
+            }
             if (plan.d_cum) cudaFree(plan.d_cum);
             plan.d_cum = nullptr;
             cudaError_t e = cudaMalloc(&plan.d_cum, (size_t)(workers + 2) * sizeof(double) + sizeof(int));
@@ -1231,6 +1309,8 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
             plan.cum_tiles = plan.num_tiles;
             plan.cum_kbw = kbw;
             plan.cum_for_n = n;
+            plan.cum_dev = dev;
+            plan.cum_elem = elem_bits;
         }
     }
     plan.last_resident = args.resident;

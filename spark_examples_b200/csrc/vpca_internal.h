@@ -38,7 +38,7 @@ struct GramPlan {
     int* d_win_done = nullptr;
     bool adaptive = true;     // VPCA_ADAPTIVE=0 keeps the stream-K split equal instead of speed-weighted
     double* d_cum = nullptr;  // cumulative worker shares (workers + 1 doubles) + update counter
-    int cum_workers = 0, cum_tiles = 0, cum_kbw = 0, cum_for_n = 0;   // what the split in d_cum was made for
+    int cum_workers = 0, cum_tiles = 0, cum_kbw = 0, cum_for_n = 0, cum_dev = 0, cum_elem = 0;   // what the split in d_cum was made for
     // fused multi-GPU reduction: Gram buffers / barrier flags of all ranks, peer-mapped through CUDA IPC
     int num_peers = 0, peer_rank = 0, peer_epoch = 0;
     int32_t* peer_S[16] = {};     // Gram of rank d as seen from this device: the address of row 0 (for a rank that stores
