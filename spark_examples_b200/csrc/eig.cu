@@ -644,7 +644,9 @@ __global__ void __launch_bounds__(512) backtransform_kernel(const double* __rest
 // reference-grade path.  Every reduction has a fixed order: the result is run-to-run deterministic.
 constexpr int kLzMinN = 512;         // below this the direct reduction is as fast
 constexpr int kLzForcedMinN = 96;    // VPCA_EIG=lanczos: smallest n the chunked loop supports (tests)
-constexpr int kLzChunk = 16;      // steps per graph replay (population structure converges the top pairs in <= 16)
+constexpr int kLzChunk = 16;      // steps per chunk (population structure converges the top pairs in <= 16)
+constexpr int kLzVerify = 8;      // steps of the deflated re-run (persistent form): its top Ritz value only has to climb ABOVE
+                                  // theta_k when a copy of a larger eigenvalue was missed, not to converge
 constexpr int kLzMaxIter = 320;   // give up (-> direct solver) beyond this
 constexpr int kLzCap = kLzMaxIter + 64;   // columns of V: main run, or k locked vectors + one verification chunk
 // st[0] = step j, st[1] = flag (0 run, 1 converged, 2 breakdown, 3 missed eigenvalue), st[2] = ticket, st[3] = step cap
@@ -887,6 +889,27 @@ __device__ __forceinline__ void lz_grid_barrier(unsigned* ctr, unsigned& target,
     __syncthreads();
 }
 
+// hrow[q] = sum over the block's rows of VT[i0 + r][q] * y[r] for q < jc: this block's share of V^T y.  Few columns
+// (the common case: jc <= 128): one warp per column, the rows spread over the lanes -- one L2 latency deep instead of R
+// dependent-latency loads per thread; many columns: one thread per column (coalesced across q).  Fixed orders either way.
+__device__ __forceinline__ void lz_share(const LzArgs& a, int i0, int R, int jc, const double* y, double* hrow) {
+    if (jc <= 128) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int q = wid; q < jc; q += kLzThreads / 32) {
+            double acc = 0.0;
+            for (int r = lane; r < R; r += 32) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
+            acc = warp_sum(acc);
+            if (lane == 0) hrow[q] = acc;
+        }
+    } else {
+        for (int q = threadIdx.x; q < jc; q += kLzThreads) {
+            double acc = 0.0;
+            for (int r = 0; r < R; ++r) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
+            hrow[q] = acc;
+        }
+    }
+}
+
 // One Gram-Schmidt pass on the rows of this block: hs = sum over blocks of hin (columns [0, jc)), y -= VT hs, and
 // (hout != nullptr) this block's share of VT^T y.  Returns hs[jc - 1] (alpha contribution) in every thread.
 __device__ __forceinline__ double lz_orth_pass(const LzArgs& a, int nblocks, int i0, int R, int jc, const double* hin,
@@ -932,13 +955,7 @@ __device__ __forceinline__ double lz_orth_pass(const LzArgs& a, int nblocks, int
         if (lane == 0) y[r] -= acc;
     }
     __syncthreads();
-    if (hout != nullptr) {
-        for (int q = threadIdx.x; q < jc; q += kLzThreads) {
-            double acc = 0.0;
-            for (int r = 0; r < R; ++r) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
-            hout[(size_t)blockIdx.x * a.cap + q] = acc;
-        }
-    }
+    if (hout != nullptr) lz_share(a, i0, R, jc, y, hout + (size_t)blockIdx.x * a.cap);
     return hs[jc - 1];
 }
 
@@ -972,11 +989,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         __syncthreads();
         for (int pass = 0; pass < 2; ++pass) {
             double* hp = pass == 0 ? hp1 : hp2;
-            for (int q = threadIdx.x; q < j; q += kLzThreads) {
-                double acc = 0.0;
-                for (int r = 0; r < R; ++r) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
-                hp[(size_t)blockIdx.x * a.cap + q] = acc;
-            }
+            lz_share(a, i0, R, j, y, hp + (size_t)blockIdx.x * a.cap);
             lz_grid_barrier(a.bar, target, nblocks);
             lz_orth_pass(a, nblocks, i0, R, j, hp, nullptr, hs, y, red2);
         }
@@ -1042,11 +1055,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
             a.VT[(size_t)(i0 + r) * a.cap + j] = wsm[i0 + r] * inv;
         }
         __syncthreads();
-        for (int q = threadIdx.x; q <= j; q += kLzThreads) {
-            double acc = 0.0;
-            for (int r = 0; r < R; ++r) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
-            hp1[(size_t)blockIdx.x * a.cap + q] = acc;
-        }
+        lz_share(a, i0, R, j + 1, y, hp1 + (size_t)blockIdx.x * a.cap);
         if (prof) a.prof[j * 4 + 1] = lz_timer();
         lz_grid_barrier(a.bar, target, nblocks);
         // ---- phase B / C: classical Gram-Schmidt, applied twice
@@ -1138,13 +1147,24 @@ void eig_free(EigWork& w) {
     w = EigWork{};
 }
 
-cudaError_t center_gram(EigWork& w, const int32_t* d_S, cudaStream_t stream) {
+cudaError_t center_gram(EigWork& w, const int32_t* d_S, cudaStream_t stream, bool materialise) {
     const int n = w.n;
     w.d_S = d_S;   // the persistent Lanczos applies the centring to vectors and reads the int32 Gram itself
     rowsum_kernel<<<(n + 7) / 8, 256, 0, stream>>>(d_S, n, w.d_rowsum);
     matrix_mean_kernel<<<1, 1024, 0, stream>>>(w.d_rowsum, n, w.d_scal, w.d_nz);
+    w.c_valid = false;
+    if (materialise) return center_matrix(w, stream);
+    return cudaGetLastError();
+}
+
+// C = S - rowMean - colMean + matrixMean as an FP64 matrix (VariantsPca.scala:216-221): what vpca_get_centered returns and
+// what the direct reduction and the five-kernel Lanczos read.  The persistent Lanczos never needs it (50 MB at N = 2504).
+cudaError_t center_matrix(EigWork& w, cudaStream_t stream) {
+    if (w.c_valid) return cudaSuccess;
+    const int n = w.n;
     const int bx = (n + 1023) / 1024 < 1 ? 1 : (n + 1023) / 1024;
-    center_kernel<<<dim3(bx, n), 256, 0, stream>>>(d_S, w.d_rowsum, w.d_scal, n, w.d_C);
+    center_kernel<<<dim3(bx, n), 256, 0, stream>>>(w.d_S, w.d_rowsum, w.d_scal, n, w.d_C);
+    w.c_valid = true;
     return cudaGetLastError();
 }
 
@@ -1229,6 +1249,7 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
                                            dim3(kLzThreads), params, persist_smem, stream);
     };
 
+    if (!persist) VPCA_TRY(center_matrix(w, stream));   // the five-kernel form reads the FP64 matrix
     if (!persist && w.lz_graph == nullptr) {
         cudaGraph_t graph = nullptr;
         VPCA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -1299,10 +1320,11 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     // Guard against a missed copy of a multiple eigenvalue (a single Krylov sequence sees one vector per eigenspace):
     // lock the k Ritz vectors as the first k basis columns and run one more chunk from a fresh start vector that is
     // orthogonal to them.  Its top Ritz value is a lower bound of the largest eigenvalue of the deflated operator.
+    const int vsteps = persist ? kLzVerify : kLzChunk;
     if (k + kLzChunk < n) {
         if (persist) {
             lz_lock_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w.d_V, n, kLzCap, w.d_evecs, k);
-            int vst[4] = {k, 0, 0, k + kLzChunk};
+            int vst[4] = {k, 0, 0, k + vsteps};
             VPCA_TRY(cudaMemcpyAsync(w.d_lzst, vst, sizeof(vst), cudaMemcpyHostToDevice, stream));
             lz_init_kernel<<<npart, 32, 0, stream>>>(w.d_lzw + (size_t)(k & 1) * n, n, 0xfaceULL, part);
             nl += 2;
@@ -1319,7 +1341,7 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
             nl += 5;
             VPCA_TRY(run_chunk(0));
         }
-        bisect_kernel<<<1, 256, 0, stream>>>(alpha + k, beta + k + 1, kLzChunk, e2, theta2, scal2);
+        bisect_kernel<<<1, 256, 0, stream>>>(alpha + k, beta + k + 1, vsteps, e2, theta2, scal2);
         lz_verify_kernel<<<1, 1, 0, stream>>>(w.d_evals, k, theta2, w.d_scal, w.d_lzst);
         nl += 2;
         VPCA_TRY(cudaMemcpyAsync(hst, w.d_lzst, sizeof(hst), cudaMemcpyDeviceToHost, stream));
@@ -1349,7 +1371,10 @@ cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches) 
         }
         w.last_method = 3;
     }
-    cudaError_t e = cudaMemsetAsync(w.d_v, 0, 2 * (size_t)n * sizeof(double), stream);
+    cudaError_t e = center_matrix(w, stream);   // the reduction works on (and overwrites) the FP64 matrix
+    if (e != cudaSuccess) return e;
+    w.c_valid = false;
+    e = cudaMemsetAsync(w.d_v, 0, 2 * (size_t)n * sizeof(double), stream);
     if (e != cudaSuccess) return e;
     cudaMemsetAsync(w.d_w, 0, (size_t)n * sizeof(double), stream);
     cudaMemsetAsync(w.d_p, 0, 2 * (size_t)n * sizeof(double), stream);

@@ -1150,7 +1150,7 @@ int64_t vpca_variant_count(vpca_ctx* ctx) {
     return ctx->total_variants;
 }
 
-static int run_center(vpca_ctx* ctx) {
+static int run_center(vpca_ctx* ctx, bool materialise) {
     if (!ctx->eig_ready) {
         cudaError_t e = eig_alloc(ctx->eig, ctx->n, std::max(ctx->num_pc, 16));
         if (e != cudaSuccess) {
@@ -1159,8 +1159,8 @@ static int run_center(vpca_ctx* ctx) {
         }
         ctx->eig_ready = true;
     }
-    CUDA_OK(ctx, center_gram(ctx->eig, ctx->d_S, ctx->stream));
-    ctx->c_launches += 3;
+    CUDA_OK(ctx, center_gram(ctx->eig, ctx->d_S, ctx->stream, materialise));
+    ctx->c_launches += materialise ? 3 : 2;
     return VPCA_OK;
 }
 
@@ -1176,7 +1176,7 @@ int vpca_compute_pca(vpca_ctx* ctx, int32_t k, double* vecs, double* evals, int3
                     "behind VariantsPca.scala:226 refuses more columns); the Gram itself has no such limit");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     CUDA_OK(ctx, cudaEventRecord(ctx->ev_e0, ctx->stream));
-    int rc = run_center(ctx);
+    int rc = run_center(ctx, false);   // row sums + mean; the solver materialises C only if it needs it
     if (rc != VPCA_OK) return rc;
     {   // VPCA_EIG=direct|lanczos|auto (default auto: Lanczos from 512 samples up, direct reduction as its fallback)
         const char* em = getenv("VPCA_EIG");
@@ -1207,7 +1207,7 @@ int vpca_get_centered(vpca_ctx* ctx, double* out) {
     if (!ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "call vpca_finalize_gram first");
     if (ctx->band_rows != ctx->n) return fail(ctx, VPCA_ERR_STATE, "this context stores a row band of the Gram");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
-    int rc = run_center(ctx);   // the eigensolve overwrites C, so recompute it
+    int rc = run_center(ctx, true);   // the eigensolve overwrites C, so recompute it
     if (rc != VPCA_OK) return rc;
     const size_t bytes = (size_t)ctx->n * ctx->n * sizeof(double);
     CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->eig.d_C, bytes, cudaMemcpyDeviceToHost, ctx->stream));

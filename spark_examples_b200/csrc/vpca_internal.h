@@ -153,6 +153,7 @@ struct EigWork {
     int* d_lzst = nullptr;      // {step, flag, ticket, step cap}
     unsigned* d_lzbar = nullptr;   // grid barrier counter of the persistent Lanczos kernel
     long long* d_lzprof = nullptr; // VPCA_LZ_PROF=1: phase timestamps of block 0 (first 64 steps)
+    bool c_valid = false;       // d_C holds the centred matrix of the last center_gram()
     int lz_blocks = 0;          // blocks of the persistent kernel (= SMs; 0: cooperative launch unavailable or VPCA_LZ_PERSIST=0)
     const int32_t* d_S = nullptr;   // the (symmetrised) int32 Gram the last center_gram() read
     cudaGraphExec_t lz_graph = nullptr;   // kLzChunk Lanczos steps
@@ -162,7 +163,9 @@ struct EigWork {
 };
 cudaError_t eig_alloc(EigWork& w, int n, int kmax);
 void eig_free(EigWork& w);
-cudaError_t center_gram(EigWork& w, const int32_t* d_S, cudaStream_t stream);
+// row sums + matrix mean always; the FP64 matrix C only when `materialise` (or later, on demand, through center_matrix)
+cudaError_t center_gram(EigWork& w, const int32_t* d_S, cudaStream_t stream, bool materialise);
+cudaError_t center_matrix(EigWork& w, cudaStream_t stream);
 cudaError_t eig_topk(EigWork& w, int k, cudaStream_t stream, int64_t* launches);
 
 // ---- synthetic generator (synth.cu) ----------------------------------------------------------------
