@@ -917,6 +917,10 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:      # the CPU arm gets every host core again, not only the ones local to the GPU (bind_to_gpu_numa_node)
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except (AttributeError, OSError):
+            pass
         v, info = cpu_similarity_sample(n, args.cpu_sample_variants, repeats=args.cpu_repeats)
         cpu = {"value": v, "unit": UNIT, "cores": info["threads"], "kind": "port",
                "sample": f"{info['variants']} variants x {n} samples (fixed sample; median {info['seconds']:.2f} s of "

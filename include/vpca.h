@@ -354,6 +354,9 @@ int vpca_accumulate_joined(vpca_ctx* ctx, int64_t partition_id);
 int vpca_debug_rebalance(const int32_t* tiles, int32_t num_tiles, int32_t workers, int32_t kb_window, int32_t col_limit,
                          double* cum, int32_t* out, int32_t max_pieces);
 int vpca_debug_tiles(int32_t n_samples, int32_t cta_group, int32_t exact, int32_t* out, int32_t max_tiles);
+/* Diagnostic: how many clusters of cluster_size CTAs of the Gram kernel (one CTA per SM) `device` can hold at once
+ * (cudaOccupancyMaxActiveClusters); negative vpca_status on error. */
+int vpca_debug_max_clusters(int32_t device, int32_t cluster_size);
 int vpca_debug_plan(const int32_t* tiles, int32_t num_tiles, int32_t workers, int32_t kb_window, int32_t* out, int32_t max_pieces);
 
 #ifdef __cplusplus

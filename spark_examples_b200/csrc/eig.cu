@@ -864,6 +864,7 @@ struct LzArgs {
     int* st;                // st[0] = next step, st[1] = flag (0 run, 2 breakdown), st[3] = step cap
     unsigned* bar;          // grid barrier counter, zero at launch
     int n, cap, nsteps, pre;
+    int rows_smem;          // leading rows of every block's share of S that are kept in shared memory for the whole launch
     long long* prof;        // optional (VPCA_LZ_PROF=1): block 0's globaltimer at the phase boundaries of each step, 4 per step
 };
 
@@ -971,12 +972,29 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
     double* wsm = lzsm;                                  // n: w_in
     double* hs = wsm + (((size_t)n + 1) & ~(size_t)1);   // cap
     double* y = hs + a.cap;                              // rows_per
-    double* segp = y + rows_per;                         // rows_per x nseg
+    double* segp = y + ((rows_per + 1) & ~1);            // rows_per x nseg (even offsets keep the int4 rows below 16-byte aligned)
+    // The block's rows of S never change: the first rows_smem of them live in shared memory for the whole launch (at
+    // N = 2504 all 17 rows, 170 KB), so a step's mat-vec costs no L2 traffic at all for them.
+    const int spitch = (n + 3) & ~3;
+    int32_t* ssm = reinterpret_cast<int32_t*>(segp + (((size_t)rows_per * nseg + 1) & ~(size_t)1));
+    const int rs = min(R, a.rows_smem);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double rc = (double)n;
     const double mm = a.scal[0];
     unsigned target = 0;
     if (a.st[1] != 0) return;   // every block reads the same flag (nothing in this launch changes it before this point)
+    if ((n & 3) == 0) {
+        for (int e = threadIdx.x; e < rs * (n >> 2); e += kLzThreads) {
+            const int r = e / (n >> 2), c4 = e - r * (n >> 2);
+            reinterpret_cast<int4*>(ssm + (size_t)r * spitch)[c4] = __ldg(reinterpret_cast<const int4*>(a.S + (size_t)(i0 + r) * n) + c4);
+        }
+    } else {
+        for (int e = threadIdx.x; e < rs * n; e += kLzThreads) {
+            const int r = e / n, c = e - r * n;
+            ssm[(size_t)r * spitch + c] = __ldg(a.S + (size_t)(i0 + r) * n + c);
+        }
+    }
+    __syncthreads();
     int j = a.st[0];
     const int jend = min(j + a.nsteps, a.st[3]);
     double* hp1 = a.hpart;
@@ -1024,7 +1042,8 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         const bool vec4 = (n & 3) == 0;
         for (int task = wid; task < R * nseg; task += kLzThreads / 32) {
             const int r = task / nseg, sg = task - r * nseg;
-            const int32_t* __restrict__ srow = a.S + (size_t)(i0 + r) * n;
+            const bool in_smem = r < rs;
+            const int32_t* srow = in_smem ? ssm + (size_t)r * spitch : a.S + (size_t)(i0 + r) * n;
             const int c0 = sg * kLzSeg, c1 = min(n, c0 + kLzSeg);
             double acc = 0.0;
             if (vec4) {
@@ -1033,7 +1052,8 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
                 for (int u = 0; u < kLzSeg / 128; ++u) {
                     const int c = c0 + (u * 32 + lane) * 4;
                     if (c < c1) {
-                        const int4 sv = __ldg(reinterpret_cast<const int4*>(srow + c));
+                        const int4 sv = in_smem ? *reinterpret_cast<const int4*>(srow + c)
+                                                : __ldg(reinterpret_cast<const int4*>(srow + c));
                         const double2 wa = *reinterpret_cast<const double2*>(wsm + c);
                         const double2 wb = *reinterpret_cast<const double2*>(wsm + c + 2);
                         p[u] = (double)sv.x * wa.x + (double)sv.y * wa.y + ((double)sv.z * wb.x + (double)sv.w * wb.y);
@@ -1041,7 +1061,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
                 }
                 acc = (p[0] + p[1]) + (p[2] + p[3]);
             } else {
-                for (int c = c0 + lane; c < c1; c += 32) acc += (double)__ldg(srow + c) * wsm[c];
+                for (int c = c0 + lane; c < c1; c += 32) acc += (double)(in_smem ? srow[c] : __ldg(srow + c)) * wsm[c];
             }
             acc = warp_sum(acc);
             if (lane == 0) segp[r * nseg + sg] = acc;
@@ -1216,8 +1236,18 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     const bool persist = w.lz_blocks > 0 && n <= kLzPersistMaxN;
     double* hpart = part + npart;
     const int rows_per = persist ? (n + w.lz_blocks - 1) / w.lz_blocks : 0;
-    const size_t persist_smem =
-        ((((size_t)n + 1) & ~(size_t)1) + kLzCap + rows_per + (size_t)rows_per * ((n + kLzSeg - 1) / kLzSeg)) * sizeof(double);
+    const size_t base_smem =
+        ((((size_t)n + 1) & ~(size_t)1) + kLzCap + (((size_t)rows_per + 1) & ~(size_t)1) +
+         ((((size_t)rows_per * ((n + kLzSeg - 1) / kLzSeg)) + 1) & ~(size_t)1)) * sizeof(double);
+    // what is left of the 227 KB a block may use (minus the kernel's ~9 KB of static shared memory) holds rows of S
+    int rows_smem = 0;
+    {
+        const size_t budget = 232448 - 9216 - 1024;
+        const size_t row_bytes = (size_t)((n + 3) & ~3) * sizeof(int32_t);
+        if (persist && base_smem < budget) rows_smem = (int)std::min<size_t>((size_t)rows_per, (budget - base_smem) / row_bytes);
+        if (const char* sr = getenv("VPCA_LZ_SROWS"); sr != nullptr) rows_smem = std::min(rows_smem, std::max(0, atoi(sr)));
+    }
+    const size_t persist_smem = base_smem + (size_t)rows_smem * ((n + 3) & ~3) * sizeof(int32_t);
     if (persist) VPCA_TRY(cudaFuncSetAttribute(lz_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
     auto run_chunk = [&](int pre) -> cudaError_t {
         if (!persist) {
@@ -1242,6 +1272,7 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
         a.cap = kLzCap;
         a.nsteps = kLzChunk;
         a.pre = pre;
+        a.rows_smem = rows_smem;
         a.prof = w.d_lzprof;
         void* params[] = {&a};
         nl += 1;

@@ -110,6 +110,7 @@ struct GramArgs {
     const double* cum; // cum[w] = fraction of every window's units owned by workers < w (cum[0] = 0, cum[W] = 1)
     int col_limit;     // TMEM columns the accumulators of one worker may take (512; mxf4: 480)
     int acc_stride;    // large-N schedule: TMEM columns between the two double-buffered accumulators (256; mxf4: 240)
+    int red64;         // epilogue packs two cells per 64-bit red (VPCA_RED64=0: one 32-bit red per cell)
     int tx_shift;      // TMA transaction bytes per stage = STAGE_BYTES >> tx_shift (1 for packed 4-bit sources: the
                        // mbarrier counts the 8 data bytes of every 16-byte shared-memory chunk, not the gap)
 };
@@ -590,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                 // rows (the even lane takes row 2 jj of both columns, the odd lane row 2 jj + 1), which halves the
                 // number of reds -- the L2 / NVLink atomic rate, not bytes, is what the flush runs against.  Needs an
                 // even row pitch (8-byte alignment of an even column); transposed chunks scatter and stay 32-bit.
-                if (!xpose && (a.n & 1) == 0) {
+                if (!xpose && a.red64 != 0 && (a.n & 1) == 0) {
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) {
                         const int row0 = rbase + 2 * jj, row1 = row0 + 1;
@@ -669,7 +670,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
 // stays exact whatever the split is (integer atomics); shares are clamped so that a worker never spans more than
 // the two tiles it has TMEM accumulators for.
 __global__ void rebalance_kernel(const long long* __restrict__ prof, double* __restrict__ cum, int workers, int cta_group,
-                                 double max_share, long long min_ns, int* __restrict__ gen, const TileDesc* __restrict__ tiles,
+                                 double gain, double max_share, long long min_ns, int* __restrict__ gen, const TileDesc* __restrict__ tiles,
                                  int num_tiles, int total_weight, int kbw, int col_limit) {
     __shared__ double sh[1024];
     __shared__ double cand[1025];
@@ -709,7 +710,7 @@ __global__ void rebalance_kernel(const long long* __restrict__ prof, double* __r
     double share = 0.0;
     if (active) {
         const double est = speed / red_sum;
-        share = 0.3 * share_old + 0.7 * est;
+        share = (1.0 - gain) * share_old + gain * est;
         const double avg = 1.0 / workers;
         share = fmin(fmax(share, 0.5 * avg), max_share * avg);
     }
@@ -1165,6 +1166,10 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         if (ad != nullptr) plan.adaptive = atoi(ad) != 0;
         const char* mx = getenv("VPCA_E2M1_MXF4");
         if (mx != nullptr) plan.e2m1_mxf4 = atoi(mx) != 0;
+        const char* r64 = getenv("VPCA_RED64");
+        if (r64 != nullptr) plan.red64 = atoi(r64) != 0;
+        const char* gain = getenv("VPCA_REBALANCE_GAIN");
+        if (gain != nullptr) plan.gain = std::min(1.0, std::max(0.1, atof(gain)));
         const char* ex = getenv("VPCA_EXACT_COVER");
         if (ex != nullptr) plan.exact_cover = atoi(ex) != 0;
     }
@@ -1265,6 +1270,7 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     args.elems_per_kb = elems_per_kb;
     args.acc_stride = mxf4 ? kUmmaNScaled : kUmmaN;
     args.col_limit = plan.tiles_col_limit;
+    args.red64 = plan.red64 ? 1 : 0;
     {
         int kbw = plan.kb_window;
         if (kbw <= 0 && panel > 0) kbw = args.kb_per_panel;   // one L2 window per panel
@@ -1342,7 +1348,7 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     if (adapt) {
         // shares move towards the measured speeds, at most 35 % above the mean; a split under which some worker's
         // accumulators would not fit TMEM is rejected by the kernel itself
-        rebalance_kernel<<<1, 1024, 0, stream>>>(plan.d_prof, plan.d_cum, workers, cgp, 1.35, 300000,
+        rebalance_kernel<<<1, 1024, 0, stream>>>(plan.d_prof, plan.d_cum, workers, cgp, plan.gain, 1.35, 300000,
                                                  reinterpret_cast<int*>(plan.d_cum + workers + 2), static_cast<const TileDesc*>(plan.d_tiles), plan.num_tiles,
                                                  plan.total_weight, args.kb_window, plan.tiles_col_limit);
         le = cudaGetLastError();
@@ -1377,6 +1383,36 @@ cudaError_t gram_preload_kernels(cudaStream_t stream) {
     add_i32_kernel<<<1, 32, 0, stream>>>(nullptr, nullptr, 0);
     symmetrize_kernel<<<dim3(1, 1), dim3(32, 8), 0, stream>>>(nullptr, 0);    // n = 0: every access is masked
     return cudaGetLastError();
+}
+
+// How many clusters of `cluster_size` CTAs of the int8 Gram kernel (1 CTA per SM: ~200 KB of shared memory each) the
+// current device can hold at once -- the GPC layout decides whether a 4- or 8-CTA cluster (TMA multicast of a shared
+// operand) could still use every SM.  Diagnostic only.
+int gram_debug_max_clusters(int cluster_size) {
+    using C = Cfg<2, 0>;
+    if (cudaFuncSetAttribute(gram_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) return -1;
+    if (cluster_size > 8 &&
+        cudaFuncSetAttribute(gram_kernel<2, 0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -1;
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(sms / cluster_size * cluster_size));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, gram_kernel<2, 0>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return clusters;
 }
 
 cudaError_t gram_symmetrize(int32_t* d_S, int n, cudaStream_t stream) {

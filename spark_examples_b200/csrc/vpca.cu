@@ -1464,6 +1464,14 @@ int vpca_debug_lanczos_profile(vpca_ctx* ctx, int64_t* out, int32_t max_steps) {
     return steps;
 }
 
+int vpca_debug_max_clusters(int32_t device, int32_t cluster_size) {
+    if (cluster_size < 1 || cluster_size > 16) return fail(nullptr, VPCA_ERR_BAD_ARG, "cluster_size must be in [1, 16]");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, VPCA_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    const int c = gram_debug_max_clusters(cluster_size);
+    if (c < 0) return fail(nullptr, VPCA_ERR_CUDA, "cudaOccupancyMaxActiveClusters failed for cluster size %d", cluster_size);
+    return c;
+}
+
 int vpca_debug_tiles(int32_t n_samples, int32_t cta_group, int32_t exact, int32_t* out, int32_t max_tiles) {
     if (n_samples < 2 || max_tiles < 0) return fail(nullptr, VPCA_ERR_BAD_ARG, "vpca_debug_tiles: bad argument");
     return gram_debug_tiles(n_samples, cta_group, exact, out, max_tiles);

@@ -36,6 +36,8 @@ struct GramPlan {
     int sync_lead = 0;        // VPCA_SYNC_LEAD: windows a worker may lead the slowest one by (0 = no pacing; measured
                               // on B200: pacing only slows every worker to the slowest one)
     int* d_win_done = nullptr;
+    bool red64 = true;        // VPCA_RED64=0: one 32-bit red per cell in the flush instead of two cells per 64-bit red
+    double gain = 0.7;        // VPCA_REBALANCE_GAIN: how far a launch moves the shares towards the measured speeds
     bool adaptive = true;     // VPCA_ADAPTIVE=0 keeps the stream-K split equal instead of speed-weighted
     double* d_cum = nullptr;  // cumulative worker shares (workers + 1 doubles) + update counter
     int cum_workers = 0, cum_tiles = 0, cum_kbw = 0, cum_for_n = 0, cum_dev = 0, cum_elem = 0;   // what the split in d_cum was made for
@@ -75,6 +77,7 @@ cudaError_t gram_peer_barrier(GramPlan& plan, cudaStream_t stream);
 cudaError_t gram_preload_kernels(cudaStream_t stream);   // see gram_sm100.cu: lazy module loading vs spinning barriers
 cudaError_t encode_preload_kernels();
 void gram_plan_free(GramPlan& plan);
+int gram_debug_max_clusters(int cluster_size);
 int gram_debug_tiles(int n, int cta_group, int exact, int32_t* out, int max_tiles);
 int gram_debug_plan(const int32_t* tiles8, int num_tiles, int workers, int kbw, int32_t* out, int max_pieces);
 int gram_debug_repair(const int32_t* tiles8, int num_tiles, int workers, int kbw, int col_limit, double* cum, int32_t* out,

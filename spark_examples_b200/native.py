@@ -45,7 +45,7 @@ EXPORTED_SYMBOLS = (
     "vpca_accumulate_bits", "vpca_gram_set_peer_mode", "vpca_gram_gather", "vpca_accumulate_bed",
     "vpca_synchronize", "vpca_host_alloc", "vpca_host_free", "vpca_gram_set_peers_local", "vpca_owner_row_bands",
     "vpca_get_gram_band", "vpca_variant_count", "vpca_debug_rebalance",
-    "vpca_debug_lanczos_profile", "vpca_hash_keys", "vpca_join_rows", "vpca_join_fetch", "vpca_accumulate_joined",
+    "vpca_debug_lanczos_profile", "vpca_debug_max_clusters", "vpca_hash_keys", "vpca_join_rows", "vpca_join_fetch", "vpca_accumulate_joined",
     "vpca_pool_create", "vpca_pool_destroy", "vpca_pool_size", "vpca_pool_ctx", "vpca_pool_last_error", "vpca_pool_reset",
     "vpca_pool_accumulate_calls", "vpca_pool_accumulate_calls_u16", "vpca_pool_accumulate_bits", "vpca_pool_accumulate_bed",
     "vpca_pool_commit", "vpca_pool_abort", "vpca_pool_reduce_and_finalize", "vpca_pool_get_gram", "vpca_pool_compute_pca",
@@ -587,6 +587,17 @@ def debugPlan(tiles: np.ndarray, workers: int, kb_window: int) -> np.ndarray:
     if cnt < 0:
         raise VpcaError(VPCA_ERR_STATE, L.vpca_last_error(None).decode("utf-8", "replace"))
     return out[:cnt]
+
+
+def maxClusters(device: int, cluster_size: int) -> int:
+    """Clusters of `cluster_size` Gram-kernel CTAs the device holds at once (vpca_debug_max_clusters)."""
+    L = load_library()
+    L.vpca_debug_max_clusters.restype = ctypes.c_int
+    L.vpca_debug_max_clusters.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    c = L.vpca_debug_max_clusters(int(device), int(cluster_size))
+    if c < 0:
+        raise VpcaError(c, L.vpca_last_error(None).decode("utf-8", "replace"))
+    return c
 
 
 def debugRebalance(tiles: np.ndarray, workers: int, kb_window: int, cum: np.ndarray, col_limit: int = 512):
