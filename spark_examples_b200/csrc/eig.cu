@@ -850,6 +850,7 @@ __global__ void lz_verify_kernel(const double* __restrict__ theta, int k, const 
 constexpr int kLzPersistMaxN = 16384;   // w_in staged in shared memory: 8 n bytes
 constexpr int kLzThreads = 1024;
 constexpr int kLzSeg = 512;             // columns per warp task of the matvec
+constexpr int kLzVtCols = 32;           // leading basis columns of the block's rows that are mirrored in shared memory
 
 struct LzArgs {
     const int32_t* S;
@@ -865,7 +866,7 @@ struct LzArgs {
     unsigned* bar;          // grid barrier counter, zero at launch
     int n, cap, nsteps, pre;
     int rows_smem;          // leading rows of every block's share of S that are kept in shared memory for the whole launch
-    long long* prof;        // optional (VPCA_LZ_PROF=1): block 0's globaltimer at the phase boundaries of each step, 4 per step
+    long long* prof;        // optional (VPCA_LZ_PROF=1): block 0's globaltimer at the phase boundaries of each step, 8 per step
 };
 
 __device__ __forceinline__ long long lz_timer() {
@@ -893,19 +894,25 @@ __device__ __forceinline__ void lz_grid_barrier(unsigned* ctr, unsigned& target,
 // hrow[q] = sum over the block's rows of VT[i0 + r][q] * y[r] for q < jc: this block's share of V^T y.  Few columns
 // (the common case: jc <= 128): one warp per column, the rows spread over the lanes -- one L2 latency deep instead of R
 // dependent-latency loads per thread; many columns: one thread per column (coalesced across q).  Fixed orders either way.
-__device__ __forceinline__ void lz_share(const LzArgs& a, int i0, int R, int jc, const double* y, double* hrow) {
+// Entry (row i0 + r, column q) of the basis: the first kLzVtCols columns of the block's rows are mirrored in shared memory
+// (a solve rarely needs more than 16 + 8 + k columns, so the Gram-Schmidt passes run without an L2 round trip).
+__device__ __forceinline__ double lz_vt(const LzArgs& a, const double* vts, int i0, int r, int q) {
+    return q < kLzVtCols ? vts[r * kLzVtCols + q] : a.VT[(size_t)(i0 + r) * a.cap + q];
+}
+
+__device__ __forceinline__ void lz_share(const LzArgs& a, const double* vts, int i0, int R, int jc, const double* y, double* hrow) {
     if (jc <= 128) {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         for (int q = wid; q < jc; q += kLzThreads / 32) {
             double acc = 0.0;
-            for (int r = lane; r < R; r += 32) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
+            for (int r = lane; r < R; r += 32) acc += lz_vt(a, vts, i0, r, q) * y[r];
             acc = warp_sum(acc);
             if (lane == 0) hrow[q] = acc;
         }
     } else {
         for (int q = threadIdx.x; q < jc; q += kLzThreads) {
             double acc = 0.0;
-            for (int r = 0; r < R; ++r) acc += a.VT[(size_t)(i0 + r) * a.cap + q] * y[r];
+            for (int r = 0; r < R; ++r) acc += lz_vt(a, vts, i0, r, q) * y[r];
             hrow[q] = acc;
         }
     }
@@ -914,7 +921,7 @@ __device__ __forceinline__ void lz_share(const LzArgs& a, int i0, int R, int jc,
 // One Gram-Schmidt pass on the rows of this block: hs = sum over blocks of hin (columns [0, jc)), y -= VT hs, and
 // (hout != nullptr) this block's share of VT^T y.  Returns hs[jc - 1] (alpha contribution) in every thread.
 __device__ __forceinline__ double lz_orth_pass(const LzArgs& a, int nblocks, int i0, int R, int jc, const double* hin,
-                                               double* hout, double* hs, double* y, double* red2) {
+                                               double* hout, double* hs, double* y, double* red2, const double* vts) {
     // hs[q] = sum over blocks of hin[b][q].  148 dependent-latency L2 loads per column if one thread walked the blocks;
     // instead warp w takes the blocks b = w, w + 32, ... (a handful of independent coalesced loads per lane, 32 columns
     // at a time) and the 32 partial sums of a column are added in a fixed order: deterministic and ~1 L2 latency deep.
@@ -949,14 +956,13 @@ __device__ __forceinline__ double lz_orth_pass(const LzArgs& a, int nblocks, int
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int r = wid; r < R; r += kLzThreads / 32) {
-        const double* __restrict__ vt = a.VT + (size_t)(i0 + r) * a.cap;
         double acc = 0.0;
-        for (int q = lane; q < jc; q += 32) acc += vt[q] * hs[q];
+        for (int q = lane; q < jc; q += 32) acc += lz_vt(a, vts, i0, r, q) * hs[q];
         acc = warp_sum(acc);
         if (lane == 0) y[r] -= acc;
     }
     __syncthreads();
-    if (hout != nullptr) lz_share(a, i0, R, jc, y, hout + (size_t)blockIdx.x * a.cap);
+    if (hout != nullptr) lz_share(a, vts, i0, R, jc, y, hout + (size_t)blockIdx.x * a.cap);
     return hs[jc - 1];
 }
 
@@ -976,7 +982,8 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
     // The block's rows of S never change: the first rows_smem of them live in shared memory for the whole launch (at
     // N = 2504 all 17 rows, 170 KB), so a step's mat-vec costs no L2 traffic at all for them.
     const int spitch = (n + 3) & ~3;
-    int32_t* ssm = reinterpret_cast<int32_t*>(segp + (((size_t)rows_per * nseg + 1) & ~(size_t)1));
+    double* vts = segp + (((size_t)rows_per * nseg + 1) & ~(size_t)1);   // rows_per x kLzVtCols
+    int32_t* ssm = reinterpret_cast<int32_t*>(vts + (size_t)rows_per * kLzVtCols);
     const int rs = min(R, a.rows_smem);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double rc = (double)n;
@@ -996,6 +1003,11 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
     }
     __syncthreads();
     int j = a.st[0];
+    for (int e = threadIdx.x; e < R * kLzVtCols; e += kLzThreads) {       // the columns earlier launches (or the lock) wrote
+        const int r = e / kLzVtCols, q = e - r * kLzVtCols;
+        vts[e] = q < j ? a.VT[(size_t)(i0 + r) * a.cap + q] : 0.0;
+    }
+    __syncthreads();
     const int jend = min(j + a.nsteps, a.st[3]);
     double* hp1 = a.hpart;
     double* hp2 = a.hpart + (size_t)nblocks * a.cap;
@@ -1007,9 +1019,9 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         __syncthreads();
         for (int pass = 0; pass < 2; ++pass) {
             double* hp = pass == 0 ? hp1 : hp2;
-            lz_share(a, i0, R, j, y, hp + (size_t)blockIdx.x * a.cap);
+            lz_share(a, vts, i0, R, j, y, hp + (size_t)blockIdx.x * a.cap);
             lz_grid_barrier(a.bar, target, nblocks);
-            lz_orth_pass(a, nblocks, i0, R, j, hp, nullptr, hs, y, red2);
+            lz_orth_pass(a, nblocks, i0, R, j, hp, nullptr, hs, y, red2, vts);
         }
         for (int r = threadIdx.x; r < R; r += kLzThreads) w_in[i0 + r] = y[r];
         lz_grid_barrier(a.bar, target, nblocks);
@@ -1020,8 +1032,8 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         const double* w_in = a.wbuf + (size_t)(j & 1) * n;
         double* w_out = a.wbuf + (size_t)((j + 1) & 1) * n;
         // ---- phase A: stage w_in, beta_j, y = C v_j on the own rows, share of V^T y
-        const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && j < 64;
-        if (prof) a.prof[j * 4 + 0] = lz_timer();
+        const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && j < 32;
+        if (prof) a.prof[j * 8 + 0] = lz_timer();
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         for (int c = threadIdx.x; c < n; c += kLzThreads) {
             const double wv = __ldcg(w_in + c);
@@ -1033,6 +1045,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         s0 = block_sum(s0, red);
         s1 = block_sum(s1, red);
         s2 = block_sum(s2, red);   // (block_sum syncs: wsm is complete)
+        if (prof) a.prof[j * 8 + 1] = lz_timer();
         const double nrm = sqrt(s0);
         if (!(nrm > 0.0) || !(nrm <= DBL_MAX)) {   // exact breakdown or non-finite: every block sees the same value
             broke = true;
@@ -1067,28 +1080,33 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
             if (lane == 0) segp[r * nseg + sg] = acc;
         }
         __syncthreads();
+        if (prof) a.prof[j * 8 + 2] = lz_timer();
         for (int r = threadIdx.x; r < R; r += kLzThreads) {
             double acc = 0.0;
             for (int sg = 0; sg < nseg; ++sg) acc += segp[r * nseg + sg];
             const double rbar = __ddiv_rn(a.rowsum[i0 + r], rc);
             y[r] = (acc - rbar * s1 - s2 + mm * s1) * inv;
-            a.VT[(size_t)(i0 + r) * a.cap + j] = wsm[i0 + r] * inv;
+            const double vj = wsm[i0 + r] * inv;
+            a.VT[(size_t)(i0 + r) * a.cap + j] = vj;
+            if (j < kLzVtCols) vts[r * kLzVtCols + j] = vj;
         }
         __syncthreads();
-        lz_share(a, i0, R, j + 1, y, hp1 + (size_t)blockIdx.x * a.cap);
-        if (prof) a.prof[j * 4 + 1] = lz_timer();
+        if (prof) a.prof[j * 8 + 3] = lz_timer();
+        lz_share(a, vts, i0, R, j + 1, y, hp1 + (size_t)blockIdx.x * a.cap);
+        if (prof) a.prof[j * 8 + 4] = lz_timer();
         lz_grid_barrier(a.bar, target, nblocks);
         // ---- phase B / C: classical Gram-Schmidt, applied twice
-        if (prof) a.prof[j * 4 + 2] = lz_timer();
-        const double a1 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp1, hp2, hs, y, red2);
-        if (prof) a.prof[j * 4 + 3] = lz_timer();
+        if (prof) a.prof[j * 8 + 5] = lz_timer();
+        const double a1 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp1, hp2, hs, y, red2, vts);
+        if (prof) a.prof[j * 8 + 6] = lz_timer();
         lz_grid_barrier(a.bar, target, nblocks);
-        const double a2 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp2, nullptr, hs, y, red2);
+        const double a2 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp2, nullptr, hs, y, red2, vts);
         for (int r = threadIdx.x; r < R; r += kLzThreads) w_out[i0 + r] = y[r];
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             a.alpha[j] = a1 + a2;
             a.beta[j] = nrm;
         }
+        if (prof) a.prof[j * 8 + 7] = lz_timer();
         lz_grid_barrier(a.bar, target, nblocks);
     }
     if (blockIdx.x == 0) {
@@ -1238,7 +1256,7 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     const int rows_per = persist ? (n + w.lz_blocks - 1) / w.lz_blocks : 0;
     const size_t base_smem =
         ((((size_t)n + 1) & ~(size_t)1) + kLzCap + (((size_t)rows_per + 1) & ~(size_t)1) +
-         ((((size_t)rows_per * ((n + kLzSeg - 1) / kLzSeg)) + 1) & ~(size_t)1)) * sizeof(double);
+         ((((size_t)rows_per * ((n + kLzSeg - 1) / kLzSeg)) + 1) & ~(size_t)1) + (size_t)rows_per * kLzVtCols) * sizeof(double);
     // what is left of the 227 KB a block may use (minus the kernel's ~9 KB of static shared memory) holds rows of S
     int rows_smem = 0;
     {

@@ -675,7 +675,7 @@ __global__ void rebalance_kernel(const long long* __restrict__ prof, double* __r
     __shared__ double sh[1024];
     __shared__ double cand[1025];
     __shared__ double red_sum, red_min;
-    __shared__ int reject;
+    __shared__ int reject, need_repair;
     const int w = threadIdx.x;
     const bool active = w < workers;
     double t = 0.0, share_old = 0.0;
@@ -685,7 +685,10 @@ __global__ void rebalance_kernel(const long long* __restrict__ prof, double* __r
         share_old = cum[w + 1] - cum[w];
     }
     sh[w] = active ? t : 1e30;
-    if (w == 0) reject = 0;
+    if (w == 0) {
+        reject = 0;
+        need_repair = 0;
+    }
     __syncthreads();
     if (w == 0) {
         double mn = 1e30, mx = 0.0;
@@ -732,7 +735,17 @@ __global__ void rebalance_kernel(const long long* __restrict__ prof, double* __r
     // accumulators or more than col_limit columns: e.g. the tail of one tile, a whole 13-unit tile and the head of a
     // third) stops at the edge of the tile that does not fit, and its neighbour starts there.  One thread walks the
     // workers in order; the tile cursor only moves forward, so the walk is O(workers + tiles).
-    if (w == 0 && !repair_split(tiles, num_tiles, workers, (long long)total_weight * kbw, kbw, col_limit, cand)) reject = 1;
+    // common case: every worker's pieces fit under the candidate as it is -- checked by all workers in parallel; only
+    // when one does not, one thread walks the workers in order and repairs (tens of microseconds: kept off the usual path)
+    if (active) {
+        const long long uw = (long long)total_weight * kbw;
+        const long long ub = (long long)((double)uw * cand[w]);
+        const long long ue = (w + 1 == workers) ? uw : (long long)((double)uw * cand[w + 1]);
+        int hint = 0;
+        if (feasible_end(tiles, num_tiles, ub, ue, kbw, col_limit, hint) < ue) atomicExch(&need_repair, 1);
+    }
+    __syncthreads();
+    if (need_repair && w == 0 && !repair_split(tiles, num_tiles, workers, (long long)total_weight * kbw, kbw, col_limit, cand)) reject = 1;
     __syncthreads();
     if (reject) return;
     if (w <= workers) cum[w] = cand[w];

@@ -1459,8 +1459,8 @@ int vpca_debug_lanczos_profile(vpca_ctx* ctx, int64_t* out, int32_t max_steps) {
     if (!ctx->eig_ready || ctx->eig.d_lzprof == nullptr) return 0;
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    const int steps = std::min(max_steps, 64);
-    CUDA_OK(ctx, cudaMemcpy(out, ctx->eig.d_lzprof, (size_t)steps * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    const int steps = std::min(max_steps, 32);
+    CUDA_OK(ctx, cudaMemcpy(out, ctx->eig.d_lzprof, (size_t)steps * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return steps;
 }
 

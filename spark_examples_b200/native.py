@@ -378,9 +378,9 @@ class NativePca:
         return off, idx[:nnz]
 
     def lanczosProfile(self) -> np.ndarray:
-        """(steps, 4) int64 ns timestamps of block 0 of the persistent Lanczos kernel (VPCA_LZ_PROF=1)."""
-        out = np.zeros((64, 4), dtype=np.int64)
-        cnt = self._lib.vpca_debug_lanczos_profile(self._h, _host_ptr(out), 64)
+        """(steps, 8) int64 ns timestamps of block 0 of the persistent Lanczos kernel (VPCA_LZ_PROF=1)."""
+        out = np.zeros((32, 8), dtype=np.int64)
+        cnt = self._lib.vpca_debug_lanczos_profile(self._h, _host_ptr(out), 32)
         if cnt < 0:
             self._check(cnt)
         return out[:cnt]

@@ -42,11 +42,12 @@ def main():
                     pr = pr[(pr[:, 0] > 0)]
                     if len(pr) > 2:
                         step = np.diff(pr[:, 0])
+                        med = lambda x: round(float(np.median(x)) / 1e3, 2)
                         print(json.dumps({"n": n, "lanczos_phase_us": {
-                            "step_total_med": round(float(np.median(step[step > 0])) / 1e3, 2),
-                            "A_matvec_and_share": round(float(np.median(pr[:, 1] - pr[:, 0])) / 1e3, 2),
-                            "barrier_1": round(float(np.median(pr[:, 2] - pr[:, 1])) / 1e3, 2),
-                            "B_gram_schmidt_pass": round(float(np.median(pr[:, 3] - pr[:, 2])) / 1e3, 2)}}), flush=True)
+                            "step_total": med(step[step > 0]), "stage_w_and_norms": med(pr[:, 1] - pr[:, 0]),
+                            "matvec": med(pr[:, 2] - pr[:, 1]), "y_and_basis_column": med(pr[:, 3] - pr[:, 2]),
+                            "share_of_VTy": med(pr[:, 4] - pr[:, 3]), "barrier_1": med(pr[:, 5] - pr[:, 4]),
+                            "gram_schmidt_pass_1": med(pr[:, 6] - pr[:, 5]), "barrier_2_and_pass_2": med(pr[:, 7] - pr[:, 6])}}), flush=True)
                 print(json.dumps({"n": n, "mode": mode, "k": k, "method": st["eig_method"], "iters": st["eig_iterations"],
                                   "device_ms": round(st["last_eig_ms"], 3), "eig_ms_med": round(times[len(times)//2], 3), "eig_ms_min": round(times[0], 3),
                                   "us_per_step": round(times[len(times)//2] * 1e3 / n, 2), "max_rel_err": err}), flush=True)
