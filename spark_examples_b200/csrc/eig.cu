@@ -869,6 +869,30 @@ struct LzArgs {
     long long* prof;        // optional (VPCA_LZ_PROF=1): block 0's globaltimer at the phase boundaries of each step, 8 per step
 };
 
+// int32 -> double without the (slow) I2F.F64: the bits 0x43300000'(x ^ 0x80000000) are the double 2^52 + 2^31 + x, and one
+// exact FP64 subtraction leaves x.
+__device__ __forceinline__ double lz_i2d(int x) {
+    return __hiloint2double(0x43300000, x ^ (int)0x80000000) - 4503601774854144.0;
+}
+
+// Three block-wide sums with one pair of barriers (fixed order: warp shuffles, then the warp totals in warp order).
+__device__ __forceinline__ void block_sum3(double& a0, double& a1, double& a2, double* red3) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    __syncthreads();   // protect red3 from the previous use
+    if (lane == 0) {
+        red3[wid] = a0;
+        red3[32 + wid] = a1;
+        red3[64 + wid] = a2;
+    }
+    __syncthreads();
+    a0 = warp_sum(lane < nw ? red3[lane] : 0.0);
+    a1 = warp_sum(lane < nw ? red3[32 + lane] : 0.0);
+    a2 = warp_sum(lane < nw ? red3[64 + lane] : 0.0);
+}
+
 __device__ __forceinline__ long long lz_timer() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -970,6 +994,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
     extern __shared__ __align__(16) double lzsm[];
     __shared__ double red[33];
     __shared__ double red2[(kLzThreads / 32) * 33];
+    __shared__ double red3[96];
     const int n = a.n, nblocks = (int)gridDim.x;
     const int rows_per = (n + nblocks - 1) / nblocks;
     const int i0 = min(n, (int)blockIdx.x * rows_per);
@@ -983,7 +1008,8 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
     // N = 2504 all 17 rows, 170 KB), so a step's mat-vec costs no L2 traffic at all for them.
     const int spitch = (n + 3) & ~3;
     double* vts = segp + (((size_t)rows_per * nseg + 1) & ~(size_t)1);   // rows_per x kLzVtCols
-    int32_t* ssm = reinterpret_cast<int32_t*>(vts + (size_t)rows_per * kLzVtCols);
+    double* rbar_sm = vts + (size_t)rows_per * kLzVtCols;                // n: rowSums / N (VariantsPca.scala:216), once per launch
+    int32_t* ssm = reinterpret_cast<int32_t*>(rbar_sm + (((size_t)n + 1) & ~(size_t)1));
     const int rs = min(R, a.rows_smem);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double rc = (double)n;
@@ -1001,6 +1027,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
             ssm[(size_t)r * spitch + c] = __ldg(a.S + (size_t)(i0 + r) * n + c);
         }
     }
+    for (int c = threadIdx.x; c < n; c += kLzThreads) rbar_sm[c] = __ddiv_rn(a.rowsum[c], rc);
     __syncthreads();
     int j = a.st[0];
     for (int e = threadIdx.x; e < R * kLzVtCols; e += kLzThreads) {       // the columns earlier launches (or the lock) wrote
@@ -1035,16 +1062,25 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && j < 32;
         if (prof) a.prof[j * 8 + 0] = lz_timer();
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        for (int c = threadIdx.x; c < n; c += kLzThreads) {
-            const double wv = __ldcg(w_in + c);
-            wsm[c] = wv;
-            s0 += wv * wv;
-            s1 += wv;
-            s2 += __ddiv_rn(a.rowsum[c], rc) * wv;
+        for (int c0 = threadIdx.x; c0 < n; c0 += 4 * kLzThreads) {
+            double wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {   // the (up to) four L2 loads of a thread are in flight together
+                const int c = c0 + u * kLzThreads;
+                wv[u] = c < n ? __ldcg(w_in + c) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * kLzThreads;
+                if (c < n) {
+                    wsm[c] = wv[u];
+                    s0 += wv[u] * wv[u];
+                    s1 += wv[u];
+                    s2 += rbar_sm[c] * wv[u];
+                }
+            }
         }
-        s0 = block_sum(s0, red);
-        s1 = block_sum(s1, red);
-        s2 = block_sum(s2, red);   // (block_sum syncs: wsm is complete)
+        block_sum3(s0, s1, s2, red3);   // (syncs: wsm is complete)
         if (prof) a.prof[j * 8 + 1] = lz_timer();
         const double nrm = sqrt(s0);
         if (!(nrm > 0.0) || !(nrm <= DBL_MAX)) {   // exact breakdown or non-finite: every block sees the same value
@@ -1069,7 +1105,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
                                                 : __ldg(reinterpret_cast<const int4*>(srow + c));
                         const double2 wa = *reinterpret_cast<const double2*>(wsm + c);
                         const double2 wb = *reinterpret_cast<const double2*>(wsm + c + 2);
-                        p[u] = (double)sv.x * wa.x + (double)sv.y * wa.y + ((double)sv.z * wb.x + (double)sv.w * wb.y);
+                        p[u] = lz_i2d(sv.x) * wa.x + lz_i2d(sv.y) * wa.y + (lz_i2d(sv.z) * wb.x + lz_i2d(sv.w) * wb.y);
                     }
                 }
                 acc = (p[0] + p[1]) + (p[2] + p[3]);
@@ -1084,8 +1120,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         for (int r = threadIdx.x; r < R; r += kLzThreads) {
             double acc = 0.0;
             for (int sg = 0; sg < nseg; ++sg) acc += segp[r * nseg + sg];
-            const double rbar = __ddiv_rn(a.rowsum[i0 + r], rc);
-            y[r] = (acc - rbar * s1 - s2 + mm * s1) * inv;
+            y[r] = (acc - rbar_sm[i0 + r] * s1 - s2 + mm * s1) * inv;
             const double vj = wsm[i0 + r] * inv;
             a.VT[(size_t)(i0 + r) * a.cap + j] = vj;
             if (j < kLzVtCols) vts[r * kLzVtCols + j] = vj;
@@ -1256,11 +1291,11 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     const int rows_per = persist ? (n + w.lz_blocks - 1) / w.lz_blocks : 0;
     const size_t base_smem =
         ((((size_t)n + 1) & ~(size_t)1) + kLzCap + (((size_t)rows_per + 1) & ~(size_t)1) +
-         ((((size_t)rows_per * ((n + kLzSeg - 1) / kLzSeg)) + 1) & ~(size_t)1) + (size_t)rows_per * kLzVtCols) * sizeof(double);
+         ((((size_t)rows_per * ((n + kLzSeg - 1) / kLzSeg)) + 1) & ~(size_t)1) + (size_t)rows_per * kLzVtCols + (((size_t)n + 1) & ~(size_t)1)) * sizeof(double);
     // what is left of the 227 KB a block may use (minus the kernel's ~9 KB of static shared memory) holds rows of S
     int rows_smem = 0;
     {
-        const size_t budget = 232448 - 9216 - 1024;
+        const size_t budget = 232448 - 10240 - 1024;
         const size_t row_bytes = (size_t)((n + 3) & ~3) * sizeof(int32_t);
         if (persist && base_smem < budget) rows_smem = (int)std::min<size_t>((size_t)rows_per, (budget - base_smem) / row_bytes);
         if (const char* sr = getenv("VPCA_LZ_SROWS"); sr != nullptr) rows_smem = std::min(rows_smem, std::max(0, atoi(sr)));
