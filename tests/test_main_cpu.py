@@ -36,6 +36,16 @@ class OracleBackedNative:
         self.log.append(("bed", pid, rows.shape[0]))
         self.staged[pid] = self.o.c_similarity(self.n, off, idx, 1)
 
+    def joinRows(self, mode, keys, offsets, idx, n_left=0, variant_set_count=2):
+        from spark_examples_b200.variants_common import JoinedSlice
+        self.joined = variants_pca.joined_rows_on_host(JoinedSlice(mode, keys, offsets, idx, n_left, variant_set_count))
+        self.log.append(("join", mode, len(keys)))
+        return len(self.joined.offsets) - 1, int(self.joined.offsets[-1])
+
+    def accumulateJoined(self, pid):
+        self.log.append(("joined", pid, len(self.joined.offsets) - 1))
+        self.staged[pid] = self.o.c_similarity(self.n, self.joined.offsets, self.joined.idx, 1)
+
     def commit(self, pid):
         self.S += self.staged.pop(pid)
 
@@ -108,6 +118,27 @@ def test_main_from_vcf(tmp_path, capsys, oracle, fake_native):
     assert [e[0] for e in fake_native[0].log] == ["calls"] * 3                   # 400 records in partitions of 150
     part = (tmp_path / "o-pca.tsv" / "part-00000").read_text().splitlines()      # saveAsTextFile layout (:241-245)
     assert len(part) == n and part[0].split("\t")[0] == "NA00000" and part[0].split("\t")[3] == "trial"
+
+
+def test_main_from_two_vcf_files_joins_on_the_variant_key(tmp_path, capsys, oracle, fake_native):
+    """Two variant sets (--vcf-path a,b): main takes the join branch of getCallsRdd (VariantsPca.scala:159); the rows of
+    both files and their key bytes go to the native join in ONE call, the joined rows are accumulated as one partition."""
+    d = _cohort(oracle, n=50, nv=300)
+    na = 30
+    gt = {0: "0/0", 1: "0/1", 2: "1/1"}
+    keep_a = np.arange(300) % 3 != 0                    # each file misses a third of the sites: the join keeps the overlap
+    keep_b = np.arange(300) % 3 != 1
+    def recs(rows, keep):
+        return [dict(chrom="chr2", pos=500 + j, ref="G", alt=["T"], gts=[gt[int(x)] for x in d[rows, j]]) for j in range(300) if keep[j]]
+    pa, pb = str(tmp_path / "setA.vcf"), str(tmp_path / "setB.vcf")
+    sa, sb = [f"A{i:03d}" for i in range(na)], [f"B{i:03d}" for i in range(50 - na)]
+    vcf.write_vcf(pa, sa, recs(slice(0, na), keep_a))
+    vcf.write_vcf(pb, sb, recs(slice(na, 50), keep_b))
+    out, lines = _run_main(["--vcf-path", f"{pa},{pb}"], capsys)
+    both = keep_a & keep_b
+    assert lines == _expected_lines(oracle, (d > 0)[:, both], sa + sb, ["setA"] * na + ["setB"] * (50 - na))
+    log = fake_native[0].log
+    assert [e[0] for e in log] == ["join", "joined"] and log[0][2] == int(keep_a.sum() + keep_b.sum())
 
 
 def test_main_from_bed(tmp_path, capsys, oracle, fake_native):
