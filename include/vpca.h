@@ -355,6 +355,9 @@ int vpca_accumulate_joined(vpca_ctx* ctx, int64_t partition_id);
 int vpca_debug_rebalance(const int32_t* tiles, int32_t num_tiles, int32_t workers, int32_t kb_window, int32_t col_limit,
                          double* cum, int32_t* out, int32_t max_pieces);
 int vpca_debug_tiles(int32_t n_samples, int32_t cta_group, int32_t exact, int32_t* out, int32_t max_tiles);
+/* Host-only: the tiles (int8 / bf16 rectangles, same 8-int records as vpca_debug_tiles) an owner-computes context that
+ * stores rows [row0, row0 + rows) of the Gram enumerates -- only products whose rows of S lie in the band. */
+int vpca_debug_band_tiles(int32_t n_samples, int32_t cta_group, int32_t row0, int32_t rows, int32_t* out, int32_t max_tiles);
 /* Diagnostic: how many clusters of cluster_size CTAs of the Gram kernel (one CTA per SM) `device` can hold at once
  * (cudaOccupancyMaxActiveClusters); negative vpca_status on error. */
 int vpca_debug_max_clusters(int32_t device, int32_t cluster_size);

@@ -110,6 +110,7 @@ struct GramArgs {
     const double* cum; // cum[w] = fraction of every window's units owned by workers < w (cum[0] = 0, cum[W] = 1)
     int col_limit;     // TMEM columns the accumulators of one worker may take (512; mxf4: 480)
     int acc_stride;    // large-N schedule: TMEM columns between the two double-buffered accumulators (256; mxf4: 240)
+    int row_limit;     // rows of S at or beyond this one are never written (n, or the end of an owner-computes band)
     int red64;         // epilogue packs two cells per 64-bit red (VPCA_RED64=0: one 32-bit red per cell)
     int tx_shift;      // TMA transaction bytes per stage = STAGE_BYTES >> tx_shift (1 for packed 4-bit sources: the
                        // mbarrier counts the 8 data bytes of every 16-byte shared-memory chunk, not the gap)
@@ -556,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
             const int colbase = ((CG == 2 && cta_rank != 0) ? s.rowA1 : s.rowA0) + q * 32;   // sample of the A row, lane 0
             const int col = colbase + (int)lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s.col;
-            const int row_end = min(a.n, s.rowB + s.n_eff);                 // B rows this tile owns
+            const int row_end = min(a.row_limit, s.rowB + s.n_eff);         // B rows this tile owns
             const int nchunks = filler ? 0 : (s.n_eff + 31) / 32;
 #pragma unroll 1
             for (int c = 0; c < nchunks; ++c) {
@@ -931,6 +932,7 @@ std::map<SplitKey, std::vector<double>> g_splits;
 
 static void remember_split(GramPlan& plan) {
     if (plan.d_cum == nullptr || plan.cum_workers <= 0 || !plan.adaptive) return;
+    if (plan.own_hi > plan.own_lo && plan.num_peers <= 1) return;   // a band's tile list is not the cohort's
     std::vector<double> cum((size_t)plan.cum_workers + 1);
     if (cudaMemcpy(cum.data(), plan.d_cum, cum.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
         cudaGetLastError();
@@ -972,7 +974,8 @@ int gram_read_profile(GramPlan& plan, long long* out, int max_ctas) {
 //     r = 4t the block (col 4t, row 4t + 2) is taken out of row 4t + 2 and computed in row 4t as its mirror image
 //     (col 4t + 2, row 4t), written transposed: both rows become even and every needed block is covered exactly once.
 //     Two-row tiles come first, one-row tiles last (a worker's accumulators must fit the 512 TMEM columns).
-static void make_tiles(int n, int cg, bool exact, int bn, std::vector<TileDesc>& out, int* num_full) {
+static void make_tiles(int n, int cg, bool exact, int bn, int row_lo, int row_hi, std::vector<TileDesc>& out, int* num_full) {
+    // [row_lo, row_hi): the rows of S to produce (the whole triangle, or the band an owner-computes context stores)
     out.clear();
     auto n_eff = [&](int row0, int want) { return std::min(want, ((n - row0) + 15) & ~15); };
     if (!exact) {
@@ -980,21 +983,22 @@ static void make_tiles(int n, int cg, bool exact, int bn, std::vector<TileDesc>&
         // bn = 240: 3 strips of 240 rows and 8 of 224 instead of 10 of 240 and one of 104).  Tiles of nearly equal
         // weight keep every worker of the resident schedule inside two tiles (two accumulators) under an even split.
         const int BM = 128 * cg;
-        const int nbn = (n + bn - 1) / bn, nbm = (n + BM - 1) / BM;
-        const int units = (n + 15) / 16;
-        std::vector<int> row0(nbn + 1, 0);
+        const int span = row_hi - row_lo;
+        const int nbn = (span + bn - 1) / bn, nbm = (n + BM - 1) / BM;
+        const int units = (span + 15) / 16;
+        std::vector<int> row0(nbn + 1, row_lo);
         for (int b = 0; b < nbn; ++b) row0[b + 1] = row0[b] + 16 * (units / nbn + (b < units % nbn ? 1 : 0));
         constexpr int kStrip = 8;
         for (int bb = 0; bb < nbn; bb += kStrip)
             for (int am = 0; am < nbm; ++am)
                 for (int b = bb; b < std::min(nbn, bb + kStrip); ++b) {
-                    const int max_row = std::min(n, row0[b + 1]) - 1;
+                    const int max_row = std::min(row_hi, row0[b + 1]) - 1;
                     if (am * BM > max_row) continue;   // wholly above the diagonal
                     TileDesc t{};
                     t.rowA0 = am * BM;
                     t.rowA1 = am * BM + 128;
                     t.rowB = row0[b];
-                    t.n_eff = row0[b + 1] - row0[b];
+                    t.n_eff = std::min(row0[b + 1], ((row_hi + 15) & ~15)) - row0[b];
                     t.acc_cols = bn;
                     out.push_back(t);
                 }
@@ -1065,10 +1069,10 @@ static void make_tiles(int n, int cg, bool exact, int bn, std::vector<TileDesc>&
     }
 }
 
-static cudaError_t build_tiles(GramPlan& plan, int n, bool exact, int BN, cudaStream_t stream) {
+static cudaError_t build_tiles(GramPlan& plan, int n, bool exact, int BN, int row_lo, int row_hi, cudaStream_t stream) {
     std::vector<TileDesc> tiles;
     int num_full = 0;
-    make_tiles(n, plan.cta_group, exact, BN, tiles, &num_full);
+    make_tiles(n, plan.cta_group, exact, BN, row_lo, row_hi, tiles, &num_full);
     if (plan.d_tiles) cudaFree(plan.d_tiles);
     plan.d_tiles = nullptr;
     cudaError_t e = cudaMalloc(&plan.d_tiles, tiles.size() * sizeof(TileDesc));
@@ -1084,6 +1088,8 @@ static cudaError_t build_tiles(GramPlan& plan, int n, bool exact, int BN, cudaSt
     plan.tiles_for_n = n;
     plan.tiles_for_cg = plan.cta_group;
     plan.tiles_for_bn = exact ? -1 : BN;
+    plan.tiles_row_lo = row_lo;
+    plan.tiles_row_hi = row_hi;
     plan.tiles_col_limit = (!exact && BN == kUmmaNScaled) ? (int)kSfCol : (int)kTmemCols;   // mxf4: scale columns at 480
     return e;
 }
@@ -1114,7 +1120,16 @@ static bool initial_split(const GramPlan& plan, int workers, int kbw, std::vecto
 int gram_debug_tiles(int n, int cta_group, int exact, int32_t* out, int max_tiles) {
     std::vector<TileDesc> tiles;
     int num_full = 0;
-    make_tiles(n, cta_group == 1 ? 1 : 2, exact != 0, exact ? kUmmaN : kUmmaNScaled, tiles, &num_full);
+    make_tiles(n, cta_group == 1 ? 1 : 2, exact != 0, exact ? kUmmaN : kUmmaNScaled, 0, n, tiles, &num_full);
+    const int cnt = std::min<int>((int)tiles.size(), max_tiles);
+    if (out != nullptr && cnt > 0) memcpy(out, tiles.data(), (size_t)cnt * sizeof(TileDesc));
+    return (int)tiles.size();
+}
+
+int gram_debug_band_tiles(int n, int cta_group, int row_lo, int row_hi, int32_t* out, int max_tiles) {
+    std::vector<TileDesc> tiles;
+    int num_full = 0;
+    make_tiles(n, cta_group == 1 ? 1 : 2, false, kUmmaN, row_lo, row_hi, tiles, &num_full);
     const int cnt = std::min<int>((int)tiles.size(), max_tiles);
     if (out != nullptr && cnt > 0) memcpy(out, tiles.data(), (size_t)cnt * sizeof(TileDesc));
     return (int)tiles.size();
@@ -1203,9 +1218,15 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     }
     const bool mxf4 = (elem_bits == 4 && plan.e2m1_mxf4);
     const int tile_bn = mxf4 ? kUmmaNScaled : kUmmaN;
-    const bool exact = !mxf4 && plan.exact_cover;   // kind::mxf4 keeps 256 x 240 rectangles (block scales in TMEM)
-    if (plan.tiles_for_n != n || plan.tiles_for_cg != plan.cta_group || plan.tiles_for_bn != (exact ? -1 : tile_bn)) {
-        cudaError_t e = build_tiles(plan, n, exact, tile_bn, stream);
+    // Owner-computes band (a context that stores only rows [own_lo, own_hi) of S and has no peers to flush to): only the
+    // tiles of those rows are enumerated -- the caller feeds every variant of the cohort to every band's context and no
+    // cell is produced twice anywhere (SURVEY 8e "shard output tiles across GPUs ... no reduction").
+    const bool banded = plan.own_hi > plan.own_lo && plan.num_peers <= 1;
+    const int row_lo = banded ? plan.own_lo : 0, row_hi = banded ? plan.own_hi : n;
+    const bool exact = !mxf4 && plan.exact_cover && !banded;   // kind::mxf4 keeps 256 x 240 rectangles (block scales in TMEM)
+    if (plan.tiles_for_n != n || plan.tiles_for_cg != plan.cta_group || plan.tiles_for_bn != (exact ? -1 : tile_bn) ||
+        plan.tiles_row_lo != row_lo || plan.tiles_row_hi != row_hi) {
+        cudaError_t e = build_tiles(plan, n, exact, tile_bn, row_lo, row_hi, stream);
         if (e != cudaSuccess) return e;
     }
     if (panel > 0) {
@@ -1266,7 +1287,8 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     }
 
     GramArgs args{};
-    args.S = d_S;
+    // a band is addressed through the virtual origin of the full matrix: row r lives at d_S + (r - own_lo) * n
+    args.S = banded ? d_S - (ptrdiff_t)plan.own_lo * n : d_S;
     args.num_peers = (plan.num_peers > 1 && d_S == plan.peer_base[plan.peer_rank]) ? plan.num_peers : 0;
     for (int d = 0; d < kMaxPeers; ++d) args.peer[d] = d < plan.num_peers ? plan.peer_S[d] : nullptr;
     args.peer_mode = plan.peer_mode;
@@ -1283,6 +1305,7 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
     args.elems_per_kb = elems_per_kb;
     args.acc_stride = mxf4 ? kUmmaNScaled : kUmmaN;
     args.col_limit = plan.tiles_col_limit;
+    args.row_limit = row_hi;
     args.red64 = plan.red64 ? 1 : 0;
     {
         int kbw = plan.kb_window;
@@ -1304,7 +1327,7 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         if (args.resident && (plan.d_cum == nullptr || plan.cum_workers != workers || plan.cum_tiles != plan.num_tiles ||
                               plan.cum_kbw != kbw || plan.cum_for_n != n || plan.cum_elem != elem_bits)) {
             remember_split(plan);
-            if (plan.adaptive) {   // a split learned earlier on this device for the same schedule, if it still fits TMEM
+            if (plan.adaptive && !banded) {   // a split learned earlier on this device for the same schedule, if it still fits TMEM
                 std::lock_guard<std::mutex> lk(g_split_mu);
                 auto it = g_splits.find(SplitKey{dev, n, plan.num_tiles, kbw, workers, elem_bits});
                 if (it != g_splits.end()) {

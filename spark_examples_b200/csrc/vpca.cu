@@ -163,6 +163,8 @@ void free_lane(vpca_ctx::Lane& L) {
 }
 
 void copy_peers(const GramPlan& from, GramPlan& to) {
+    to.own_lo = from.own_lo;
+    to.own_hi = from.own_hi;
     to.num_peers = from.num_peers;
     to.peer_rank = from.peer_rank;
     to.peer_mode = from.peer_mode;
@@ -352,7 +354,8 @@ struct CallScope {
             target = slot->d_S;
             ctx->inflight_variants += nv;   // reserved now, so that concurrent tasks cannot jointly pass the bound
         } else if (ctx->band_rows != ctx->n) {
-            return fail(ctx, VPCA_ERR_STATE, "a band-only Gram takes device-resident input in owner-rows mode");
+            return fail(ctx, VPCA_ERR_STATE, "a band-only Gram takes device-resident input (vpca_accumulate_panels / "
+                        "vpca_accumulate_dense with on_device = 1)");
         }
         return VPCA_OK;
     }
@@ -551,6 +554,10 @@ int vpca_create(const vpca_config* cfg, vpca_ctx** out) {
     }
     ctx->band_row0 = band ? cfg->gram_band_row0 : 0;
     ctx->band_rows = band ? cfg->gram_band_rows : ctx->n;
+    if (band) {   // without peers the Gram kernel computes exactly these rows (owner-computes), with peers it flushes to owners
+        ctx->plan.own_lo = ctx->band_row0;
+        ctx->plan.own_hi = ctx->band_row0 + ctx->band_rows;
+    }
     if (cfg->stream != nullptr) {
         ctx->stream = static_cast<cudaStream_t>(cfg->stream);
     } else {
@@ -1015,8 +1022,10 @@ int vpca_accumulate_panels(vpca_ctx* ctx, const void* d_x, int64_t nv, int64_t p
         return fail(ctx, VPCA_ERR_BAD_ARG, "vpca_accumulate_panels: panel_variants must be a positive multiple of 128");
     if (ctx->finalized) return fail(ctx, VPCA_ERR_STATE, "Gram already finalized; call vpca_reset first");
     if ((reinterpret_cast<uintptr_t>(d_x) & 31) != 0) return fail(ctx, VPCA_ERR_BAD_ARG, "panels must be 32-byte aligned");
-    if (ctx->band_rows != ctx->n && !(ctx->plan.num_peers > 1 && ctx->plan.peer_mode == 1))
-        return fail(ctx, VPCA_ERR_STATE, "a band-only Gram needs vpca_gram_set_peers_local + VPCA_PEER_OWNER_ROWS first");
+    // a band-only Gram either has peers in owner-rows mode (every context gets a variant shard and flushes each row to
+    // its owner) or no peers at all (owner-computes: every context gets ALL variants and produces only its own rows)
+    if (ctx->band_rows != ctx->n && ctx->plan.num_peers > 1 && ctx->plan.peer_mode != 1)
+        return fail(ctx, VPCA_ERR_STATE, "a band-only Gram with peers needs VPCA_PEER_OWNER_ROWS");
     CUDA_OK(ctx, cudaSetDevice(ctx->cfg.device));
     if (nv == 0) return VPCA_OK;
     int rc = check_overflow(ctx, nv);
@@ -1462,6 +1471,12 @@ int vpca_debug_lanczos_profile(vpca_ctx* ctx, int64_t* out, int32_t max_steps) {
     const int steps = std::min(max_steps, 32);
     CUDA_OK(ctx, cudaMemcpy(out, ctx->eig.d_lzprof, (size_t)steps * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return steps;
+}
+
+int vpca_debug_band_tiles(int32_t n_samples, int32_t cta_group, int32_t row0, int32_t rows, int32_t* out, int32_t max_tiles) {
+    if (n_samples < 2 || max_tiles < 0 || row0 < 0 || rows < 1 || row0 + rows > n_samples)
+        return fail(nullptr, VPCA_ERR_BAD_ARG, "vpca_debug_band_tiles: bad argument");
+    return gram_debug_band_tiles(n_samples, cta_group, row0, row0 + rows, out, max_tiles);
 }
 
 int vpca_debug_max_clusters(int32_t device, int32_t cluster_size) {

@@ -28,6 +28,9 @@ struct GramPlan {
     int tiles_for_n = -1;     // n_samples the tile list was built for
     int tiles_for_cg = 0;
     int tiles_for_bn = 0;
+    int tiles_row_lo = 0, tiles_row_hi = 0;   // rows of S the tile list covers
+    int own_lo = 0, own_hi = 0;   // band-only context: the rows of S it stores (own_hi == 0: the whole matrix); without
+                                  // peers the Gram kernel then computes exactly those rows (owner-computes)
     bool e2m1_mxf4 = true;    // packed e2m1 cells run through kind::mxf4 (2x MMA rate, unit block scales);
                               // VPCA_E2M1_MXF4=0 selects kind::f8f6f4 (TMA-expanded cells, int8 rate)
     int last_resident = 0;
@@ -79,6 +82,7 @@ cudaError_t gram_preload_kernels(cudaStream_t stream);   // see gram_sm100.cu: l
 cudaError_t encode_preload_kernels();
 void gram_plan_free(GramPlan& plan);
 int gram_debug_max_clusters(int cluster_size);
+int gram_debug_band_tiles(int n, int cta_group, int row_lo, int row_hi, int32_t* out, int max_tiles);
 int gram_debug_tiles(int n, int cta_group, int exact, int32_t* out, int max_tiles);
 int gram_debug_plan(const int32_t* tiles8, int num_tiles, int workers, int kbw, int32_t* out, int max_pieces);
 int gram_debug_repair(const int32_t* tiles8, int num_tiles, int workers, int kbw, int col_limit, double* cum, int32_t* out,

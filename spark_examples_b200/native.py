@@ -45,7 +45,7 @@ EXPORTED_SYMBOLS = (
     "vpca_accumulate_bits", "vpca_gram_set_peer_mode", "vpca_gram_gather", "vpca_accumulate_bed",
     "vpca_synchronize", "vpca_host_alloc", "vpca_host_free", "vpca_gram_set_peers_local", "vpca_owner_row_bands",
     "vpca_get_gram_band", "vpca_variant_count", "vpca_debug_rebalance",
-    "vpca_debug_lanczos_profile", "vpca_debug_max_clusters", "vpca_hash_keys", "vpca_join_rows", "vpca_join_fetch", "vpca_accumulate_joined",
+    "vpca_debug_lanczos_profile", "vpca_debug_max_clusters", "vpca_debug_band_tiles", "vpca_hash_keys", "vpca_join_rows", "vpca_join_fetch", "vpca_accumulate_joined",
     "vpca_pool_create", "vpca_pool_destroy", "vpca_pool_size", "vpca_pool_ctx", "vpca_pool_last_error", "vpca_pool_reset",
     "vpca_pool_accumulate_calls", "vpca_pool_accumulate_calls_u16", "vpca_pool_accumulate_bits", "vpca_pool_accumulate_bed",
     "vpca_pool_commit", "vpca_pool_abort", "vpca_pool_reduce_and_finalize", "vpca_pool_get_gram", "vpca_pool_compute_pca",
@@ -587,6 +587,19 @@ def debugPlan(tiles: np.ndarray, workers: int, kb_window: int) -> np.ndarray:
     if cnt < 0:
         raise VpcaError(VPCA_ERR_STATE, L.vpca_last_error(None).decode("utf-8", "replace"))
     return out[:cnt]
+
+
+def debugBandTiles(n_samples: int, cta_group: int, row0: int, rows: int) -> np.ndarray:
+    """Tiles of an owner-computes band context (vpca_debug_band_tiles), (tiles, 8) int32 like debugTiles."""
+    L = load_library()
+    L.vpca_debug_band_tiles.restype = ctypes.c_int
+    L.vpca_debug_band_tiles.argtypes = [ctypes.c_int32] * 4 + [ctypes.c_void_p, ctypes.c_int32]
+    cnt = L.vpca_debug_band_tiles(int(n_samples), int(cta_group), int(row0), int(rows), None, 0)
+    if cnt < 0:
+        raise VpcaError(cnt, L.vpca_last_error(None).decode("utf-8", "replace"))
+    out = np.zeros((cnt, 8), dtype=np.int32)
+    L.vpca_debug_band_tiles(int(n_samples), int(cta_group), int(row0), int(rows), _host_ptr(out), cnt)
+    return out
 
 
 def maxClusters(device: int, cluster_size: int) -> int:

@@ -180,6 +180,43 @@ def test_band_only_grams_hold_the_owner_rows(oracle):
             c.close()
 
 
+@pytest.mark.parametrize("dtype_name", ["i8", "e2m1"])
+def test_owner_computes_bands_need_no_reduction(oracle, dtype_name):
+    """The other biobank form (SURVEY 8e "shard output tiles across GPUs ... no reduction"): band-only contexts WITHOUT peers.
+    Every context is fed ALL variants and its Gram kernel enumerates only the tiles of the rows it stores, so nothing is
+    flushed to anybody and nothing is produced twice.  Two launches (two halves of the cohort) to cover accumulation."""
+    import torch
+    from spark_examples_b200 import native
+    world, n, nv, P = 4, 1400, 8192, 2048
+    dtype = {"i8": native.DTYPE_I8, "e2m1": native.DTYPE_E2M1}[dtype_name]
+    devs = _devices(world)
+    bands = native.ownerRowBands(n, world)
+    off, idx = oracle.c_synth_calls(SEED, n, 0, nv)
+    S_want = np.tril(oracle.c_similarity(n, off, idx, 2))
+    ctxs = []
+    try:
+        for r in range(world):
+            ctxs.append(native.NativePca(n, device=devs[r], dtype=dtype, max_multiplicity=1, gram_band=bands[r]))
+        for r, c in enumerate(ctxs):
+            with torch.cuda.device(devs[r]):
+                buf = torch.empty(c.panelBytes(nv // 2, P), dtype=torch.uint8, device=f"cuda:{devs[r]}")
+                for half in range(2):
+                    c.synthPanelsDevice(SEED, half * (nv // 2), nv // 2, 0, buf.data_ptr(), P)
+                    c.accumulatePanels(buf.data_ptr(), nv // 2, P)
+                    c.synchronize()
+            c.finalizeGram()
+            row0, rows = bands[r]
+            got = c.gramBand(row0, rows)
+            assert np.array_equal(np.tril(got, k=row0), S_want[row0:row0 + rows])
+            assert not np.triu(got, k=row0 + 1).any()            # nothing above the diagonal, nothing outside the band's tiles
+            assert c.stats()["variants_accumulated"] == nv
+    finally:
+        for c in ctxs:
+            c.synchronize()
+        for c in ctxs:
+            c.close()
+
+
 def test_band_only_biobank_scale_n(oracle):
     """N = 70 000 across 4 band-only contexts (the whole matrix would be 19.6 GB per context; the bands sum to that once):
     64-bit addressing of the virtual Gram origin, spot-checked rows against an fp32 matmul."""

@@ -153,3 +153,28 @@ def test_mxf4_accumulators_sit_below_the_scale_columns():
     assert (tiles[:, 6] == 240).all()
     pieces = native.debugPlan(tiles, 74, 104)
     assert pieces[:, 5].max() <= 480 and set(pieces[:, 4]) <= {0, 240}
+
+
+@pytest.mark.parametrize("n,world", [(2504, 8), (1092, 4), (100_000, 8), (777, 2), (10_000, 3)])
+def test_owner_computes_bands_tile_the_triangle_exactly_once(n, world):
+    """Biobank form without a reduction: context q stores rows [lo_q, hi_q) of S and enumerates only the
+    products of those rows.  Over all bands every cell with row >= col must be produced exactly once, no tile may reach
+    past its band (the band is all the memory the context has), and the bands carry equal shares of the MMA work."""
+    bands = native.ownerRowBands(n, world)
+    work = []
+    blocks = {}                                          # (row block of 16, col block of 128) -> times produced
+    for row0, rows in bands:
+        t = native.debugBandTiles(n, 2, row0, rows)
+        assert (t[:, 2] >= row0).all() and (t[:, 2] % 16 == 0).all() and (t[:, 3] % 16 == 0).all()
+        assert (np.minimum(t[:, 2] + t[:, 3], n) <= row0 + rows).all()          # never beyond the band (ragged last band: n)
+        work.append(int((256 * t[:, 3]).sum()))
+        for a0, a1, rb, ne, *_ in t:
+            assert a1 == a0 + 128
+            for r16 in range(rb // 16, (min(rb + ne, n) + 15) // 16):
+                for cb in (a0 // 128, a1 // 128):
+                    if cb * 128 <= min(r16 * 16 + 15, n - 1) and cb * 128 < n:      # the block touches row >= col
+                        blocks[(r16, cb)] = blocks.get((r16, cb), 0) + 1
+    assert set(blocks.values()) == {1}
+    need = sum(1 for r16 in range((n + 15) // 16) for cb in range((n + 127) // 128) if cb * 128 <= min(r16 * 16 + 15, n - 1))
+    assert len(blocks) == need
+    assert max(work) <= 1.25 * (sum(work) / world) + 256 * 256 * 4     # equal shares of the triangle, up to tile granularity

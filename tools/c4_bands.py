@@ -1,11 +1,13 @@
 #!/usr/bin/env python
-"""BASELINE configs[3] on all GPUs of one box: 100 000 samples x 500 000 variants, the 40 GB int32 Gram held ONCE across the
+"""BASELINE configs[3] on all GPUs of one box (two forms, --mode): 100 000 samples x 500 000 variants, the 40 GB int32 Gram held ONCE across the
 box as row bands (rank q allocates only the rows it owns: 5 GB at 8 GPUs), variants sharded over the GPUs
 (`for (c1 <- callset; c2 <- callset) matrix(c1, c2) += 1`, VariantsPca.scala:186-188, one partition matrix per GPU, with the
 sizing note of :176-177 answered by never materialising a second copy).  One process drives every GPU -- the process model of
 the reference's `local[*]` driver JVM (VariantsPca.scala:38-50) -- through vpca_gram_set_peers_local: every Gram kernel's
 epilogue adds its tile straight into the band of the rank that owns the row (red.relaxed.sys over NVLink), so there is no
-reduce step and no gather; the bands ARE the result.
+reduce step and no gather; the bands ARE the result.  `--mode owner-computes` is the other form SURVEY 8e names: every GPU
+holds ALL variants (50 GB of int8 genotypes) and its Gram kernel enumerates only the tiles of the rows it stores -- no peers,
+no traffic between the GPUs at all.
 
 Times the Gram launches with CUDA events per device (max over devices = the job), and checks without an N x N oracle:
   * diag(S) = carrier counts of the whole cohort, per band;
@@ -32,14 +34,20 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--panel", type=int, default=8192)
     ap.add_argument("--check-rows", type=int, default=3, help="sampled whole rows per band checked against fp32 matmul")
+    ap.add_argument("--mode", choices=["owner-flush", "owner-computes"], default="owner-flush",
+                    help="owner-flush: every GPU holds a variant shard and its kernel adds each tile into the band of the row's "
+                         "owner over NVLink; owner-computes: every GPU holds ALL variants and computes only its own band (no "
+                         "traffic between GPUs at all; 50 GB of genotypes per GPU)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     world = args.gpus or torch.cuda.device_count()
     n, P = args.samples, args.panel
-    per = (args.variants + world - 1) // world
+    computes = args.mode == "owner-computes"
+    per = args.variants if computes else (args.variants + world - 1) // world
     bands = native.ownerRowBands(n, world)
     ctxs, bufs, streams = [], [], []
-    report = {"config": f"{n} samples x {per * world} variants over {world} GPU(s), one process, band-only Grams",
+    total_v = per if computes else per * world
+    report = {"config": f"{n} samples x {total_v} variants over {world} GPU(s), one process, band-only Grams, {args.mode}",
               "n": n, "variants_per_gpu": per, "world": world, "panel": P,
               "band_rows": [b[1] for b in bands], "band_gb": [round(b[1] * n * 4 / 2 ** 30, 2) for b in bands]}
     try:
@@ -48,12 +56,13 @@ def main():
             s = torch.cuda.Stream(device=r)
             streams.append(s)
             ctxs.append(native.NativePca(n, device=r, stream=s.cuda_stream, max_multiplicity=1, gram_band=bands[r]))
-        native.setPeersLocal(ctxs, "owner_rows")
+        if not computes:
+            native.setPeersLocal(ctxs, "owner_rows")
         for r, c in enumerate(ctxs):
             torch.cuda.set_device(r)
             buf = torch.zeros(c.panelBytes(per, P), dtype=torch.uint8, device=f"cuda:{r}")
             bufs.append(buf)
-            c.synthPanelsDevice(20240901, r * per, per, 0, buf.data_ptr(), P)
+            c.synthPanelsDevice(20240901, 0 if computes else r * per, per, 0, buf.data_ptr(), P)
         for c in ctxs:
             c.synchronize()
         times = []
@@ -71,8 +80,9 @@ def main():
                     c.accumulatePanels(bufs[r].data_ptr(), per, P)
                     b.record()
                 ev.append((a, b))
-            for c in ctxs:
-                c.gatherGram()        # closing all-rank barrier on every stream: all remote adds have landed
+            if not computes:
+                for c in ctxs:
+                    c.gatherGram()    # closing all-rank barrier on every stream: all remote adds have landed
             for c in ctxs:
                 c.synchronize()
             per_dev = [a.elapsed_time(b) for a, b in ev]
@@ -80,17 +90,18 @@ def main():
                 times.append(per_dev)
         ms_dev = np.median(np.array(times), axis=0)
         ms = float(ms_dev.max())
-        ops = float(n) * (n + 1) * per * world
+        ops = float(n) * (n + 1) * total_v
         st = [c.stats() for c in ctxs]
         report.update({
             "gram_ms_per_device_median": [round(float(x), 2) for x in ms_dev],
             "gram_ms_job": round(ms, 2),
-            "cells_per_s": n * per * world / (ms * 1e-3),
+            "cells_per_s": n * total_v / (ms * 1e-3),
             "syrk_tops_per_gpu": round(ops / world / (ms * 1e-3) / 1e12, 1),
             "frac_of_nominal_int8_4500": round(ops / world / (ms * 1e-3) / 1e12 / 4500.0, 3),
             "resident_schedule": [s["gram_resident"] for s in st],
             # lower triangle of S, minus the part whose owner is the writer itself, crosses NVLink once per rank
-            "remote_red_bytes_per_gpu_upper_bound": int(n * (n + 1) // 2 * 4 * (world - 1) / world),
+            "remote_red_bytes_per_gpu_upper_bound": 0 if computes else int(n * (n + 1) // 2 * 4 * (world - 1) / world),
+            "genotype_bytes_per_gpu": int(n) * int(per),
         })
         # ---- checks: the rows of X on one device as fp32 (6.25 GB per 62 500-variant shard would be 25 GB as fp32, so
         #      the reference values are computed shard by shard from the int8 panels)
@@ -102,8 +113,9 @@ def main():
             sel = x[:, rows, :]                                            # slice or index list
             return sel.permute(1, 0, 2).reshape(sel.shape[1], npan * P).to(torch.float32)
 
+        shard_devs = [0] if computes else list(range(world))     # owner-computes: every device holds the whole cohort
         carriers = torch.zeros(n, dtype=torch.int64)
-        for r in range(world):
+        for r in shard_devs:
             x = bufs[r].view(torch.int8)[: npan * n * P].view(npan, n, P)
             carriers += (x != 0).sum(dim=(0, 2)).cpu()
         ok_diag, ok_rows, ok_blocks = True, True, True
@@ -115,10 +127,10 @@ def main():
             for row in pick:
                 ok_diag = ok_diag and int(got[row][row]) == int(carriers[row])
             want = {row: torch.zeros(row + 1, dtype=torch.float64) for row in pick}
-            for r in range(world):
+            for r in shard_devs:
                 torch.cuda.set_device(r)
                 xr = shard_rows(r, pick)                                   # (len(pick), K)
-                for r0 in range(0, n, 8192):
+                for r0 in range(0, max(pick) + 1, 8192):             # columns beyond the last sampled row are never needed
                     r1 = min(n, r0 + 8192)
                     blk = (xr @ shard_rows(r, slice(r0, r1)).t()).to(torch.float64).cpu()   # exact: counts < 2^24
                     for i, row in enumerate(pick):
@@ -132,7 +144,7 @@ def main():
             bc = int(rng.integers(0, max(1, br - 256)))
             gb = c.gramBand(br, min(256, row0 + rows - br))[:, bc:bc + 256].astype(np.int64)
             wb = torch.zeros(gb.shape, dtype=torch.float64)
-            for r in range(world):
+            for r in shard_devs:
                 torch.cuda.set_device(r)
                 wb += (shard_rows(r, slice(br, br + gb.shape[0])) @ shard_rows(r, slice(bc, bc + gb.shape[1])).t()).to(torch.float64).cpu()
             ok_blocks = ok_blocks and bool(np.array_equal(gb, wb.numpy().astype(np.int64)))
