@@ -624,6 +624,7 @@ int vpca_synchronize(vpca_ctx* ctx) {
 
 int vpca_reset(vpca_ctx* ctx) {
     if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
+    std::lock_guard<std::mutex> jl(ctx->join_mu);   // lock order everywhere: join_mu, then mu
     std::lock_guard<std::mutex> lk(ctx->mu);
     for (auto& L : ctx->lanes)
         if (L.busy) return fail(ctx, VPCA_ERR_STATE, "vpca_reset while an accumulate call is in flight");
@@ -635,6 +636,7 @@ int vpca_reset(vpca_ctx* ctx) {
     ctx->total_variants = 0;
     ctx->inflight_variants = 0;
     ctx->st.variants_accumulated = 0;
+    ctx->join.out_rows = -1;   // joined rows of an earlier analysis do not outlive a reset (join_mu is held, see above)
     return VPCA_OK;
 }
 
