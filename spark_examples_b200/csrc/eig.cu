@@ -1369,7 +1369,8 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
         // look at the residual after every replay up to 64 steps, then after every other one
         if (chunk > 4 && (chunk & 1) && chunk != max_chunks) continue;
         bisect_kernel<<<k, 256, 0, stream>>>(alpha, beta + 1, m, e2, w.d_evals, w.d_scal);
-        invit_kernel<true><<<1, 256, 8 * (size_t)m * sizeof(double), stream>>>(alpha, beta + 1, m, k, w.d_evals, w.d_scal,
+        // a tridiagonal matrix of a few dozen rows: one warp (its block-wide reductions then cost no barrier latency)
+        invit_kernel<true><<<1, m <= 128 ? 32 : 256, 8 * (size_t)m * sizeof(double), stream>>>(alpha, beta + 1, m, k, w.d_evals, w.d_scal,
                                                                                 w.d_lu, Y);
         lz_check_kernel<<<1, 32, 0, stream>>>(part, persist ? 1 : npart, Y, m, k, w.d_scal, w.d_lzst, res, tol);
         nl += 3;

@@ -103,6 +103,9 @@ def main():
             "remote_red_bytes_per_gpu_upper_bound": 0 if computes else int(n * (n + 1) // 2 * 4 * (world - 1) / world),
             "genotype_bytes_per_gpu": int(n) * int(per),
         })
+        print(json.dumps(dict(report, checks="pending")), flush=True)     # the timings survive a failure in the checks below
+        if args.out:
+            Path(args.out).write_text(json.dumps(dict(report, checks="pending")) + "\n")
         # ---- checks: the rows of X on one device as fp32 (6.25 GB per 62 500-variant shard would be 25 GB as fp32, so
         #      the reference values are computed shard by shard from the int8 panels)
         npan = (per + P - 1) // P
@@ -117,7 +120,8 @@ def main():
         carriers = torch.zeros(n, dtype=torch.int64)
         for r in shard_devs:
             x = bufs[r].view(torch.int8)[: npan * n * P].view(npan, n, P)
-            carriers += (x != 0).sum(dim=(0, 2)).cpu()
+            for p_ in range(npan):                                   # panel by panel: the int64 sum of a whole shard would not fit
+                carriers += (x[p_] != 0).sum(dim=1).cpu()
         ok_diag, ok_rows, ok_blocks = True, True, True
         rng = np.random.default_rng(7)
         for q, c in enumerate(ctxs):

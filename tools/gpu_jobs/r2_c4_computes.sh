@@ -5,5 +5,3 @@ mkdir -p gpurun_out
 nvidia-smi -L | head -8
 timeout 900 python tools/c4_bands.py --mode owner-computes --reps 3 --check-rows 2 --out gpurun_out/r2_c4_8gpu_owner_computes.json 2> gpurun_out/r2_c4_computes.err | cut -c1-1500
 echo "c4 owner-computes rc=${PIPESTATUS[0]}"; tail -3 gpurun_out/r2_c4_computes.err | cut -c1-300
-timeout 600 python tools/c4_bands.py --mode owner-flush --reps 3 --check-rows 1 --out gpurun_out/r2_c4_8gpu_owner_flush_b.json 2> gpurun_out/r2_c4_flush.err | cut -c1-1200
-echo "c4 owner-flush rc=${PIPESTATUS[0]}"
