@@ -378,9 +378,10 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const d
 // block b computes the (b+1)-th largest eigenvalue by multisection: every round each thread counts at one shift.
 __global__ void __launch_bounds__(256) bisect_kernel(const double* __restrict__ d, const double* __restrict__ e, int n,
                                                      double* __restrict__ e2, double* __restrict__ evals,
-                                                     double* __restrict__ scal) {
+                                                     double* __restrict__ scal, const int* __restrict__ gate = nullptr) {
     __shared__ int sel;
     __shared__ double sh_lo, sh_hi, sh_piv;
+    if (gate != nullptr && *gate == 0) return;   // speculatively enqueued behind a convergence test that failed
     const int tid = threadIdx.x, nt = blockDim.x;
     // Gershgorin interval, pivmin, squared off-diagonals (every block writes the same e2 values)
     double gl = DBL_MAX, gu = -DBL_MAX, emax = 0.0;
@@ -660,7 +661,9 @@ __device__ __forceinline__ double lz_uniform(unsigned long long i, unsigned long
 }
 
 // <<<ceil(n/32), 32>>>: start vector (not yet normalised) and the per-block partial sums of its squared norm
-__global__ void lz_init_kernel(double* __restrict__ w, int n, unsigned long long salt, double* __restrict__ part) {
+__global__ void lz_init_kernel(double* __restrict__ w, int n, unsigned long long salt, double* __restrict__ part,
+                               const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;
     const int i = blockIdx.x * 32 + threadIdx.x;
     double v = 0.0;
     if (i < n) {
@@ -820,13 +823,15 @@ __global__ void __launch_bounds__(256) lz_ritz_kernel(const double* __restrict__
                                           ((sm[4][lane] + sm[5][lane]) + (sm[6][lane] + sm[7][lane]));
 }
 
-__global__ void __launch_bounds__(512) lz_finish_kernel(double* __restrict__ Z, int n) {
+__global__ void __launch_bounds__(512) lz_finish_kernel(double* __restrict__ Z, int n, const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;
     normalise_and_orient(Z + (size_t)blockIdx.x * n, n);
 }
 
 // One thread: the deflated re-run found a Ritz value above theta_k -> an eigenvalue was missed.
 __global__ void lz_verify_kernel(const double* __restrict__ theta, int k, const double* __restrict__ theta2,
-                                 const double* __restrict__ scal, int* __restrict__ st) {
+                                 const double* __restrict__ scal, int* __restrict__ st, const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;
     const double tnorm = fmax(scal[2], DBL_MIN);
     if (st[1] == 2) return;
     st[1] = (theta2[0] > theta[k - 1] + 1e-9 * tnorm) ? 3 : 1;
@@ -865,6 +870,7 @@ struct LzArgs {
     int* st;                // st[0] = next step, st[1] = flag (0 run, 2 breakdown), st[3] = step cap
     unsigned* bar;          // grid barrier counter, zero at launch
     int n, cap, nsteps, pre;
+    const int* gate;        // != nullptr: the launch is speculative and returns at once while *gate == 0
     int rows_smem;          // leading rows of every block's share of S that are kept in shared memory for the whole launch
     long long* prof;        // optional (VPCA_LZ_PROF=1): block 0's globaltimer at the phase boundaries of each step, 8 per step
 };
@@ -1015,6 +1021,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
     const double rc = (double)n;
     const double mm = a.scal[0];
     unsigned target = 0;
+    if (a.gate != nullptr && *a.gate == 0) return;
     if (a.st[1] != 0) return;   // every block reads the same flag (nothing in this launch changes it before this point)
     if ((n & 3) == 0) {
         for (int e = threadIdx.x; e < rs * (n >> 2); e += kLzThreads) {
@@ -1162,9 +1169,25 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
     }
 }
 
+// One thread, right after lz_check_kernel: converged (st[1] == 1) arms the deflated re-run that is already enqueued behind it
+// (st[4] = 1, step window [k, k + vsteps), flag back to "running"); otherwise st[4] = 0 and every kernel of that re-run
+// returns at once, leaving the state of the main run untouched for the next chunk.
+__global__ void lz_gate_kernel(int* __restrict__ st, int k, int vsteps) {
+    if (st[1] == 1) {
+        st[4] = 1;
+        st[0] = k;
+        st[1] = 0;
+        st[3] = k + vsteps;
+    } else {
+        st[4] = 0;
+    }
+}
+
 // Z[:, c] = VT Y[:, c] for the row-major basis: one warp per (row, c).
 __global__ void __launch_bounds__(256) lz_ritz_rm_kernel(const double* __restrict__ VT, int n, int cap,
-                                                         const double* __restrict__ Y, int m, int k, double* __restrict__ Z) {
+                                                         const double* __restrict__ Y, int m, int k, double* __restrict__ Z,
+                                                         const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -1179,7 +1202,9 @@ __global__ void __launch_bounds__(256) lz_ritz_rm_kernel(const double* __restric
 }
 
 // VT[:, 0..k) = Z (the converged Ritz vectors become the locked leading columns of the deflated run)
-__global__ void lz_lock_kernel(double* __restrict__ VT, int n, int cap, const double* __restrict__ Z, int k) {
+__global__ void lz_lock_kernel(double* __restrict__ VT, int n, int cap, const double* __restrict__ Z, int k,
+                               const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     for (int c = 0; c < k; ++c) VT[(size_t)i * cap + c] = Z[(size_t)c * n + i];
@@ -1265,7 +1290,8 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
         VPCA_TRY(cudaMalloc(&w.d_V, (size_t)n * kLzCap * sizeof(double)));
         VPCA_TRY(cudaMalloc(&w.d_lzw, 2 * (size_t)n * sizeof(double)));
         VPCA_TRY(cudaMalloc(&w.d_lzs, small_doubles * sizeof(double)));
-        VPCA_TRY(cudaMalloc(&w.d_lzst, 4 * sizeof(int)));
+        VPCA_TRY(cudaMalloc(&w.d_lzst, 8 * sizeof(int)));
+        VPCA_TRY(cudaMemset(w.d_lzst, 0, 8 * sizeof(int)));
         VPCA_TRY(cudaMalloc(&w.d_lzbar, sizeof(unsigned)));
         if (const char* pf = getenv("VPCA_LZ_PROF"); pf != nullptr && atoi(pf) != 0) {
             VPCA_TRY(cudaMalloc(&w.d_lzprof, 64 * 4 * sizeof(long long)));
@@ -1302,7 +1328,7 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     }
     const size_t persist_smem = base_smem + (size_t)rows_smem * ((n + 3) & ~3) * sizeof(int32_t);
     if (persist) VPCA_TRY(cudaFuncSetAttribute(lz_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
-    auto run_chunk = [&](int pre) -> cudaError_t {
+    auto run_chunk = [&](int pre, const int* gate = nullptr) -> cudaError_t {
         if (!persist) {
             nl += 5 * kLzChunk;
             return cudaGraphLaunch(w.lz_graph, stream);
@@ -1325,6 +1351,7 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
         a.cap = kLzCap;
         a.nsteps = kLzChunk;
         a.pre = pre;
+        a.gate = gate;
         a.rows_smem = rows_smem;
         a.prof = w.d_lzprof;
         void* params[] = {&a};
@@ -1354,8 +1381,11 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     const double tol = 1e-12;
     int max_iter = kLzMaxIter;
     if (const char* mi = getenv("VPCA_EIG_MAXIT")) max_iter = std::max(kLzChunk, std::min(kLzMaxIter, atoi(mi)));
-    int hst[4] = {0, 0, 0, max_iter};
+    int hst[8] = {0, 0, 0, max_iter, 0, 0, 0, 0};
     double hres[2] = {0.0, 0.0};
+    const int vsteps = persist ? kLzVerify : kLzChunk;
+    const char* spe = getenv("VPCA_LZ_SPECULATE");
+    const bool speculate = persist && k + kLzChunk < n && !(spe != nullptr && atoi(spe) == 0);
     VPCA_TRY(cudaMemcpyAsync(w.d_lzst, hst, sizeof(hst), cudaMemcpyHostToDevice, stream));
     lz_init_kernel<<<npart, 32, 0, stream>>>(w.d_lzw, n, 0x5eedULL, part);
     nl += 1;
@@ -1374,9 +1404,33 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
                                                                                 w.d_lu, Y);
         lz_check_kernel<<<1, 32, 0, stream>>>(part, persist ? 1 : npart, Y, m, k, w.d_scal, w.d_lzst, res, tol);
         nl += 3;
+        const bool spec = speculate && chunk == 1;
+        if (spec) {
+            // The usual case converges at the first test.  Everything that follows a successful test -- Ritz vectors,
+            // locking them, the deflated re-run and its verdict -- is enqueued NOW behind a one-thread gate, so the host
+            // synchronises once per solve; had the test failed, every gated kernel returns at once and the main run
+            // goes on below with its state untouched.
+            const int* gate = w.d_lzst + 4;
+            lz_gate_kernel<<<1, 1, 0, stream>>>(w.d_lzst, k, vsteps);
+            lz_ritz_rm_kernel<<<(n + 7) / 8, 256, 0, stream>>>(w.d_V, n, kLzCap, Y, m, k, w.d_evecs, gate);
+            lz_finish_kernel<<<k, 512, 0, stream>>>(w.d_evecs, n, gate);
+            lz_lock_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w.d_V, n, kLzCap, w.d_evecs, k, gate);
+            lz_init_kernel<<<npart, 32, 0, stream>>>(w.d_lzw + (size_t)(k & 1) * n, n, 0xfaceULL, part, gate);
+            VPCA_TRY(run_chunk(1, gate));
+            bisect_kernel<<<1, 256, 0, stream>>>(alpha + k, beta + k + 1, vsteps, e2, theta2, scal2, gate);
+            lz_verify_kernel<<<1, 1, 0, stream>>>(w.d_evals, k, theta2, w.d_scal, w.d_lzst, gate);
+            nl += 7;
+        }
         VPCA_TRY(cudaMemcpyAsync(hst, w.d_lzst, sizeof(hst), cudaMemcpyDeviceToHost, stream));
         VPCA_TRY(cudaMemcpyAsync(hres, res, sizeof(hres), cudaMemcpyDeviceToHost, stream));
         VPCA_TRY(cudaStreamSynchronize(stream));
+        if (spec && hst[4] == 1) {   // converged at the first test; the re-run has delivered its verdict in st[1]
+            w.last_iters = m;
+            if (launches) *launches += nl;
+            if (hst[1] != 1) return cudaGetLastError();   // missed eigenvalue (3) or breakdown (2): the caller falls back
+            *used = true;
+            return cudaGetLastError();
+        }
         if (hst[1] == 1) {
             converged = true;
             break;
@@ -1405,7 +1459,6 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     // Guard against a missed copy of a multiple eigenvalue (a single Krylov sequence sees one vector per eigenspace):
     // lock the k Ritz vectors as the first k basis columns and run one more chunk from a fresh start vector that is
     // orthogonal to them.  Its top Ritz value is a lower bound of the largest eigenvalue of the deflated operator.
-    const int vsteps = persist ? kLzVerify : kLzChunk;
     if (k + kLzChunk < n) {
         if (persist) {
             lz_lock_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w.d_V, n, kLzCap, w.d_evecs, k);
