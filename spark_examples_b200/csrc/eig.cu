@@ -1096,31 +1096,58 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         }
         const double inv = 1.0 / nrm;
         const bool vec4 = (n & 3) == 0;
-        for (int task = wid; task < R * nseg; task += kLzThreads / 32) {
-            const int r = task / nseg, sg = task - r * nseg;
-            const bool in_smem = r < rs;
-            const int32_t* srow = in_smem ? ssm + (size_t)r * spitch : a.S + (size_t)(i0 + r) * n;
-            const int c0 = sg * kLzSeg, c1 = min(n, c0 + kLzSeg);
-            double acc = 0.0;
-            if (vec4) {
-                double p[4] = {0.0, 0.0, 0.0, 0.0};
+        if (vec4) {
+            // A warp keeps ONE 512-column segment of w in registers (16 doubles per lane) and walks rows of S under it:
+            // per element only the 4 bytes of S are read again (shared memory or L2), not the 8 bytes of w as well.
+            // Column workers cw = 0 .. CW-1 own the segments cw, cw + CW, ...; G = 32 / CW row groups share the rows.
+            const int CW = min(nseg, kLzThreads / 32), G = (kLzThreads / 32) / CW;
+            const int cw = wid % CW, g = wid / CW;
+            if (g < G) {
+                for (int sg = cw; sg < nseg; sg += CW) {
+                    const int c0 = sg * kLzSeg, c1 = min(n, c0 + kLzSeg);
+                    double2 wa[kLzSeg / 128], wb[kLzSeg / 128];
 #pragma unroll
-                for (int u = 0; u < kLzSeg / 128; ++u) {
-                    const int c = c0 + (u * 32 + lane) * 4;
-                    if (c < c1) {
-                        const int4 sv = in_smem ? *reinterpret_cast<const int4*>(srow + c)
-                                                : __ldg(reinterpret_cast<const int4*>(srow + c));
-                        const double2 wa = *reinterpret_cast<const double2*>(wsm + c);
-                        const double2 wb = *reinterpret_cast<const double2*>(wsm + c + 2);
-                        p[u] = lz_i2d(sv.x) * wa.x + lz_i2d(sv.y) * wa.y + (lz_i2d(sv.z) * wb.x + lz_i2d(sv.w) * wb.y);
+                    for (int u = 0; u < kLzSeg / 128; ++u) {
+                        const int c = c0 + (u * 32 + lane) * 4;
+                        if (c < c1) {
+                            wa[u] = *reinterpret_cast<const double2*>(wsm + c);
+                            wb[u] = *reinterpret_cast<const double2*>(wsm + c + 2);
+                        } else {
+                            wa[u] = make_double2(0.0, 0.0);
+                            wb[u] = make_double2(0.0, 0.0);
+                        }
+                    }
+                    for (int r = g; r < R; r += G) {
+                        const bool in_smem = r < rs;
+                        const int32_t* srow = in_smem ? ssm + (size_t)r * spitch : a.S + (size_t)(i0 + r) * n;
+                        double p[kLzSeg / 128];
+#pragma unroll
+                        for (int u = 0; u < kLzSeg / 128; ++u) {
+                            const int c = c0 + (u * 32 + lane) * 4;
+                            p[u] = 0.0;
+                            if (c < c1) {
+                                const int4 sv = in_smem ? *reinterpret_cast<const int4*>(srow + c)
+                                                        : __ldg(reinterpret_cast<const int4*>(srow + c));
+                                p[u] = lz_i2d(sv.x) * wa[u].x + lz_i2d(sv.y) * wa[u].y + (lz_i2d(sv.z) * wb[u].x + lz_i2d(sv.w) * wb[u].y);
+                            }
+                        }
+                        double acc = (p[0] + p[1]) + (p[2] + p[3]);
+                        acc = warp_sum(acc);
+                        if (lane == 0) segp[r * nseg + sg] = acc;
                     }
                 }
-                acc = (p[0] + p[1]) + (p[2] + p[3]);
-            } else {
-                for (int c = c0 + lane; c < c1; c += 32) acc += (double)(in_smem ? srow[c] : __ldg(srow + c)) * wsm[c];
             }
-            acc = warp_sum(acc);
-            if (lane == 0) segp[r * nseg + sg] = acc;
+        } else {
+            for (int task = wid; task < R * nseg; task += kLzThreads / 32) {
+                const int r = task / nseg, sg = task - r * nseg;
+                const bool in_smem = r < rs;
+                const int32_t* srow = in_smem ? ssm + (size_t)r * spitch : a.S + (size_t)(i0 + r) * n;
+                const int c0 = sg * kLzSeg, c1 = min(n, c0 + kLzSeg);
+                double acc = 0.0;
+                for (int c = c0 + lane; c < c1; c += 32) acc += (double)(in_smem ? srow[c] : __ldg(srow + c)) * wsm[c];
+                acc = warp_sum(acc);
+                if (lane == 0) segp[r * nseg + sg] = acc;
+            }
         }
         __syncthreads();
         if (prof) a.prof[j * 8 + 2] = lz_timer();

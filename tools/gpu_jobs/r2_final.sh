@@ -4,6 +4,9 @@
 #   (b) ncu --set full of one warmed-up Gram launch per dtype (DRAM bytes, tensor pipe, L2),
 #   (c) ncu --set full of the persistent Lanczos kernel + launch list of a whole vpca_compute_pca.
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_pca_gpu.py tests/test_parity_fullsize_gpu.py -q -m gpu --maxfail=5 --tb=short 2>&1 | tail -4 | cut -c1-300
+VPCA_LZ_PROF=1 EIG_N=2504 EIG_MODES=auto EIG_REPS=7 timeout 300 python tools/eig_bench.py 2>&1 | tail -2
+EIG_N=1092,4096,10000 EIG_MODES=auto EIG_REPS=5 timeout 300 python tools/eig_bench.py 2>&1 | tail -3
 timeout 900 python bench.py > gpurun_out/r2_bench_final_1gpu.json 2> gpurun_out/r2_bench_final_1gpu.err
 echo "bench rc=$?"; tail -c 1500 gpurun_out/r2_bench_final_1gpu.json; tail -3 gpurun_out/r2_bench_final_1gpu.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_final_reference.json 2> gpurun_out/r2_bench_final_reference.err
