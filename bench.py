@@ -462,11 +462,10 @@ def run_b200(args):
     tp = ROOT / "profiles" / "r2_gram_traffic.json"
     if tp.exists():
         try:
-            import hashlib
             tj = json.loads(tp.read_text())
-            src_hash = hashlib.sha256((ROOT / "spark_examples_b200" / "csrc" / "gram_sm100.cu").read_bytes()).hexdigest()[:16]
+            src_hash = native.gramSourceFingerprint()     # code only: comments and whitespace do not count
             ent = tj.get(args.dtype, {})
-            if ent.get("kernel_source_sha256_16") == src_hash:
+            if ent.get("kernel_code_sha256_16") == src_hash:
                 traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
         except Exception:
             traffic = None

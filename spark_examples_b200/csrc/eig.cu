@@ -6,12 +6,16 @@
 //   :224-227  RowMatrix(rows).computePrincipalComponents(numPc): spark-mllib 1.6.1 forms Cov = C^T C/(m-1) - ... and
 //             takes the first k left singular vectors of Cov (LAPACK dgesdd).  C = J S J is symmetric PSD, so those
 //             are the eigenvectors of C for its k largest eigenvalues; we compute them from C directly:
-//               1. Householder tridiagonalisation  C = Q T Q^T           (N steps, 2 kernels per step)
+//   N >= 512 (default): Lanczos with full reorthogonalisation for the top k pairs only -- as ONE persistent cooperative
+//               kernel per 16-step chunk that reads the int32 Gram S itself and applies the centring to the vector
+//               (lz_persist_kernel below); the five-kernel CUDA-graph form of round 1 remains for N > 16384;
+//   small N, VPCA_EIG=direct, and the fallback of the Krylov solver:
+//               1. Householder tridiagonalisation  C = Q T Q^T           (N steps, 1-2 kernels per step, not blocked)
 //               2. k largest eigenvalues of T by Sturm-count multisection (parallel over shifts)
 //               3. eigenvectors of T by inverse iteration               (tridiagonal LU with partial pivoting)
 //               4. back-transformation  z = Q y  with the stored reflectors, normalise, fix the sign.
-// Everything is HBM/L2-latency bound FP64 vector work (the 50 MB matrix at N = 2504 lives in L2): rows are
-// contiguous so every pass is coalesced; one warp owns one row in the trailing update.
+// Everything is latency-bound FP64 vector work (at N = 2504 the matrix lives in L2, or for Lanczos in shared memory): rows
+// are contiguous so every pass is coalesced.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -638,8 +642,9 @@ __global__ void __launch_bounds__(512) backtransform_kernel(const double* __rest
 // above, on m instead of N) give Ritz values theta and vectors z = V y whose residual is |beta_m y_m|.  One step
 // costs one pass over C (50 MB from L2 at N = 2504) instead of the N steps the reduction needs, and population
 // structure separates the top of the spectrum, so a few dozen steps reach |beta_m y_m| <= 1e-12 ||T||.
-// Five launches per step (matvec | V^T w | w -= V h | V^T w | w -= V h), step index and stop flag in device
-// memory so that kLzChunk steps replay from one CUDA graph; the host looks at the residual after a replay.
+// Graph form (N > 16384, VPCA_LZ_PERSIST=0): five launches per step (matvec | V^T w | w -= V h | V^T w | w -= V h), step
+// index and stop flag in device memory so that kLzChunk steps replay from one CUDA graph; the host looks at the residual
+// after a replay.  Persistent form (default): see lz_persist_kernel further down.
 // Anything unusual -- breakdown, slow convergence, a larger eigenvalue found by the deflated re-run that guards
 // against a missed copy of a multiple eigenvalue -- falls back to the direct reduction, which remains the
 // reference-grade path.  Every reduction has a fixed order: the result is run-to-run deterministic.

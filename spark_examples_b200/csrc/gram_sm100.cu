@@ -12,20 +12,28 @@
 //   * an output tile is the product of A row blocks (128 samples each: one per CTA, so two with cta_group::2) and up to
 //     256 B rows; its accumulator holds D[m][n] = sum_v X[rowA + m][v] * X[rowB + n][v] and is written TRANSPOSED,
 //     S[rowB + n][rowA + m], so that the 32 lanes of a warp (= 32 consecutive m) hit 32 consecutive int32 of one row of S;
-//   * EXACT BLOCK COVER (int8 / bf16 / f8f6f4): in units of 128 x 128 blocks the lower triangle of S has nb (nb + 1) / 2
-//     blocks, and a tile always multiplies TWO A blocks (M = 256: an MMA costs 128 rows per CTA whatever it needs), so
-//     the square 256 x 256 tiling pays 4 blocks for each of the nb / 2 diagonal tiles although only 3 are needed.  The
-//     A blocks of a pair need not be adjacent and the B rows may be a single block (N = 128), and a block above the
-//     diagonal may be computed in place of its mirror image and written transposed; with that freedom the tile list of
-//     build_tiles covers every needed block exactly once (2504 samples: 210 blocks instead of 220, 4.5 % less MMA
-//     work).  kind::mxf4 keeps the square 256 x 240 tiling (its block scales take 16 TMEM columns);
+//   * default tiling: rectangles of 256 A rows (two adjacent 128-blocks) x up to 256 B rows that touch row >= col, the B
+//     strips of nearly equal width (2504 samples: 7 x 256 + 3 x 240; kind::mxf4: 3 x 240 + 8 x 224 because its block scales
+//     take 16 TMEM columns), so that tiles have nearly equal weight and a worker never spans three of them;
+//   * EXACT BLOCK COVER (VPCA_EXACT_COVER=1; int8 / bf16 / f8f6f4; measured SLOWER on B200 and therefore off by default --
+//     its N = 128 tiles need 96 B/clk per SM from L2 where a 256 x 256 tile needs 64, and L2 -> SM delivers ~58): in units
+//     of 128 x 128 blocks the lower triangle of S has nb (nb + 1) / 2 blocks, and a tile always multiplies TWO A blocks
+//     (M = 256: an MMA costs 128 rows per CTA whatever it needs), so the square tiling pays 4 blocks for each of the nb / 2
+//     diagonal tiles although only 3 are needed.  The A blocks of a pair need not be adjacent and the B rows may be a
+//     single block (N = 128), and a block above the diagonal may be computed in place of its mirror image and written
+//     transposed; with that freedom the tile list of build_tiles covers every needed block exactly once (2504 samples:
+//     210 blocks instead of 220, 4.5 % less MMA work);
+//   * owner-computes bands: a context that stores only rows [own_lo, own_hi) of S and has no peers enumerates only the
+//     tiles of those rows (every variant is fed to every band's context; nothing is flushed anywhere else);
 //   * the variant axis is cut into k-blocks of 128 bytes (one swizzle atom) and into windows of `kb_window`
 //     k-blocks; in every window the (tile, k-block) units are split evenly over the workers (CTA pairs), and all
 //     workers walk the windows in the same order, so the slice of X a window needs (n x kb_window*128 B, sized to
 //     sit in L2) is fetched from HBM once and re-read from L2 by the other tiles;
-//   * when there are at most as many tiles as workers (N = 2504: 55 tiles, 74 pairs) a worker touches <= 2 tiles,
-//     always the same two, so both accumulators stay resident in TMEM (2 x 256 columns) for the whole launch and
-//     are flushed once at the end; otherwise (large N) it is plain stream-K with double-buffered accumulators.
+//   * when the pieces of every worker fit its TMEM columns (N = 2504: 55 tiles, 74 pairs: a worker touches <= 2 tiles,
+//     always the same ones) the accumulators stay resident in TMEM for the whole launch and are flushed once at the end;
+//     otherwise (large N) it is whole-tile waves + a stream-K tail with double-buffered accumulators;
+//   * the split of a window over the workers is speed-weighted from launch to launch (rebalance_kernel, repair_split);
+//   * the flush packs two cells into one 64-bit red (no carry between the halves: counts are non-negative, sums < 2^31).
 // Integer atomics make the result independent of the order of the flushes: S is bit-exact.
 #include <cuda.h>
 #include <cuda_runtime.h>

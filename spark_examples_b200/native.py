@@ -602,6 +602,18 @@ def debugBandTiles(n_samples: int, cta_group: int, row0: int, rows: int) -> np.n
     return out
 
 
+def gramSourceFingerprint() -> str:
+    """sha256 (16 hex digits) of csrc/gram_sm100.cu with comments and whitespace removed: what an ncu capture of the Gram
+    kernel is tied to (profiles/r2_gram_traffic.json) -- editing a comment does not orphan a capture, editing code does."""
+    import hashlib
+    import re
+    src = (Path(__file__).resolve().parent / "csrc" / "gram_sm100.cu").read_text()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    src = re.sub(r"\s+", "", src)
+    return hashlib.sha256(src.encode()).hexdigest()[:16]
+
+
 def maxClusters(device: int, cluster_size: int) -> int:
     """Clusters of `cluster_size` Gram-kernel CTAs the device holds at once (vpca_debug_max_clusters)."""
     L = load_library()

@@ -55,8 +55,10 @@ def main():
         tot = to_bytes(out[0]["dram__bytes_read.sum"]) + to_bytes(out[0]["dram__bytes_write.sum"])
         tp = ROOT / "profiles" / "r2_gram_traffic.json"
         tj = json.loads(tp.read_text()) if tp.exists() else {}
-        src = (ROOT / "spark_examples_b200" / "csrc" / "gram_sm100.cu").read_bytes()
-        tj[args.traffic] = {"dram_bytes_per_launch": int(tot), "kernel_source_sha256_16": hashlib.sha256(src).hexdigest()[:16],
+        import sys
+        sys.path.insert(0, str(ROOT))
+        from spark_examples_b200 import native
+        tj[args.traffic] = {"dram_bytes_per_launch": int(tot), "kernel_code_sha256_16": native.gramSourceFingerprint(),
                             "source": args.source or f"{args.out}: dram__bytes_read.sum + dram__bytes_write.sum of one warmed-up launch"}
         tp.write_text(json.dumps(tj, indent=1) + "\n")
 
