@@ -1101,7 +1101,11 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         }
         const double inv = 1.0 / nrm;
         const bool vec4 = (n & 3) == 0;
-        if (vec4) {
+        // column workers x row groups must fill most of the 32 warps (5 x 6 at N = 2504, 8 x 4 at 4096); cohorts whose segment
+        // count leaves more than a fifth of them idle (e.g. 20 segments at N = 10 000) use the (row, segment) task list below
+        const int CWp = min(nseg, kLzThreads / 32), Gp = (kLzThreads / 32) / CWp;
+        const bool regw = vec4 && 5 * CWp * Gp >= 4 * (kLzThreads / 32);
+        if (regw) {
             // A warp keeps ONE 512-column segment of w in registers (16 doubles per lane) and walks rows of S under it:
             // per element only the 4 bytes of S are read again (shared memory or L2), not the 8 bytes of w as well.
             // Column workers cw = 0 .. CW-1 own the segments cw, cw + CW, ...; G = 32 / CW row groups share the rows.
@@ -1141,6 +1145,29 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
                         if (lane == 0) segp[r * nseg + sg] = acc;
                     }
                 }
+            }
+        } else if (vec4) {
+            for (int task = wid; task < R * nseg; task += kLzThreads / 32) {
+                const int r = task / nseg, sg = task - r * nseg;
+                const bool in_smem = r < rs;
+                const int32_t* srow = in_smem ? ssm + (size_t)r * spitch : a.S + (size_t)(i0 + r) * n;
+                const int c0 = sg * kLzSeg, c1 = min(n, c0 + kLzSeg);
+                double p[kLzSeg / 128];
+#pragma unroll
+                for (int u = 0; u < kLzSeg / 128; ++u) {
+                    const int c = c0 + (u * 32 + lane) * 4;
+                    p[u] = 0.0;
+                    if (c < c1) {
+                        const int4 sv = in_smem ? *reinterpret_cast<const int4*>(srow + c)
+                                                : __ldg(reinterpret_cast<const int4*>(srow + c));
+                        const double2 wa = *reinterpret_cast<const double2*>(wsm + c);
+                        const double2 wb = *reinterpret_cast<const double2*>(wsm + c + 2);
+                        p[u] = lz_i2d(sv.x) * wa.x + lz_i2d(sv.y) * wa.y + (lz_i2d(sv.z) * wb.x + lz_i2d(sv.w) * wb.y);
+                    }
+                }
+                double acc = (p[0] + p[1]) + (p[2] + p[3]);
+                acc = warp_sum(acc);
+                if (lane == 0) segp[r * nseg + sg] = acc;
             }
         } else {
             for (int task = wid; task < R * nseg; task += kLzThreads / 32) {

@@ -265,12 +265,9 @@ class VariantsPcaDriver:
                 else:
                     parts.append(_rows_to_batch([extractCallInfo(v, mapping) for v in part]))
             return CallsRdd(parts, n)
-        if os.environ.get("VPCA_HOST_JOIN") != "1":
-            # keying, join / merge and the concatenation of the calls run on the GPU and feed the encoder there
-            return CallsRdd([self._joined_slice(data, variantSetCount)], n)
-        callsets = self.joinDatasets(data) if variantSetCount == 2 else self.mergeDatasets(data, variantSetCount)
-        per = self.conf.variantsPerPartition()
-        return CallsRdd([_rows_to_batch(callsets[i:i + per]) for i in range(0, max(len(callsets), 1), per)], n)
+        # keying, join / merge and the concatenation of the calls run on the GPU and feed the encoder there (csrc/join.cu);
+        # joinDatasets / mergeDatasets above stay as the record-level mirror of the reference's public methods
+        return CallsRdd([self._joined_slice(data, variantSetCount)], n)
 
     # -- VariantsPca.scala:182-191 ----------------------------------------------------------------------------------
     def getSimilarityMatrix(self, callsets: CallsRdd) -> SimilarityMatrix:

@@ -186,9 +186,10 @@ def test_compute_pca_needs_two_components():
         d.computePca(None)
 
 
-def test_joined_slice_rows_equal_the_record_level_join_and_merge(monkeypatch):
+def test_joined_slice_rows_equal_the_record_level_join_and_merge():
     """getCallsRdd hands 2+ datasets to the GPU as a JoinedSlice; its host rendering (collect) must equal what the
-    record-level joinDatasets / mergeDatasets (VPCA_HOST_JOIN=1, the dict-based restatement of :115-148) produce."""
+    record-level joinDatasets / mergeDatasets (the dict-based mirror of :115-148) produce after :164-167."""
+    from spark_examples_b200.variants_pca import _rows_to_batch
     rng = np.random.default_rng(17)
     callsets = [(f"p-{i}", f"P{i}") for i in range(9)] + [(f"q-{i}", f"Q{i}") for i in range(7)]
 
@@ -198,10 +199,10 @@ def test_joined_slice_rows_equal_the_record_level_join_and_merge(monkeypatch):
 
     d1, d2 = ds(callsets[:9], rng.integers(0, 60, 80)), ds(callsets[9:], rng.integers(0, 60, 80))   # repeated positions
     for datasets in ([d1, d2], [d1, d2, d2[:30]]):
-        got = {}
-        for host in ("0", "1"):
-            monkeypatch.setenv("VPCA_HOST_JOIN", host)
-            conf = pkg.PcaConf([])
-            d = VariantsPcaDriver(conf, common=pkg.VariantsCommon(conf, callsets=callsets, datasets=datasets))
-            got[host] = sorted(d.getCallsRdd(d.getData).collect())
-        assert got["0"] == got["1"] and len(got["0"]) > 5
+        conf = pkg.PcaConf([])
+        d = VariantsPcaDriver(conf, common=pkg.VariantsCommon(conf, callsets=callsets, datasets=datasets))
+        got = sorted(d.getCallsRdd(d.getData).collect())
+        recs = d.joinDatasets(d.getData) if len(datasets) == 2 else d.mergeDatasets(d.getData, len(datasets))
+        b = _rows_to_batch(recs)
+        want = sorted(b.idx[b.offsets[i]:b.offsets[i + 1]].tolist() for i in range(len(b.offsets) - 1))
+        assert got == want and len(got) > 5
