@@ -304,7 +304,8 @@ int vpca_get_stats(vpca_ctx* ctx, vpca_stats* out);
 int vpca_debug_gram_profile(vpca_ctx* ctx, int64_t* out, int32_t max_ctas);
 /* Diagnostic (set VPCA_LZ_PROF=1 before the first vpca_compute_pca): block 0's timestamps of the persistent Lanczos kernel,
  * 8 x int64 nanoseconds per step {step start, start vector staged + norms, mat-vec done, y and the new basis column written,
- * share of V^T y written, first grid barrier passed, first Gram-Schmidt pass done, second pass done (third barrier next)}
+ * shares of V^T y and V^T v_j written, first grid barrier passed, fused Gram-Schmidt pass done, next start vector written
+ * (second grid barrier next)}
  * for steps 0..31 (each slot holds the last launch that ran that step index); returns the number of steps written or a
  * negative vpca_status. */
 int vpca_debug_lanczos_profile(vpca_ctx* ctx, int64_t* out, int32_t max_steps);

@@ -870,6 +870,7 @@ struct LzArgs {
     double* wbuf;           // 2 n
     double* alpha;
     double* beta;
+    double* G;              // cap x cap: Gram matrix V^T V of the basis, row j filled at step j (one-reduction Gram-Schmidt)
     double* hpart;          // 2 x blocks x cap
     double* part;           // part[0] = ||w||^2 after the last step (one partial for lz_check_kernel)
     int* st;                // st[0] = next step, st[1] = flag (0 run, 2 breakdown), st[3] = step cap
@@ -953,42 +954,45 @@ __device__ __forceinline__ void lz_share(const LzArgs& a, const double* vts, int
     }
 }
 
+// dst[q] = sum over the blocks of src[b][q], q < jc.  148 dependent-latency L2 loads per column if one thread walked the
+// blocks; instead warp w takes the blocks b = w, w + 32, ... (a handful of independent coalesced loads per lane, 32 columns
+// at a time) and the 32 partial sums of a column are added in warp order: deterministic and ~1 L2 latency deep.
+// Ends with a block barrier: dst is complete for every thread.
+__device__ __forceinline__ void lz_reduce_cols(const LzArgs& a, int nblocks, const double* src, int jc, double* dst, double* red2) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int qc = 0; qc < jc; qc += 32) {
+        const int q = qc + lane;
+        double acc = 0.0;
+        if (q < jc) {
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            int b = wid;
+            for (; b + 96 < nblocks; b += 128) {
+                p0 += __ldcg(src + (size_t)b * a.cap + q);
+                p1 += __ldcg(src + (size_t)(b + 32) * a.cap + q);
+                p2 += __ldcg(src + (size_t)(b + 64) * a.cap + q);
+                p3 += __ldcg(src + (size_t)(b + 96) * a.cap + q);
+            }
+            for (; b < nblocks; b += 32) p0 += __ldcg(src + (size_t)b * a.cap + q);
+            acc = (p0 + p1) + (p2 + p3);
+        }
+        __syncthreads();                 // red2 of the previous column chunk has been consumed
+        red2[wid * 33 + lane] = acc;
+        __syncthreads();
+        if (wid == 0 && q < jc) {
+            double t = 0.0;
+#pragma unroll 8
+            for (int w2 = 0; w2 < kLzThreads / 32; ++w2) t += red2[w2 * 33 + lane];
+            dst[q] = t;
+        }
+    }
+    __syncthreads();
+}
+
 // One Gram-Schmidt pass on the rows of this block: hs = sum over blocks of hin (columns [0, jc)), y -= VT hs, and
 // (hout != nullptr) this block's share of VT^T y.  Returns hs[jc - 1] (alpha contribution) in every thread.
 __device__ __forceinline__ double lz_orth_pass(const LzArgs& a, int nblocks, int i0, int R, int jc, const double* hin,
                                                double* hout, double* hs, double* y, double* red2, const double* vts) {
-    // hs[q] = sum over blocks of hin[b][q].  148 dependent-latency L2 loads per column if one thread walked the blocks;
-    // instead warp w takes the blocks b = w, w + 32, ... (a handful of independent coalesced loads per lane, 32 columns
-    // at a time) and the 32 partial sums of a column are added in a fixed order: deterministic and ~1 L2 latency deep.
-    {
-        const int lane_ = threadIdx.x & 31, wid_ = threadIdx.x >> 5;
-        for (int qc = 0; qc < jc; qc += 32) {
-            const int q = qc + lane_;
-            double acc = 0.0;
-            if (q < jc) {
-                double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-                int b = wid_;
-                for (; b + 96 < nblocks; b += 128) {
-                    p0 += __ldcg(hin + (size_t)b * a.cap + q);
-                    p1 += __ldcg(hin + (size_t)(b + 32) * a.cap + q);
-                    p2 += __ldcg(hin + (size_t)(b + 64) * a.cap + q);
-                    p3 += __ldcg(hin + (size_t)(b + 96) * a.cap + q);
-                }
-                for (; b < nblocks; b += 32) p0 += __ldcg(hin + (size_t)b * a.cap + q);
-                acc = (p0 + p1) + (p2 + p3);
-            }
-            __syncthreads();                 // red2 of the previous column chunk has been consumed
-            red2[wid_ * 33 + lane_] = acc;
-            __syncthreads();
-            if (wid_ == 0 && q < jc) {
-                double t = 0.0;
-#pragma unroll 8
-                for (int w2 = 0; w2 < kLzThreads / 32; ++w2) t += red2[w2 * 33 + lane_];
-                hs[q] = t;
-            }
-        }
-    }
-    __syncthreads();
+    lz_reduce_cols(a, nblocks, hin, jc, hs, red2);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int r = wid; r < R; r += kLzThreads / 32) {
         double acc = 0.0;
@@ -999,6 +1003,56 @@ __device__ __forceinline__ double lz_orth_pass(const LzArgs& a, int nblocks, int
     __syncthreads();
     if (hout != nullptr) lz_share(a, vts, i0, R, jc, y, hout + (size_t)blockIdx.x * a.cap);
     return hs[jc - 1];
+}
+
+// Both Gram-Schmidt passes of step j with ONE cross-block reduction.  Classical Gram-Schmidt applied twice computes
+// h1 = V^T y, y' = y - V h1, h2 = V^T y', y'' = y' - V h2; but h2 = V^T y - (V^T V) h1 = (I - G) h1 with G = V^T V, and the
+// new row of G, g = V^T v_j, can ride on the same reduction as h1 (both are sums of block-local shares).  So every block
+// reduces (h1, g), completes its copy of G, forms h = h1 + (I - G) h1 itself and updates y -= V h: one reduction and one
+// grid barrier less per step than two explicit passes, the same orthogonality to rounding.  Returns alpha_j = h[j].
+__device__ __forceinline__ double lz_fused_pass(const LzArgs& a, int nblocks, int i0, int R, int j, const double* hin,
+                                                const double* gin, double* hs, double* gs, double* Gs, double* y,
+                                                double* red2, const double* vts) {
+    const int jc = j + 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    lz_reduce_cols(a, nblocks, hin, jc, hs, red2);   // h1
+    lz_reduce_cols(a, nblocks, gin, jc, gs, red2);   // g = row j of G
+    // row / column j of G: every block keeps the leading kLzVtCols x kLzVtCols corner in shared memory, block 0 also
+    // writes the full matrix to global memory for the (rare) solves that run past kLzVtCols columns and for later launches
+    for (int q = threadIdx.x; q < jc; q += kLzThreads) {
+        if (j < kLzVtCols) {
+            Gs[j * kLzVtCols + q] = gs[q];
+            Gs[q * kLzVtCols + j] = gs[q];
+        }
+        if (blockIdx.x == 0) {
+            a.G[(size_t)j * a.cap + q] = gs[q];
+            a.G[(size_t)q * a.cap + j] = gs[q];
+        }
+    }
+    __syncthreads();
+    // h = h1 + (I - G) h1 on columns 0 .. j; G(q, j) = g[q] is this step's, older entries come from the mirror / global
+    double hq = 0.0;
+    const int q0 = threadIdx.x;
+    if (q0 < jc) {
+        double acc = 0.0;
+        for (int p = 0; p < jc; ++p) {
+            const double gqp = (p == j) ? gs[q0] : (q0 == j) ? gs[p]
+                               : (q0 < kLzVtCols && p < kLzVtCols) ? Gs[q0 * kLzVtCols + p] : __ldcg(a.G + (size_t)q0 * a.cap + p);
+            acc += gqp * hs[p];
+        }
+        hq = hs[q0] + (hs[q0] - acc);
+    }
+    __syncthreads();
+    if (q0 < jc) hs[q0] = hq;
+    __syncthreads();
+    for (int r = wid; r < R; r += kLzThreads / 32) {
+        double acc = 0.0;
+        for (int q = lane; q < jc; q += 32) acc += lz_vt(a, vts, i0, r, q) * hs[q];
+        acc = warp_sum(acc);
+        if (lane == 0) y[r] -= acc;
+    }
+    __syncthreads();
+    return hs[j];
 }
 
 __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs a) {
@@ -1020,7 +1074,10 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
     const int spitch = (n + 3) & ~3;
     double* vts = segp + (((size_t)rows_per * nseg + 1) & ~(size_t)1);   // rows_per x kLzVtCols
     double* rbar_sm = vts + (size_t)rows_per * kLzVtCols;                // n: rowSums / N (VariantsPca.scala:216), once per launch
-    int32_t* ssm = reinterpret_cast<int32_t*>(rbar_sm + (((size_t)n + 1) & ~(size_t)1));
+    double* Gs = rbar_sm + (((size_t)n + 1) & ~(size_t)1);               // kLzVtCols x kLzVtCols corner of G = V^T V
+    double* gs = Gs + kLzVtCols * kLzVtCols;                             // cap: the new row of G
+    double* vjs = gs + a.cap;                                            // rows_per: the block's rows of v_j
+    int32_t* ssm = reinterpret_cast<int32_t*>(vjs + ((rows_per + 1) & ~1));
     const int rs = min(R, a.rows_smem);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double rc = (double)n;
@@ -1046,13 +1103,36 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         const int r = e / kLzVtCols, q = e - r * kLzVtCols;
         vts[e] = q < j ? a.VT[(size_t)(i0 + r) * a.cap + q] : 0.0;
     }
+    for (int e = threadIdx.x; e < kLzVtCols * kLzVtCols; e += kLzThreads) {   // G of the columns earlier launches built
+        const int q = e / kLzVtCols, p2 = e - q * kLzVtCols;
+        Gs[e] = (q < j && p2 < j && !a.pre) ? __ldcg(a.G + (size_t)q * a.cap + p2) : 0.0;
+    }
     __syncthreads();
     const int jend = min(j + a.nsteps, a.st[3]);
     double* hp1 = a.hpart;
     double* hp2 = a.hpart + (size_t)nblocks * a.cap;
 
     if (a.pre && j > 0 && j < jend) {
-        // deflated restart: the start vector is made orthogonal to the j locked columns (two passes) before step j
+        // deflated restart: G of the j locked columns first (column c against columns 0 .. c: one share + reduction each)
+        for (int c = 0; c < j; ++c) {
+            for (int r = threadIdx.x; r < R; r += kLzThreads) y[r] = lz_vt(a, vts, i0, r, c);
+            __syncthreads();
+            lz_share(a, vts, i0, R, c + 1, y, hp2 + (size_t)blockIdx.x * a.cap);
+            lz_grid_barrier(a.bar, target, nblocks);
+            lz_reduce_cols(a, nblocks, hp2, c + 1, gs, red2);
+            for (int q = threadIdx.x; q <= c; q += kLzThreads) {
+                if (c < kLzVtCols) {
+                    Gs[c * kLzVtCols + q] = gs[q];
+                    Gs[q * kLzVtCols + c] = gs[q];
+                }
+                if (blockIdx.x == 0) {
+                    a.G[(size_t)c * a.cap + q] = gs[q];
+                    a.G[(size_t)q * a.cap + c] = gs[q];
+                }
+            }
+            lz_grid_barrier(a.bar, target, nblocks);   // hp2 is reused by the next column
+        }
+        // then the start vector is made orthogonal to the j locked columns (two explicit passes) before step j
         double* w_in = a.wbuf + (size_t)(j & 1) * n;
         for (int r = threadIdx.x; r < R; r += kLzThreads) y[r] = w_in[i0 + r];
         __syncthreads();
@@ -1190,21 +1270,21 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
             const double vj = wsm[i0 + r] * inv;
             a.VT[(size_t)(i0 + r) * a.cap + j] = vj;
             if (j < kLzVtCols) vts[r * kLzVtCols + j] = vj;
+            vjs[r] = vj;
         }
         __syncthreads();
         if (prof) a.prof[j * 8 + 3] = lz_timer();
-        lz_share(a, vts, i0, R, j + 1, y, hp1 + (size_t)blockIdx.x * a.cap);
+        lz_share(a, vts, i0, R, j + 1, y, hp1 + (size_t)blockIdx.x * a.cap);     // share of h1 = V^T y
+        lz_share(a, vts, i0, R, j + 1, vjs, hp2 + (size_t)blockIdx.x * a.cap);   // share of g = V^T v_j (row j of G)
         if (prof) a.prof[j * 8 + 4] = lz_timer();
         lz_grid_barrier(a.bar, target, nblocks);
-        // ---- phase B / C: classical Gram-Schmidt, applied twice
+        // ---- phase B: both Gram-Schmidt passes from one reduction (lz_fused_pass)
         if (prof) a.prof[j * 8 + 5] = lz_timer();
-        const double a1 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp1, hp2, hs, y, red2, vts);
+        const double aj = lz_fused_pass(a, nblocks, i0, R, j, hp1, hp2, hs, gs, Gs, y, red2, vts);
         if (prof) a.prof[j * 8 + 6] = lz_timer();
-        lz_grid_barrier(a.bar, target, nblocks);
-        const double a2 = lz_orth_pass(a, nblocks, i0, R, j + 1, hp2, nullptr, hs, y, red2, vts);
         for (int r = threadIdx.x; r < R; r += kLzThreads) w_out[i0 + r] = y[r];
         if (blockIdx.x == 0 && threadIdx.x == 0) {
-            a.alpha[j] = a1 + a2;
+            a.alpha[j] = aj;
             a.beta[j] = nrm;
         }
         if (prof) a.prof[j * 8 + 7] = lz_timer();
@@ -1298,7 +1378,7 @@ void eig_free(EigWork& w) {
     cudaFree(w.d_C); cudaFree(w.d_rowsum); cudaFree(w.d_v); cudaFree(w.d_w); cudaFree(w.d_p);
     cudaFree(w.d_diag); cudaFree(w.d_off); cudaFree(w.d_tau); cudaFree(w.d_scal); cudaFree(w.d_evals);
     cudaFree(w.d_evecs); cudaFree(w.d_lu); cudaFree(w.d_nz); cudaFree(w.d_step);
-    cudaFree(w.d_V); cudaFree(w.d_lzw); cudaFree(w.d_lzs); cudaFree(w.d_lzst); cudaFree(w.d_lzbar); cudaFree(w.d_lzprof);
+    cudaFree(w.d_V); cudaFree(w.d_lzw); cudaFree(w.d_lzs); cudaFree(w.d_lzst); cudaFree(w.d_lzbar); cudaFree(w.d_lzprof); cudaFree(w.d_lzG);
     if (w.graph_exec != nullptr) cudaGraphExecDestroy(w.graph_exec);
     if (w.lz_graph != nullptr) cudaGraphExecDestroy(w.lz_graph);
     w = EigWork{};
@@ -1352,6 +1432,8 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
         VPCA_TRY(cudaMalloc(&w.d_lzst, 8 * sizeof(int)));
         VPCA_TRY(cudaMemset(w.d_lzst, 0, 8 * sizeof(int)));
         VPCA_TRY(cudaMalloc(&w.d_lzbar, sizeof(unsigned)));
+        VPCA_TRY(cudaMalloc(&w.d_lzG, (size_t)kLzCap * kLzCap * sizeof(double)));
+        VPCA_TRY(cudaMemset(w.d_lzG, 0, (size_t)kLzCap * kLzCap * sizeof(double)));
         if (const char* pf = getenv("VPCA_LZ_PROF"); pf != nullptr && atoi(pf) != 0) {
             VPCA_TRY(cudaMalloc(&w.d_lzprof, 64 * 4 * sizeof(long long)));
             VPCA_TRY(cudaMemset(w.d_lzprof, 0, 64 * 4 * sizeof(long long)));
@@ -1376,7 +1458,8 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
     const int rows_per = persist ? (n + w.lz_blocks - 1) / w.lz_blocks : 0;
     const size_t base_smem =
         ((((size_t)n + 1) & ~(size_t)1) + kLzCap + (((size_t)rows_per + 1) & ~(size_t)1) +
-         ((((size_t)rows_per * ((n + kLzSeg - 1) / kLzSeg)) + 1) & ~(size_t)1) + (size_t)rows_per * kLzVtCols + (((size_t)n + 1) & ~(size_t)1)) * sizeof(double);
+         ((((size_t)rows_per * ((n + kLzSeg - 1) / kLzSeg)) + 1) & ~(size_t)1) + (size_t)rows_per * kLzVtCols + (((size_t)n + 1) & ~(size_t)1) +
+         (size_t)kLzVtCols * kLzVtCols + kLzCap + (((size_t)rows_per + 1) & ~(size_t)1)) * sizeof(double);
     // what is left of the 227 KB a block may use (minus the kernel's ~9 KB of static shared memory) holds rows of S
     int rows_smem = 0;
     {
@@ -1403,6 +1486,7 @@ static cudaError_t lanczos_topk(EigWork& w, int k, cudaStream_t stream, int64_t*
         a.alpha = alpha;
         a.beta = beta;
         a.hpart = hpart;
+        a.G = w.d_lzG;
         a.part = part;
         a.st = w.d_lzst;
         a.bar = w.d_lzbar;

@@ -160,6 +160,7 @@ struct EigWork {
     double* d_lzs = nullptr;    // alpha | beta | h | h2 | e2 | Y | theta2 | res | scal2 | part
     int* d_lzst = nullptr;      // {step, flag, ticket, step cap}
     unsigned* d_lzbar = nullptr;   // grid barrier counter of the persistent Lanczos kernel
+    double* d_lzG = nullptr;       // kLzCap x kLzCap: V^T V of the Lanczos basis (one-reduction Gram-Schmidt)
     long long* d_lzprof = nullptr; // VPCA_LZ_PROF=1: phase timestamps of block 0 (first 64 steps)
     bool c_valid = false;       // d_C holds the centred matrix of the last center_gram()
     int lz_blocks = 0;          // blocks of the persistent kernel (= SMs; 0: cooperative launch unavailable or VPCA_LZ_PERSIST=0)

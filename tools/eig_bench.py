@@ -46,8 +46,9 @@ def main():
                         print(json.dumps({"n": n, "lanczos_phase_us": {
                             "step_total": med(step[step > 0]), "stage_w_and_norms": med(pr[:, 1] - pr[:, 0]),
                             "matvec": med(pr[:, 2] - pr[:, 1]), "y_and_basis_column": med(pr[:, 3] - pr[:, 2]),
-                            "share_of_VTy": med(pr[:, 4] - pr[:, 3]), "barrier_1": med(pr[:, 5] - pr[:, 4]),
-                            "gram_schmidt_pass_1": med(pr[:, 6] - pr[:, 5]), "barrier_2_and_pass_2": med(pr[:, 7] - pr[:, 6])}}), flush=True)
+                            "shares_of_VTy_and_VTv": med(pr[:, 4] - pr[:, 3]), "barrier_1": med(pr[:, 5] - pr[:, 4]),
+                            "fused_gram_schmidt": med(pr[:, 6] - pr[:, 5]), "write_w": med(pr[:, 7] - pr[:, 6]),
+                            "barrier_2": round(med(step[step > 0]) - med(pr[:, 7] - pr[:, 0]), 2)}}), flush=True)
                 print(json.dumps({"n": n, "mode": mode, "k": k, "method": st["eig_method"], "iters": st["eig_iterations"],
                                   "device_ms": round(st["last_eig_ms"], 3), "eig_ms_med": round(times[len(times)//2], 3), "eig_ms_min": round(times[0], 3),
                                   "us_per_step": round(times[len(times)//2] * 1e3 / n, 2), "max_rel_err": err}), flush=True)
