@@ -1015,8 +1015,16 @@ __device__ __forceinline__ double lz_fused_pass(const LzArgs& a, int nblocks, in
                                                 double* red2, const double* vts) {
     const int jc = j + 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    lz_reduce_cols(a, nblocks, hin, jc, hs, red2);   // h1
-    lz_reduce_cols(a, nblocks, gin, jc, gs, red2);   // g = row j of G
+    if (gin == nullptr) {
+        // packed shares: columns [0, jc) of hin hold the shares of h1, columns [jc, 2 jc) those of g -- ONE reduction round
+        // (for 2 jc <= 32 a single L2 latency) yields both
+        lz_reduce_cols(a, nblocks, hin, 2 * jc, hs, red2);
+        for (int q = threadIdx.x; q < jc; q += kLzThreads) gs[q] = hs[jc + q];
+        __syncthreads();
+    } else {
+        lz_reduce_cols(a, nblocks, hin, jc, hs, red2);   // h1
+        lz_reduce_cols(a, nblocks, gin, jc, gs, red2);   // g = row j of G
+    }
     // row / column j of G: every block keeps the leading kLzVtCols x kLzVtCols corner in shared memory, block 0 also
     // writes the full matrix to global memory for the (rare) solves that run past kLzVtCols columns and for later launches
     for (int q = threadIdx.x; q < jc; q += kLzThreads) {
@@ -1274,13 +1282,14 @@ __global__ void __launch_bounds__(kLzThreads, 1) lz_persist_kernel(const LzArgs 
         }
         __syncthreads();
         if (prof) a.prof[j * 8 + 3] = lz_timer();
+        const bool packed = 2 * (j + 1) <= a.cap;   // both shares side by side in one buffer: one reduction round later
         lz_share(a, vts, i0, R, j + 1, y, hp1 + (size_t)blockIdx.x * a.cap);     // share of h1 = V^T y
-        lz_share(a, vts, i0, R, j + 1, vjs, hp2 + (size_t)blockIdx.x * a.cap);   // share of g = V^T v_j (row j of G)
+        lz_share(a, vts, i0, R, j + 1, vjs, (packed ? hp1 + (j + 1) : hp2) + (size_t)blockIdx.x * a.cap);   // share of g = V^T v_j
         if (prof) a.prof[j * 8 + 4] = lz_timer();
         lz_grid_barrier(a.bar, target, nblocks);
         // ---- phase B: both Gram-Schmidt passes from one reduction (lz_fused_pass)
         if (prof) a.prof[j * 8 + 5] = lz_timer();
-        const double aj = lz_fused_pass(a, nblocks, i0, R, j, hp1, hp2, hs, gs, Gs, y, red2, vts);
+        const double aj = lz_fused_pass(a, nblocks, i0, R, j, hp1, packed ? nullptr : hp2, hs, gs, Gs, y, red2, vts);
         if (prof) a.prof[j * 8 + 6] = lz_timer();
         for (int r = threadIdx.x; r < R; r += kLzThreads) w_out[i0 + r] = y[r];
         if (blockIdx.x == 0 && threadIdx.x == 0) {
