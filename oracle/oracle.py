@@ -216,6 +216,97 @@ def np_get_calls(variants, mapping):
     return rows
 
 
+# -- multi-dataset keying (VariantsPca.scala:62-78, :115-148).  The hash is Guava's `Hashing.murmur3_128()` --
+#    com.google.guava, pulled in through google-genomics-utils and shaded at build.sbt:44, NOT under /root/reference: the
+#    published MurmurHash3_x64_128 algorithm (Austin Appleby, public domain; seed 0) restated here with numpy uint64
+#    arithmetic, pinned on Guava's known answers in tests/test_oracle.py.
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _u64(x):
+    return np.uint64(int(x) & 0xFFFFFFFFFFFFFFFF)
+
+
+def _rotl(x, r):
+    x = int(x)
+    return _u64((x << r) | (x >> (64 - r)))
+
+
+def _mul(a, b):
+    return _u64(int(a) * int(b))
+
+
+def _fmix(k):
+    k = int(k)
+    k ^= k >> 33
+    k = (k * 0xFF51AFD7ED558CCD) & 0xFFFFFFFFFFFFFFFF
+    k ^= k >> 33
+    k = (k * 0xC4CEB9FE1A85EC53) & 0xFFFFFFFFFFFFFFFF
+    k ^= k >> 33
+    return _u64(k)
+
+
+def np_murmur3_128(data: bytes) -> bytes:
+    """`Hashing.murmur3_128().hashBytes(data).asBytes()`: 16 bytes, h1 then h2, little-endian."""
+    c1, c2 = _u64(0x87C37B91114253D5), _u64(0x4CF5AD432745937F)
+    h1 = h2 = _u64(0)
+    n = len(data)
+    body = np.frombuffer(data[: n - n % 16], dtype="<u8").reshape(-1, 2)
+    for k1, k2 in body:
+        h1 = _u64(int(h1) ^ int(_mul(_rotl(_mul(k1, c1), 31), c2)))
+        h1 = _u64(int(_rotl(h1, 27)) + int(h2))
+        h1 = _u64(int(h1) * 5 + 0x52DCE729)
+        h2 = _u64(int(h2) ^ int(_mul(_rotl(_mul(k2, c2), 33), c1)))
+        h2 = _u64(int(_rotl(h2, 31)) + int(h1))
+        h2 = _u64(int(h2) * 5 + 0x38495AB5)
+    tail = data[n - n % 16:]
+    if len(tail) > 8:
+        k2 = _u64(int.from_bytes(tail[8:], "little"))
+        h2 = _u64(int(h2) ^ int(_mul(_rotl(_mul(k2, c2), 33), c1)))
+    if len(tail) > 0:
+        k1 = _u64(int.from_bytes(tail[:8], "little"))
+        h1 = _u64(int(h1) ^ int(_mul(_rotl(_mul(k1, c1), 31), c2)))
+    h1 = _u64(int(h1) ^ n)
+    h2 = _u64(int(h2) ^ n)
+    h1 = _u64(int(h1) + int(h2))
+    h2 = _u64(int(h2) + int(h1))
+    h1, h2 = _fmix(h1), _fmix(h2)
+    h1 = _u64(int(h1) + int(h2))
+    h2 = _u64(int(h2) + int(h1))
+    return int(h1).to_bytes(8, "little") + int(h2).to_bytes(8, "little")
+
+
+def np_variant_key(contig, start, end, reference_bases, alternate_bases):
+    """VariantsPca.scala:62-78 getVariantKey: putString(contig) putLong(start) putLong(end) putString(referenceBases)
+    putString(alternateBases.mkString("")) -> HashCode.toString (hex of asBytes).  Guava writes longs little-endian
+    and, for `putString(s, UTF_8)`, the UTF-8 bytes."""
+    alt = "".join(alternate_bases or [])
+    payload = (contig.encode("utf-8") + int(start).to_bytes(8, "little", signed=True) +
+               int(end).to_bytes(8, "little", signed=True) + (reference_bases or "").encode("utf-8") + alt.encode("utf-8"))
+    return np_murmur3_128(payload).hex()
+
+
+def np_join_datasets(left, right):
+    """VariantsPca.scala:115-128 joinDatasets on two datasets of (key, calls) records: `keyBy` + `join` (inner, one output
+    per pair of records with equal keys) and `related._1 ++ related._2`.  Spark leaves the order of the joined RDD
+    unspecified; this restatement lists pairs by left record, then right record."""
+    by_key = {}
+    for key, calls in right:
+        by_key.setdefault(key, []).append(calls)
+    return [list(lc) + list(rc) for key, lc in left for rc in by_key.get(key, ())]
+
+
+def np_merge_datasets(datasets, variant_set_count):
+    """VariantsPca.scala:136-148 mergeDatasets: union of all datasets, `groupByKey`, keep the keys whose group has exactly
+    `variantSetCount` records (:144), flatten the group's calls (:145).  Groups are listed by first appearance, members
+    in union order."""
+    groups = {}
+    for ds in datasets:
+        for key, calls in ds:
+            groups.setdefault(key, []).append(calls)
+    return [[c for calls in g for c in calls] for g in groups.values() if len(g) == variant_set_count]
+
+
 def np_similarity(n, rows):
     """VariantsPca.scala:182-191 with one partition; rows: list of index lists."""
     S = np.zeros((n, n), np.int64)

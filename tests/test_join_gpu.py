@@ -16,7 +16,7 @@ def _hex(h):
     return np.ascontiguousarray(h, dtype="<u8").tobytes().hex()
 
 
-def test_hash_keys_known_answers_and_host_restatement():
+def test_hash_keys_known_answers_and_host_restatement(oracle):
     rng = np.random.default_rng(4)
     keys = [b"", b"hello", b"The quick brown fox jumps over the lazy dog"]
     keys += [bytes(rng.integers(0, 256, int(l), dtype=np.uint8)) for l in list(range(0, 70)) + [127, 128, 129, 1000]]
@@ -29,7 +29,7 @@ def test_hash_keys_known_answers_and_host_restatement():
     assert _hex(got[1]) == "029bbd41b3a7d8cb191dae486a901e5b"
     assert _hex(got[2]) == "6c1b07bc7bbc4be347939ac4a93c437a"
     for k, h in zip(keys, got):
-        assert _hex(h) == murmur3_128(k)
+        assert _hex(h) == murmur3_128(k) == oracle.np_murmur3_128(k).hex()
 
 
 def _random_slice(rng, n, rows_per, datasets, mode, universe):
@@ -55,16 +55,25 @@ def _drop_empty(off, idx):
 
 @pytest.mark.parametrize("mode,datasets", [(native.JOIN, 2), (native.MERGE, 2), (native.MERGE, 3), (native.MERGE, 5)])
 @pytest.mark.parametrize("rows_per,universe", [(1, 1), (40, 25), (3000, 2500), (20000, 60000)])
-def test_join_and_merge_rows_equal_the_host_implementation(mode, datasets, rows_per, universe):
+def test_join_and_merge_rows_equal_the_host_implementation(mode, datasets, rows_per, universe, oracle):
     rng = np.random.default_rng(rows_per * 7 + datasets)
     n = 97
     p = _random_slice(rng, n, rows_per, datasets, mode, universe)
     want = joined_rows_on_host(p)
+    # the oracle's restatement of VariantsPca.scala:115-148 on (key, calls) records, keys hashed by the oracle itself
+    recs = [(oracle.np_murmur3_128(k).hex(), p.idx[p.offsets[i]:p.offsets[i + 1]].tolist()) for i, k in enumerate(p.keys)]
+    if mode == native.JOIN:
+        ref_rows = oracle.np_join_datasets(recs[:p.n_left], recs[p.n_left:])
+    else:
+        per = len(recs) // datasets
+        ref_rows = oracle.np_merge_datasets([recs[d * per:(d + 1) * per] for d in range(datasets)], p.variant_set_count)
+    ref_rows = [r for r in ref_rows if r]                                         # :166 drops variants without carriers
     with native.NativePca(n, max_multiplicity=8) as nat:
         rows, nnz = nat.joinRows(p.mode, p.keys, p.offsets, p.idx, p.n_left, p.variant_set_count)
         off, idx = nat.joinFetch(rows, nnz)
     assert off[0] == 0 and off[-1] == nnz and (np.diff(off) >= 0).all()
     assert _drop_empty(off, idx) == _drop_empty(want.offsets, want.idx)          # same rows in the same order
+    assert _drop_empty(off, idx) == ref_rows                                      # and the oracle's rows
 
 
 def test_joined_rows_feed_the_gram_without_leaving_the_device(oracle):

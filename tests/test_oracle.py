@@ -192,3 +192,32 @@ def test_synthetic_cohort_has_separated_structure(oracle):
     C, _, _ = oracle.np_center(oracle.np_similarity_dense(X))
     w = np.linalg.eigvalsh(C)[::-1]
     assert (w[0] - w[1]) / w[0] > 0.05 and (w[1] - w[2]) / w[1] > 0.03 and w[3] / w[4] > 2
+
+
+def test_murmur3_128_known_answers_and_variant_key(oracle):
+    """Guava `Hashing.murmur3_128()` (un-vendored dependency, build.sbt:44) known answers, printed like HashCode.toString;
+    the oracle's restatement and the product's host mirror agree on random byte strings of every tail length."""
+    from spark_examples_b200.variants_pca import murmur3_128 as product_murmur, getVariantKey
+    import spark_examples_b200 as pkg
+    assert oracle.np_murmur3_128(b"").hex() == "0" * 32
+    assert oracle.np_murmur3_128(b"hello").hex() == "029bbd41b3a7d8cb191dae486a901e5b"
+    assert oracle.np_murmur3_128(b"The quick brown fox jumps over the lazy dog").hex() == "6c1b07bc7bbc4be347939ac4a93c437a"
+    rng = np.random.default_rng(8)
+    for l in list(range(0, 50)) + [63, 64, 65, 200]:
+        data = bytes(rng.integers(0, 256, l, dtype=np.uint8))
+        assert oracle.np_murmur3_128(data).hex() == product_murmur(data)
+    v = pkg.Variant("17", start=41196311, end=41196312, referenceBases="A", alternateBases=["C", "T"])
+    assert oracle.np_variant_key("17", 41196311, 41196312, "A", ["C", "T"]) == getVariantKey(v)
+    assert oracle.np_variant_key("17", 41196311, 41196312, "A", ["CT"]) == getVariantKey(v)        # mkString("") (:63-64)
+    assert oracle.np_variant_key("17", 41196311, 41196313, "A", ["CT"]) != getVariantKey(v)
+
+
+def test_join_and_merge_restatements_on_hand_cases(oracle):
+    """:115-128 inner join with duplicates on both sides (cartesian product per key); :136-148 merge keeps groups of
+    exactly variantSetCount records, whatever dataset they come from."""
+    left = [("k1", [0]), ("k2", [1, 2]), ("k1", [3])]
+    right = [("k1", [7]), ("k3", [8]), ("k1", [])]
+    assert oracle.np_join_datasets(left, right) == [[0, 7], [0], [3, 7], [3]]
+    ds = [[("a", [0]), ("b", [1])], [("a", [2]), ("c", [3])], [("a", [4]), ("b", [5]), ("b", [6])]]
+    assert oracle.np_merge_datasets(ds, 3) == [[0, 2, 4], [1, 5, 6]]       # "b": three records although only two datasets have it
+    assert oracle.np_merge_datasets(ds, 1) == [[3]]
