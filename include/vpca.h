@@ -338,6 +338,8 @@ int vpca_join_rows(vpca_ctx* ctx, int32_t mode, int32_t variant_set_count, int64
                    const int64_t* key_offsets, const int64_t* offsets, const int32_t* sample_idx, int64_t nrows,
                    int64_t* out_rows, int64_t* out_nnz);
 int vpca_join_fetch(vpca_ctx* ctx, int64_t* out_offsets, int32_t* out_idx);
+/* rows / calls of the retained result (what vpca_join_fetch will write); VPCA_ERR_STATE when there is none */
+int vpca_join_size(vpca_ctx* ctx, int64_t* out_rows, int64_t* out_nnz);
 int vpca_accumulate_joined(vpca_ctx* ctx, int64_t partition_id);
 
 /* Host-only introspection of the Gram schedule (works without a GPU; what tests/test_schedule.py checks).

@@ -858,6 +858,15 @@ int vpca_join_fetch(vpca_ctx* ctx, int64_t* out_offsets, int32_t* out_idx) {
     return VPCA_OK;
 }
 
+int vpca_join_size(vpca_ctx* ctx, int64_t* out_rows, int64_t* out_nnz) {
+    if (ctx == nullptr || out_rows == nullptr || out_nnz == nullptr) return fail(ctx, VPCA_ERR_BAD_ARG, "NULL argument");
+    std::lock_guard<std::mutex> jl(ctx->join_mu);
+    if (ctx->join.out_rows < 0) return fail(ctx, VPCA_ERR_STATE, "no joined rows: call vpca_join_rows first");
+    *out_rows = ctx->join.out_rows;
+    *out_nnz = ctx->join.out_nnz;
+    return VPCA_OK;
+}
+
 int vpca_accumulate_joined(vpca_ctx* ctx, int64_t partition_id) {
     if (ctx == nullptr) return fail(nullptr, VPCA_ERR_BAD_ARG, "ctx is NULL");
     std::lock_guard<std::mutex> jl(ctx->join_mu);

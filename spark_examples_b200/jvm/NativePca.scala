@@ -42,6 +42,11 @@ object NativePca {
    *  row.  The joined rows stay on the device; returns their number.  Follow with accumulateJoined + commit. */
   @native def joinRows(handle: Long, mode: Int, variantSetCount: Int, nLeft: Long, keyBytes: Array[Byte],
                        keyOffsets: Array[Long], offsets: Array[Long], sampleIdx: Array[Int], nRows: Long): Long
+  /** The joined rows as a CSR pair (offsets: rows + 1 entries, sampleIdx: at least the number of calls). */
+  @native def joinFetch(handle: Long, outOffsets: Array[Long], outSampleIdx: Array[Int]): Unit
+  /** Rows / calls of the retained join. */
+  @native def joinRowCount(handle: Long): Long
+  @native def joinCallCount(handle: Long): Long
   @native def accumulateJoined(handle: Long, partitionId: Long): Unit
   @native def commit(handle: Long, partitionId: Long): Unit
   @native def abort(handle: Long, partitionId: Long): Unit

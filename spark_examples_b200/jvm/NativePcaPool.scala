@@ -21,6 +21,9 @@ object NativePcaPool {
                      stagingLanes: Int): Long
   @native def destroy(pool: Long): Unit
   @native def size(pool: Long): Int
+  /** The NativePca handle of the GPU that serves `partitionId` (partitionId % size): for the single-context entry points
+   *  (NativePca.joinRows / accumulateJoined); the pool keeps owning it. */
+  @native def ctx(pool: Long, partitionId: Long): Long
   @native def reset(pool: Long): Unit
   @native def accumulateCalls(pool: Long, partitionId: Long, offsets: Array[Long], sampleIdx: Array[Int], nv: Long): Unit
   @native def accumulateCallsU16(pool: Long, partitionId: Long, offsets: Array[Long], sampleIdx: Array[Short], nv: Long): Unit

@@ -327,6 +327,52 @@ JNIEXPORT jlong JNICALL PCA(joinRows)(JNIEnv* env, jobject self, jlong h, jint m
     return rows;
 }
 
+/* the joined rows of the last joinRows as Java arrays (JoinedCallsRDD.compute): offsets needs rows + 1 entries, idx
+ * enough room for the calls (its length bounds what is written) */
+JNIEXPORT void JNICALL PCA(joinFetch)(JNIEnv* env, jobject self, jlong h, jlongArray outOffsets, jintArray outIdx) {
+    (void)self;
+    target t = from_ctx(h);
+    if (outOffsets == NULL || outIdx == NULL) { throw_arg(env, "joinFetch: null array%lld%lld", 0, 0); return; }
+    const jlong no = (*env)->GetArrayLength(env, outOffsets), ni = (*env)->GetArrayLength(env, outIdx);
+    if (no < 1) { throw_arg(env, "joinFetch: offsets must hold rows + 1 entries%lld%lld", 0, 0); return; }
+    int64_t* off = (int64_t*)xmalloc(env, (size_t)no * 8);
+    int32_t* ix = off ? (int32_t*)xmalloc(env, (size_t)(ni > 0 ? ni : 1) * 4) : NULL;
+    if (off == NULL || ix == NULL) { free(off); return; }
+    /* sizes of the retained result: a join of zero input rows reports them without touching anything */
+    int64_t rows = 0, nnz = 0;
+    int rc = vpca_join_size(t.ctx, &rows, &nnz);
+    if (rc == VPCA_OK && (rows + 1 > no || nnz > ni)) {
+        throw_arg(env, "joinFetch: the joined CSR has %lld rows and %lld calls; the arrays are smaller", rows, nnz);
+    } else {
+        if (rc == VPCA_OK) rc = vpca_join_fetch(t.ctx, off, ix);
+        if (rc != VPCA_OK) throw_rc(env, t, rc);
+        else {
+            (*env)->SetLongArrayRegion(env, outOffsets, 0, (jsize)(rows + 1), (const jlong*)off);
+            if (nnz > 0) (*env)->SetIntArrayRegion(env, outIdx, 0, (jsize)nnz, (const jint*)ix);
+        }
+    }
+    free(ix);
+    free(off);
+}
+
+JNIEXPORT jlong JNICALL PCA(joinRowCount)(JNIEnv* env, jobject self, jlong h) {
+    (void)self;
+    target t = from_ctx(h);
+    int64_t rows = 0, nnz = 0;
+    const int rc = vpca_join_size(t.ctx, &rows, &nnz);
+    if (rc != VPCA_OK) throw_rc(env, t, rc);
+    return rows;
+}
+
+JNIEXPORT jlong JNICALL PCA(joinCallCount)(JNIEnv* env, jobject self, jlong h) {
+    (void)self;
+    target t = from_ctx(h);
+    int64_t rows = 0, nnz = 0;
+    const int rc = vpca_join_size(t.ctx, &rows, &nnz);
+    if (rc != VPCA_OK) throw_rc(env, t, rc);
+    return nnz;
+}
+
 JNIEXPORT void JNICALL PCA(accumulateJoined)(JNIEnv* env, jobject self, jlong h, jlong pid) {
     (void)self;
     target t = from_ctx(h);
@@ -374,6 +420,11 @@ JNIEXPORT jlong JNICALL POOL(create)(JNIEnv* env, jobject self, jint n, jint nGp
 JNIEXPORT void JNICALL POOL(destroy)(JNIEnv* env, jobject self, jlong h) { (void)env; (void)self; vpca_pool_destroy((vpca_pool*)(intptr_t)h); }
 
 JNIEXPORT jint JNICALL POOL(size)(JNIEnv* env, jobject self, jlong h) { (void)env; (void)self; return vpca_pool_size((vpca_pool*)(intptr_t)h); }
+
+JNIEXPORT jlong JNICALL POOL(ctx)(JNIEnv* env, jobject self, jlong h, jlong pid) {
+    (void)env; (void)self;
+    return (jlong)(intptr_t)vpca_pool_ctx((vpca_pool*)(intptr_t)h, pid);
+}
 
 JNIEXPORT void JNICALL POOL(reset)(JNIEnv* env, jobject self, jlong h) {
     (void)self;

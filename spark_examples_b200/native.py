@@ -45,7 +45,7 @@ EXPORTED_SYMBOLS = (
     "vpca_accumulate_bits", "vpca_gram_set_peer_mode", "vpca_gram_gather", "vpca_accumulate_bed",
     "vpca_synchronize", "vpca_host_alloc", "vpca_host_free", "vpca_gram_set_peers_local", "vpca_owner_row_bands",
     "vpca_get_gram_band", "vpca_variant_count", "vpca_debug_rebalance",
-    "vpca_debug_lanczos_profile", "vpca_debug_max_clusters", "vpca_debug_band_tiles", "vpca_hash_keys", "vpca_join_rows", "vpca_join_fetch", "vpca_accumulate_joined",
+    "vpca_debug_lanczos_profile", "vpca_debug_max_clusters", "vpca_debug_band_tiles", "vpca_hash_keys", "vpca_join_rows", "vpca_join_fetch", "vpca_join_size", "vpca_accumulate_joined",
     "vpca_pool_create", "vpca_pool_destroy", "vpca_pool_size", "vpca_pool_ctx", "vpca_pool_last_error", "vpca_pool_reset",
     "vpca_pool_accumulate_calls", "vpca_pool_accumulate_calls_u16", "vpca_pool_accumulate_bits", "vpca_pool_accumulate_bed",
     "vpca_pool_commit", "vpca_pool_abort", "vpca_pool_reduce_and_finalize", "vpca_pool_get_gram", "vpca_pool_compute_pca",
@@ -140,6 +140,8 @@ def load_library() -> ctypes.CDLL:
     L.vpca_hash_keys.argtypes = [vp, vp, vp, i64, vp]
     L.vpca_join_rows.restype = ctypes.c_int
     L.vpca_join_rows.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.vpca_join_size.restype = ctypes.c_int
+    L.vpca_join_size.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.vpca_join_fetch.restype = ctypes.c_int
     L.vpca_join_fetch.argtypes = [vp, vp, vp]
     L.vpca_accumulate_joined.restype = ctypes.c_int
@@ -368,6 +370,12 @@ class NativePca:
                                              _host_ptr(payload) if len(payload) else None, _host_ptr(koff), _host_ptr(off),
                                              _host_ptr(idx) if len(idx) else None, len(keys), ctypes.byref(rows),
                                              ctypes.byref(nnz)))
+        return int(rows.value), int(nnz.value)
+
+    def joinSize(self):
+        """(rows, calls) of the joined rows the context retains (vpca_join_size)."""
+        rows, nnz = ctypes.c_int64(0), ctypes.c_int64(0)
+        self._check(self._lib.vpca_join_size(self._h, ctypes.byref(rows), ctypes.byref(nnz)))
         return int(rows.value), int(nnz.value)
 
     def joinFetch(self, rows: int, nnz: int):

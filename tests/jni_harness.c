@@ -70,6 +70,7 @@ REGION_GET(m_GetLongArrayRegion, jlong, K_LONG)
         memcpy((T*)a->data + start, buf, (size_t)len * sizeof(T));                             \
     }
 REGION_SET(m_SetIntArrayRegion, jint, K_INT)
+REGION_SET(m_SetLongArrayRegion, jlong, K_LONG)
 REGION_SET(m_SetDoubleArrayRegion, jdouble, K_DOUBLE)
 static jobject m_NewDirectByteBuffer(JNIEnv* env, void* address, jlong capacity) {
     (void)env;
@@ -84,7 +85,7 @@ static jlong m_GetDirectBufferCapacity(JNIEnv* env, jobject b) { (void)env; retu
 
 static const struct JNINativeInterface_ mock_table = {
     m_FindClass,          m_ThrowNew,          m_ExceptionCheck,      m_GetArrayLength,        m_GetByteArrayRegion,
-    m_GetShortArrayRegion, m_GetIntArrayRegion, m_GetLongArrayRegion,  m_SetIntArrayRegion,     m_SetDoubleArrayRegion,
+    m_GetShortArrayRegion, m_GetIntArrayRegion, m_GetLongArrayRegion,  m_SetIntArrayRegion,     m_SetLongArrayRegion,    m_SetDoubleArrayRegion,
     m_NewDirectByteBuffer, m_GetDirectBufferAddress, m_GetDirectBufferCapacity};
 static JNIEnv mock_env = &mock_table;
 
@@ -155,6 +156,12 @@ static int run_validate(void) {
     jarray vecs = new_array(K_DOUBLE, 5);
     POOL(computePca)(env, NULL, 0, 3, 2, vecs, NULL);
     bad += expect_throw("computePca output too small", "IllegalArgument");
+    PCA(joinRows)(env, NULL, 0, 0, 2, 1, NULL, off, off, idx, 3);
+    bad += expect_throw("joinRows with null key bytes", "IllegalArgument");
+    PCA(joinRows)(env, NULL, 0, 0, 2, 1, rows, off, off, idx, 4);      /* nrows + 1 = 5 offsets needed, 4 present */
+    bad += expect_throw("joinRows offsets shorter than nrows + 1", "IllegalArgument");
+    PCA(joinFetch)(env, NULL, 0, NULL, idx);
+    bad += expect_throw("joinFetch with null offsets", "IllegalArgument");
     /* bad configuration: rejected by the library, surfaced as an exception, no handle returned */
     const jlong h = POOL(create)(env, NULL, 1, 1, 0, 2, 2, 4, 2);     /* n_samples = 1 */
     if (h != 0) { fprintf(stderr, "FAIL create(n = 1) returned a handle\n"); ++bad; }
@@ -164,6 +171,53 @@ static int run_validate(void) {
     free_array(off); free_array(idx); free_array(idx16); free_array(rows); free_array(small); free_array(vecs);
     printf("{\"mode\": \"validate\", \"failures\": %d}\n", bad);
     return bad ? 1 : 0;
+}
+
+/* NativePca.joinRows / joinRowCount / joinCallCount / joinFetch / accumulateJoined on a hand-made pair of datasets
+ * (VariantsPca.scala:115-128): left = {kA: [0,1], kB: [2], kA: [3]}, right = {kA: [4], kC: [0], kA: [5,5]} over 6 samples.
+ * Inner join, left row then right row: [0,1,4] [0,1,5,5] [3,4] [3,5,5]. */
+static int run_join(JNIEnv* env) {
+    int bad = 0;
+    const int n = 70;
+    const jlong h = PCA(create)(env, NULL, n, 0, 0, 2, 4, 4);
+    if (expect_clean("NativePca.create") || h == 0) return 1;
+    const char* keys[6] = {"kA", "kB", "kA", "kA", "kC", "kA"};
+    const int lens[6] = {2, 1, 1, 1, 1, 2};
+    const jint calls[8] = {0, 1, 2, 3, 4, 0, 5, 5};
+    jarray kb = new_array(K_BYTE, 12), ko = new_array(K_LONG, 7), ro = new_array(K_LONG, 7), ix = new_array(K_INT, 8);
+    for (int i = 0; i < 6; ++i) {
+        memcpy((char*)kb->data + 2 * i, keys[i], 2);
+        ((jlong*)ko->data)[i + 1] = 2 * (i + 1);
+        ((jlong*)ro->data)[i + 1] = ((jlong*)ro->data)[i] + lens[i];
+    }
+    memcpy(ix->data, calls, sizeof(calls));
+    const jlong rows = PCA(joinRows)(env, NULL, h, 0, 2, 3, kb, ko, ro, ix, 6);
+    bad += expect_clean("joinRows");
+    const jlong ncalls = PCA(joinCallCount)(env, NULL, h);
+    if (rows != 4 || PCA(joinRowCount)(env, NULL, h) != 4 || ncalls != 12) { fprintf(stderr, "FAIL join size %lld rows %lld calls\n", (long long)rows, (long long)ncalls); ++bad; }
+    jarray fo = new_array(K_LONG, 5), fi = new_array(K_INT, 12);
+    PCA(joinFetch)(env, NULL, h, fo, fi);
+    bad += expect_clean("joinFetch");
+    const jlong want_off[5] = {0, 3, 7, 9, 12};
+    const jint want_idx[12] = {0, 1, 4, 0, 1, 5, 5, 3, 4, 3, 5, 5};
+    if (memcmp(fo->data, want_off, sizeof(want_off)) != 0 || memcmp(fi->data, want_idx, sizeof(want_idx)) != 0) { fprintf(stderr, "FAIL joined rows differ\n"); ++bad; }
+    PCA(accumulateJoined)(env, NULL, h, 11);
+    bad += expect_clean("accumulateJoined");
+    PCA(commit)(env, NULL, h, 11);
+    PCA(finalizeGram)(env, NULL, h);
+    bad += expect_clean("commit / finalizeGram");
+    jarray gram = new_array(K_INT, (jlong)n * n);
+    PCA(getGram)(env, NULL, h, n, gram);
+    bad += expect_clean("getGram");
+    int32_t* want = (int32_t*)calloc((size_t)n * n, sizeof(int32_t));
+    for (int r = 0; r < 4; ++r)                              /* for (c1 <- row; c2 <- row) m(c1, c2) += 1 (:186-188) */
+        for (jlong a = want_off[r]; a < want_off[r + 1]; ++a)
+            for (jlong b = want_off[r]; b < want_off[r + 1]; ++b) want[(size_t)want_idx[a] * n + want_idx[b]] += 1;
+    if (memcmp(gram->data, want, (size_t)n * n * sizeof(int32_t)) != 0) { fprintf(stderr, "FAIL Gram of the joined rows differs\n"); ++bad; }
+    free(want);
+    PCA(destroy)(env, NULL, h);
+    free_array(kb); free_array(ko); free_array(ro); free_array(ix); free_array(fo); free_array(fi); free_array(gram);
+    return bad;
 }
 
 /* ------------------------------------------------------------------------------------------------- gpu */
@@ -260,6 +314,7 @@ static int run_gpu(int n, int64_t nv_req, int gpus) {
     for (int i = 0; i < n; ++i) norm += ((double*)vecs->data)[i] * ((double*)vecs->data)[i];
     if (norm < 0.999999 || norm > 1.000001 || ((double*)evals->data)[0] < ((double*)evals->data)[1]) { fprintf(stderr, "FAIL PCs: norm %g\n", norm); ++bad; }
     POOL(destroy)(env, NULL, pool);
+    bad += run_join(env);
     printf("{\"mode\": \"gpu\", \"n_samples\": %d, \"rows\": %lld, \"gpus\": %d, \"gram_entries_differing\": %zu, \"non_zero_rows\": %d, "
            "\"eval0\": %.17g, \"eval1\": %.17g, \"failures\": %d}\n",
            n, (long long)nv, gpus, diff, (int)nz, ((double*)evals->data)[0], ((double*)evals->data)[1], bad);

@@ -48,6 +48,7 @@ struct JNINativeInterface_ {
     void (*GetIntArrayRegion)(JNIEnv* env, jintArray array, jsize start, jsize len, jint* buf);
     void (*GetLongArrayRegion)(JNIEnv* env, jlongArray array, jsize start, jsize len, jlong* buf);
     void (*SetIntArrayRegion)(JNIEnv* env, jintArray array, jsize start, jsize len, const jint* buf);
+    void (*SetLongArrayRegion)(JNIEnv* env, jlongArray array, jsize start, jsize len, const jlong* buf);
     void (*SetDoubleArrayRegion)(JNIEnv* env, jdoubleArray array, jsize start, jsize len, const jdouble* buf);
     jobject (*NewDirectByteBuffer)(JNIEnv* env, void* address, jlong capacity);
     void* (*GetDirectBufferAddress)(JNIEnv* env, jobject buf);
