@@ -90,7 +90,8 @@ struct TileDesc {
                         // (256, or 240 for kind::mxf4 whose two accumulators sit below the scale columns at 480)
     int pad1;
 };
-constexpr int kTileXpose = 1, kTileFiller = 2;
+constexpr int kTileXpose = 1, kTileFiller = 2, kTileSelfB = 4;   // kTileSelfB: the B rows ARE the pair's two A blocks (a
+                                                                  // diagonal 256 x 256 tile): B is read from the A tile, no B load
 constexpr int kMaxSegs = 4;   // (tile, k-range) pieces one worker may own per window in resident mode
 
 struct GramArgs {
@@ -484,7 +485,9 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                 // B rows per CTA: a 64-row box is enough for the N <= 128 tiles of the exact block cover (cta_group::2)
                 const bool half_box = (CG == 2) && (s.n_eff <= 128);
                 const bool two_boxes = (CG == 1) && (s.n_eff > kBoxRows);
-                const uint32_t tx_cta = (uint32_t)(C::A_BYTES + (half_box ? kBoxBytes / 2 : (two_boxes ? 2 * kBoxBytes : kBoxBytes)));
+                const bool self_b = (CG == 2) && (s.flags & kTileSelfB) != 0;   // B = the A blocks themselves: nothing to load
+                const uint32_t tx_cta =
+                    (uint32_t)(C::A_BYTES + (self_b ? 0 : (half_box ? kBoxBytes / 2 : (two_boxes ? 2 * kBoxBytes : kBoxBytes))));
                 if (a.sync_lead > 0 && leader && s.win != synced_win) {
                     synced_win = s.win;
                     if (s.win >= a.sync_lead) wait_window(a.win_done, s.win - a.sync_lead, a.active_workers);
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                         if (two_boxes) ptx::tma_load_3d(sB(st) + kBoxBytes, &tmap, full_bar(st), kc, rowB + kBoxRows, pnl);
                     } else {
                         ptx::tma_load_3d_2sm(sA(st), &tmap, full_bar(st), kc, rowA, pnl);
-                        ptx::tma_load_3d_2sm(sB(st), half_box ? &tmap_half : &tmap, full_bar(st), kc, rowB, pnl);
+                        if (!self_b) ptx::tma_load_3d_2sm(sB(st), half_box ? &tmap_half : &tmap, full_bar(st), kc, rowB, pnl);
                         if (leader) ptx::mbar_arrive_expect_tx(full_bar(st), (2u * tx_cta) >> a.tx_shift);
                         else ptx::mbar_arrive_cluster(full_bar(st), 0);
                     }
@@ -529,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const __grid_constant
                 ptx::tc_fence_after();
                 if (issuer) {
                     const uint64_t adesc = make_smem_desc(sA(st));
-                    const uint64_t bdesc = make_smem_desc(sB(st));
+                    const uint64_t bdesc = make_smem_desc((CG == 2 && (s.flags & kTileSelfB) != 0) ? sA(st) : sB(st));
                     uint32_t acc = (s.first && kb == s.kb0) ? 0u : 1u;
 #pragma unroll
                     for (int k = 0; k < kKBytes / 32; ++k) {           // UMMA_K = 32 bytes of K
@@ -982,7 +985,8 @@ int gram_read_profile(GramPlan& plan, long long* out, int max_ctas) {
 //     r = 4t the block (col 4t, row 4t + 2) is taken out of row 4t + 2 and computed in row 4t as its mirror image
 //     (col 4t + 2, row 4t), written transposed: both rows become even and every needed block is covered exactly once.
 //     Two-row tiles come first, one-row tiles last (a worker's accumulators must fit the 512 TMEM columns).
-static void make_tiles(int n, int cg, bool exact, int bn, int row_lo, int row_hi, std::vector<TileDesc>& out, int* num_full) {
+static void make_tiles(int n, int cg, bool exact, int bn, int row_lo, int row_hi, bool self_b, std::vector<TileDesc>& out,
+                       int* num_full) {
     // [row_lo, row_hi): the rows of S to produce (the whole triangle, or the band an owner-computes context stores)
     out.clear();
     auto n_eff = [&](int row0, int want) { return std::min(want, ((n - row0) + 15) & ~15); };
@@ -1008,6 +1012,10 @@ static void make_tiles(int n, int cg, bool exact, int bn, int row_lo, int row_hi
                     t.rowB = row0[b];
                     t.n_eff = std::min(row0[b + 1], ((row_hi + 15) & ~15)) - row0[b];
                     t.acc_cols = bn;
+                    // diagonal tile whose 256 B rows are exactly the two A blocks of the pair: CTA r's half of B is its own
+                    // A block, so the MMA reads B through the A tile and the producer loads nothing for B (half the
+                    // L2 -> SM bytes of the tile)
+                    if (self_b && cg == 2 && t.rowB == t.rowA0 && t.n_eff == 2 * 128) t.flags |= kTileSelfB;
                     out.push_back(t);
                 }
     } else {
@@ -1080,7 +1088,7 @@ static void make_tiles(int n, int cg, bool exact, int bn, int row_lo, int row_hi
 static cudaError_t build_tiles(GramPlan& plan, int n, bool exact, int BN, int row_lo, int row_hi, cudaStream_t stream) {
     std::vector<TileDesc> tiles;
     int num_full = 0;
-    make_tiles(n, plan.cta_group, exact, BN, row_lo, row_hi, tiles, &num_full);
+    make_tiles(n, plan.cta_group, exact, BN, row_lo, row_hi, plan.self_b, tiles, &num_full);
     if (plan.d_tiles) cudaFree(plan.d_tiles);
     plan.d_tiles = nullptr;
     cudaError_t e = cudaMalloc(&plan.d_tiles, tiles.size() * sizeof(TileDesc));
@@ -1128,7 +1136,7 @@ static bool initial_split(const GramPlan& plan, int workers, int kbw, std::vecto
 int gram_debug_tiles(int n, int cta_group, int exact, int32_t* out, int max_tiles) {
     std::vector<TileDesc> tiles;
     int num_full = 0;
-    make_tiles(n, cta_group == 1 ? 1 : 2, exact != 0, exact ? kUmmaN : kUmmaNScaled, 0, n, tiles, &num_full);
+    make_tiles(n, cta_group == 1 ? 1 : 2, exact != 0, exact ? kUmmaN : kUmmaNScaled, 0, n, true, tiles, &num_full);
     const int cnt = std::min<int>((int)tiles.size(), max_tiles);
     if (out != nullptr && cnt > 0) memcpy(out, tiles.data(), (size_t)cnt * sizeof(TileDesc));
     return (int)tiles.size();
@@ -1137,7 +1145,7 @@ int gram_debug_tiles(int n, int cta_group, int exact, int32_t* out, int max_tile
 int gram_debug_band_tiles(int n, int cta_group, int row_lo, int row_hi, int32_t* out, int max_tiles) {
     std::vector<TileDesc> tiles;
     int num_full = 0;
-    make_tiles(n, cta_group == 1 ? 1 : 2, false, kUmmaN, row_lo, row_hi, tiles, &num_full);
+    make_tiles(n, cta_group == 1 ? 1 : 2, false, kUmmaN, row_lo, row_hi, true, tiles, &num_full);
     const int cnt = std::min<int>((int)tiles.size(), max_tiles);
     if (out != nullptr && cnt > 0) memcpy(out, tiles.data(), (size_t)cnt * sizeof(TileDesc));
     return (int)tiles.size();
@@ -1202,6 +1210,8 @@ cudaError_t gram_accumulate(GramPlan& plan, const void* d_x, int elem_bits, int 
         if (ad != nullptr) plan.adaptive = atoi(ad) != 0;
         const char* mx = getenv("VPCA_E2M1_MXF4");
         if (mx != nullptr) plan.e2m1_mxf4 = atoi(mx) != 0;
+        const char* sb = getenv("VPCA_SELF_B");
+        if (sb != nullptr) plan.self_b = atoi(sb) != 0;
         const char* r64 = getenv("VPCA_RED64");
         if (r64 != nullptr) plan.red64 = atoi(r64) != 0;
         const char* gain = getenv("VPCA_REBALANCE_GAIN");

@@ -39,6 +39,7 @@ struct GramPlan {
     int sync_lead = 0;        // VPCA_SYNC_LEAD: windows a worker may lead the slowest one by (0 = no pacing; measured
                               // on B200: pacing only slows every worker to the slowest one)
     int* d_win_done = nullptr;
+    bool self_b = true;       // VPCA_SELF_B=0: diagonal tiles load their B rows although they are the pair's own A blocks
     bool red64 = true;        // VPCA_RED64=0: one 32-bit red per cell in the flush instead of two cells per 64-bit red
     double gain = 0.5;        // VPCA_REBALANCE_GAIN: how far a launch moves the shares towards the measured speeds (measured on
                               // B200, 2504 x 1M int8: 0.5 settles at 1.61 ms within three launches, 0.7 and 1.0 hover at 1.70)
