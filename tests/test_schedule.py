@@ -178,3 +178,36 @@ def test_owner_computes_bands_tile_the_triangle_exactly_once(n, world):
     need = sum(1 for r16 in range((n + 15) // 16) for cb in range((n + 127) // 128) if cb * 128 <= min(r16 * 16 + 15, n - 1))
     assert len(blocks) == need
     assert max(work) <= 1.25 * (sum(work) / world) + 256 * 256 * 4     # equal shares of the triangle, up to tile granularity
+
+
+def test_repair_is_safe_for_any_split_hypothesis():
+    """Property test of repair_split (the last line of defence before a launch: overlapping TMEM accumulators would corrupt
+    S silently): for ANY monotone split of a window -- far outside the +-35 % the rebalancer proposes, including empty and
+    huge shares -- the repaired split either fits every worker into its TMEM budget and still partitions the window, or is
+    rejected."""
+    from hypothesis import given, settings, strategies as st
+
+    tiles_by = {(n, ex): native.debugTiles(n, 2, ex) for n, ex in [(2504, True), (2504, False), (1092, True), (1500, False)]}
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.sampled_from(sorted(tiles_by)), st.integers(8, 74), st.integers(4, 128),
+           st.lists(st.floats(0.0, 4.0, allow_nan=False), min_size=74, max_size=74))
+    def check(which, workers, kbw, raw):
+        tiles = tiles_by[which]
+        col_limit = 480 if not which[1] else 512
+        share = np.asarray(raw[:workers]) + 1e-9
+        cum = np.concatenate([[0.0], np.cumsum(share / share.sum())])
+        cum[-1] = 1.0
+        try:
+            cum2, pieces = native.debugRebalance(tiles, workers, kbw, cum, col_limit)
+        except native.VpcaError:
+            return                                            # rejected: the device keeps its previous split
+        seen = np.zeros((len(tiles), kbw), int)
+        for w, t, lo, hi, col, cols in pieces:
+            assert 0 <= lo < hi <= kbw and col + tiles[t, 6] <= cols <= col_limit
+            seen[t, lo:hi] += 1
+        assert (seen == 1).all()
+        assert len(pieces) == 0 or np.bincount(pieces[:, 0], minlength=workers).max() <= 4
+        assert (np.diff(cum2) >= 0).all() and cum2[0] == 0.0 and cum2[-1] == 1.0
+
+    check()
