@@ -4,8 +4,13 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / `
 legs may import this module.  The product path (``spark_examples_b200``) never does and fails
 loudly when its CUDA library is missing.
 
-PARITY UNPINNED: the reference ships no tests/golden vectors for this path and cannot run here
-(no JVM, no Spark, the Python twin is Python-2 + py4j).  This module holds
+PINNING: the reference ships no tests/golden vectors for this path and its Scala driver cannot run here (no JVM, no
+Spark).  Its Python twin (src/main/python/variants_pca.py) is Python-2 + py4j, but the three functions of it that restate
+the encode, similarity and centering steps (:19-121) are pure Python over RDD operations: tests/golden/
+make_reference_twin_golden.py EXECUTES them (mechanical 2-to-3 rewrites, an in-memory RDD stand-in) and
+tests/test_reference_twin.py holds this module to their output bit for bit.  The eigen step (`perform_pca`, :123-152)
+needs the JVM: for that step PARITY IS UNPINNED (upstream's RowMatrixSuite known-answer case is the only anchor).
+This module holds
 
 * ``np_*``  -- a pure-numpy restatement, written independently of the C one, and
 * ``c_*``   -- ctypes bindings to ``oracle/vpca_oracle.c`` (the timed CPU baseline),

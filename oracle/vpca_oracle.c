@@ -4,10 +4,14 @@
  * This file is the parity oracle for the B200 path.  It is NOT product code: only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  *
- * PARITY UNPINNED: the reference (googlegenomics/spark-examples) ships no tests, fixtures or
- * golden vectors for this path and cannot be executed here (no JVM/Spark in the image), so this
- * restatement is pinned only by (a) a line-by-line reading of the Scala below, (b) a second,
- * independent numpy restatement (oracle/oracle.py) and (c) hand-computed cases in tests/.
+ * PINNING: the reference (googlegenomics/spark-examples) ships no tests, fixtures or golden vectors
+ * for this path and its Scala driver cannot be executed here (no JVM/Spark in the image).  What
+ * pins this restatement: (a) for encode, similarity and centering, vectors produced by the
+ * reference's OWN Python twin of these steps (src/main/python/variants_pca.py:19-121, executed
+ * by tests/golden/make_reference_twin_golden.py; tests/test_reference_twin.py holds this file to
+ * them bit for bit); (b) a line-by-line reading of the Scala below; (c) a second, independent
+ * numpy restatement (oracle/oracle.py); (d) hand-computed cases in tests/.  The eigen step has no
+ * reference-produced vector (it needs the JVM): PARITY UNPINNED for that step.
  *
  * Every function cites the reference lines it follows; paths are relative to
  * /root/reference/src/main/scala/com/google/cloud/genomics/spark/examples/ .

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Regenerates tests/golden/*.npz from the oracle (numpy restatement).  PARITY UNPINNED: the reference
+"""Regenerates tests/golden/*.npz from the oracle (numpy restatement).  These are REGRESSION vectors (reference-produced
+vectors live in reference_twin.json, see make_reference_twin_golden.py).  For the eigen step PARITY IS UNPINNED: the reference
 has no fixtures of its own and cannot be run here (no JVM/Spark), so these vectors pin the ORACLE (and,
 through the GPU tests, the CUDA path) against regressions; the hand-computed cases in tests/test_oracle.py
 and the README.md:109-119 magnitude property are the independent anchors.
